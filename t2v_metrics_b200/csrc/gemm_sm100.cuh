@@ -1,0 +1,426 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] . W[N,K]^T )
+//
+//   * operands are both K-major (activations [M,K] row-major, nn.Linear weights [N,K] row-major), fetched
+//     tile-by-tile from HBM/L2 by TMA into a 128B-swizzled shared-memory ring;
+//   * one elected thread issues tcgen05.mma (UMMA 128xBLOCK_Nx16, or 256xBLOCK_Nx16 across a CTA pair with
+//     cta_group::2); accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the
+//     main loop of tile i+1;
+//   * four epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue (bias / activation /
+//     gated-GELU / residual add / online log-sum-exp for the lm_head) before the only write to HBM.
+//
+// Replaces the cuBLAS bf16 GEMMs that the reference reaches through nn.Linear
+// (transformers/models/t5/modeling_t5.py:109-111,178-181; transformers/models/clip/modeling_clip.py:296-299,344-345).
+#pragma once
+#include "ptx.cuh"
+#include <cuda.h>
+
+namespace vqa {
+
+enum GemmEpilogue : int {
+    EPI_STORE = 0,       // C = [residual +] bf16(acc [+ bias])
+    EPI_QUICK_GELU = 1,  // C = quick_gelu(bf16(acc + bias))                 (CLIP MLP fc1)
+    EPI_GELU_ERF = 2,    // C = gelu_erf(bf16(acc + bias))                   (mlp2x_gelu projector)
+    EPI_GATED_GELU = 3,  // C = gelu_new(bf16(acc_gate)) * bf16(acc_up)      (T5 DenseGatedActDense wi_0/wi_1)
+    EPI_LSE = 4,         // no C; per-row (max, sum exp) partials + label-logit gather (lm_head + CE)
+    EPI_RELU = 5,        // C = relu(bf16(acc + bias))
+};
+
+struct GemmParams {
+    int M, N, K;              // N = number of OUTPUT columns of the logical GEMM (for GATED: 2 * out columns)
+    __nv_bfloat16* C;         // [M, ldc]
+    int ldc;
+    const __nv_bfloat16* bias;      // [N] or nullptr
+    const __nv_bfloat16* residual;  // [M, ldr] or nullptr
+    int ldr;
+    int gate_up_offset;       // GATED: row offset of the "up" weight block inside W (= d_ff)
+    // EPI_LSE
+    float* lse_max;           // [M, num_n_tiles]
+    float* lse_sum;           // [M, num_n_tiles]
+    const int* labels;        // [M]
+    float* label_logit;       // [M]
+    // scheduling
+    int num_m_tiles, num_n_tiles, group_m;
+};
+
+template <int BLOCK_N, int CG>
+struct GemmConfig {
+    static constexpr int BLOCK_M = 128;           // rows per CTA (UMMA M = 128 * CG)
+    static constexpr int BLOCK_K = 64;            // 64 bf16 = 128 B = one swizzle atom
+    static constexpr int UMMA_K = 16;
+    static constexpr int B_ROWS_PER_CTA = BLOCK_N / CG;
+    static constexpr int B_HALF_ROWS = BLOCK_N / 2;
+    static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_STAGE_BYTES = B_ROWS_PER_CTA * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM_BUDGET = 200 * 1024;
+    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int NUM_THREADS = 192;       // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+    static constexpr int TMEM_COLS = 2 * BLOCK_N; // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(BLOCK_N >= 32 && BLOCK_N <= 256 && (BLOCK_N & (BLOCK_N - 1)) == 0, "BLOCK_N must be 32..256, pow2");
+    static_assert(B_HALF_ROWS % 8 == 0, "B half tile must hold whole 8-row swizzle atoms");
+    static_assert(STAGES >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float act_gelu_new(float x) {
+    // 0.5 * x * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- transformers/activations.py NewGELUActivation
+    const float k = 0.7978845608028654f;
+    float inner = k * (x + 0.044715f * x * x * x);
+    return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+template <int BLOCK_N, int CG, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmParams p) {
+    using Cfg = GemmConfig<BLOCK_N, CG>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int BLOCK_M = Cfg::BLOCK_M;
+    constexpr int BLOCK_K = Cfg::BLOCK_K;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                      // [STAGES][128 x 64 bf16]
+    uint8_t* smem_b = smem + STAGES * Cfg::A_STAGE_BYTES;        // [STAGES][B_ROWS_PER_CTA x 64 bf16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;      // [2]
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], CG);   // CG==2: one arrive per CTA's producer, on the leader's barrier
+            mbar_init(&empty_bar[s], 1);   // one tcgen05.commit
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);        // one tcgen05.commit
+            mbar_init(&tmem_empty_bar[s], CG * 4);  // one arrive per epilogue warp (of both CTAs for CG==2)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<CG>(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tcgen05_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_workers = gridDim.x / CG;
+    const int worker = blockIdx.x / CG;
+    const int tiles_per_group = p.group_m * p.num_n_tiles;
+
+    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+        int g = t / tiles_per_group;
+        int r = t - g * tiles_per_group;
+        int m_first = g * p.group_m;
+        int gm = min(p.group_m, p.num_m_tiles - m_first);
+        m_blk = m_first + r % gm;
+        n_blk = r / gm;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = worker; t < num_tiles; t += num_workers) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                const int m_row = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                    const int k0 = kb * BLOCK_K;
+                    if constexpr (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m_row);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
+                                                                : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
+                            tma_load_2d(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0,
+                                        n_row);
+                        }
+                    } else {
+                        const int h = (int)cta_rank;
+                        int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
+                                                            : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
+                        tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m_row);
+                        tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0, n_row);
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        else           mbar_arrive_cluster(&full_bar[stage], 0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only, one thread) =====================
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = worker; t < num_tiles; t += num_workers, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::A_STAGE_BYTES));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / Cfg::UMMA_K; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+                        umma_f16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit<CG>(&empty_bar[stage]);                     // frees the smem slot when MMAs retire
+                    if (kb == num_k_blocks - 1) umma_commit<CG>(&tmem_full_bar[as]);  // accumulator ready
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
+        const uint32_t q = warp & 3u;                 // TMEM lane quadrant this warp may access
+        const int row_in_tile = q * 32 + lane;
+        int it = 0;
+        for (int t = worker; t < num_tiles; t += num_workers, ++it) {
+            int m_blk, n_blk;
+            tile_coords(t, m_blk, n_blk);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1u;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tcgen05_fence_after();
+            const int m = (m_blk * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
+            const bool row_ok = m < p.M;
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+
+            if constexpr (EPI == EPI_GATED_GELU) {
+                constexpr int OUT_COLS = BLOCK_N / 2;
+                const int n_out0 = n_blk * OUT_COLS;
+#pragma unroll 1
+                for (int c = 0; c < OUT_COLS / 32; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, g);
+                    tmem_ld_32x32b_x32(taddr + OUT_COLS + c * 32, u);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        __nv_bfloat16* crow = p.C + (size_t)m * p.ldc + n_out0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float g0 = bf16_round(__uint_as_float(g[j * 8 + 2 * e]));
+                                float g1 = bf16_round(__uint_as_float(g[j * 8 + 2 * e + 1]));
+                                float u0 = bf16_round(__uint_as_float(u[j * 8 + 2 * e]));
+                                float u1 = bf16_round(__uint_as_float(u[j * 8 + 2 * e + 1]));
+                                float h0 = bf16_round(act_gelu_new(g0)) * u0;
+                                float h1 = bf16_round(act_gelu_new(g1)) * u1;
+                                w[e] = pack_bf16x2(h0, h1);
+                            }
+                            if (n_out0 + c * 32 + j * 8 < p.N / 2)
+                                *reinterpret_cast<uint4*>(crow + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_LSE) {
+                const int n0 = n_blk * BLOCK_N;
+                const int label = row_ok ? p.labels[m] : -1;
+                float run_max = -INFINITY, run_sum = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    float x[32];
+                    float cmax = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c * 32 + j;
+                        float val = bf16_round(__uint_as_float(v[j]));   // reference logits are bf16
+                        x[j] = (n < p.N) ? val : -INFINITY;
+                        cmax = fmaxf(cmax, x[j]);
+                        if (n == label) p.label_logit[m] = val;
+                    }
+                    if (cmax > -INFINITY) {
+                        const float new_max = fmaxf(run_max, cmax);
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) s += __expf(x[j] - new_max);
+                        run_sum = run_sum * __expf(run_max - new_max) + s;
+                        run_max = new_max;
+                    }
+                }
+                if (row_ok) {
+                    p.lse_max[(size_t)m * p.num_n_tiles + n_blk] = run_max;
+                    p.lse_sum[(size_t)m * p.num_n_tiles + n_blk] = run_sum;
+                }
+            } else {
+                const int n0 = n_blk * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int nc = n0 + c * 32;
+                    if (row_ok && nc < p.N) {
+                        __nv_bfloat16* crow = p.C + (size_t)m * p.ldc + nc;
+                        const __nv_bfloat16* rrow = p.residual ? p.residual + (size_t)m * p.ldr + nc : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (nc + j * 8 < p.N) {
+                                float f[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                                if (p.bias) {
+                                    uint4 bq = __ldg(reinterpret_cast<const uint4*>(p.bias + nc + j * 8));
+                                    float2 b0 = unpack_bf16x2(bq.x), b1 = unpack_bf16x2(bq.y);
+                                    float2 b2 = unpack_bf16x2(bq.z), b3 = unpack_bf16x2(bq.w);
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+                                    f[4] += b2.x; f[5] += b2.y; f[6] += b3.x; f[7] += b3.y;
+                                }
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    float y = bf16_round(f[e]);   // the Linear's bf16 output in the reference
+                                    if constexpr (EPI == EPI_QUICK_GELU) y = act_quick_gelu(y);
+                                    if constexpr (EPI == EPI_GELU_ERF) y = act_gelu_erf(y);
+                                    if constexpr (EPI == EPI_RELU) y = fmaxf(y, 0.f);
+                                    f[e] = y;
+                                }
+                                if (rrow) {
+                                    uint4 rq = *reinterpret_cast<const uint4*>(rrow + j * 8);
+                                    float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y);
+                                    float2 r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+                                    f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                                    f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+                                }
+                                uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                                *reinterpret_cast<uint4*>(crow + j * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            // release this accumulator stage back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
+                else                   mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            }
+        }
+    }
+
+    // ---- teardown
+    tcgen05_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] (row stride ld elements) -> 2-D map, box {64 cols, box_rows}, 128B swizzle.
+inline bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                              uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct GemmLaunch {
+    const __nv_bfloat16* A; int lda;   // [M, K]
+    const __nv_bfloat16* W; int ldw;   // [w_rows, K]
+    int w_rows;                        // rows of W visible to TMA (N, or 2*d_ff for GATED)
+    GemmParams p;
+};
+
+template <int BLOCK_N, int CG, int EPI>
+inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t stream) {
+    using Cfg = GemmConfig<BLOCK_N, CG>;
+    auto kernel = gemm_bf16_sm100_kernel<BLOCK_N, CG, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    CUtensorMap ta, tb;
+    if (!make_tmap_bf16_2d(&ta, g.A, (uint64_t)g.p.M, (uint64_t)g.p.K, (uint64_t)g.lda, Cfg::BLOCK_M))
+        return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&tb, g.W, (uint64_t)g.w_rows, (uint64_t)g.p.K, (uint64_t)g.ldw, Cfg::B_HALF_ROWS))
+        return cudaErrorInvalidValue;
+    GemmParams p = g.p;
+    const int rows_per_tile = Cfg::BLOCK_M * CG;
+    p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
+    p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+    p.group_m = max(1, 2048 / rows_per_tile);
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    int workers = num_sms / CG;
+    if (workers > num_tiles) workers = num_tiles;
+    if (workers < 1) workers = 1;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CG);
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CG;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
+}
+
+}  // namespace vqa

@@ -1,0 +1,682 @@
+// libvqa_b200.so -- C ABI + host-side orchestration of the CLIP-FlanT5 VQAScore forward on one B200.
+// The forward is a fixed sequence of kernel launches on the caller's stream; no torch, no cuBLAS.
+#include "../../include/vqa_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ptx.cuh"
+#include "gemm_sm100.cuh"
+#include "elementwise.cuh"
+#include "attention.cuh"
+
+using namespace vqa;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ handle
+struct BoundTensor {
+    const void* data = nullptr;
+    int64_t shape[4] = {0, 0, 0, 0};
+    int ndim = 0;
+    int dtype = 0;
+};
+
+struct VitLayerW {
+    const bf16 *ln1_w, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+struct T5EncLayerW {
+    const bf16 *ln0, *qkv, *o, *ln1, *wi, *wo;
+};
+struct T5DecLayerW {
+    const bf16 *ln0, *qkv, *o, *ln1, *cq, *ckv, *co, *ln2, *wi, *wo;
+};
+
+struct vqa_handle {
+    vqa_clipt5_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    std::unordered_map<std::string, BoundTensor> tensors;
+    bool finalized = false;
+    int64_t launches = 0;
+    int kpad = 0;  // padded K of the patch-embedding GEMM
+    // resolved weights
+    const bf16 *patch_w = nullptr, *cls = nullptr, *pos = nullptr, *pre_ln_w = nullptr, *pre_ln_b = nullptr;
+    std::vector<VitLayerW> vit;
+    const bf16 *proj0_w = nullptr, *proj0_b = nullptr, *proj2_w = nullptr, *proj2_b = nullptr;
+    const bf16 *shared = nullptr, *enc_rel = nullptr, *dec_rel = nullptr, *enc_final_ln = nullptr,
+               *dec_final_ln = nullptr, *lm_head = nullptr;
+    std::vector<T5EncLayerW> enc;
+    std::vector<T5DecLayerW> dec;
+    // relative-position bucket LUTs (device), index rel + max_dist, rel clamped to [-max_dist, max_dist]
+    int* lut_bidir = nullptr;
+    int* lut_unidir = nullptr;
+};
+
+static thread_local std::string g_global_err;
+
+static int fail(vqa_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_global_err = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(h, VQA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ debug GEMM
+// One thread per output element; used only when VQA_GEMM_SIMT=1 (bring-up aid to separate pipeline bugs from
+// tensor-core bugs). Same epilogue semantics as the tcgen05 kernel.
+__global__ void gemm_simt_debug_kernel(const bf16* A, int lda, const bf16* W, int ldw, GemmParams p, int epi) {
+    const int n_out = (epi == EPI_GATED_GELU) ? p.N / 2 : p.N;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)p.M * n_out) return;
+    const int m = (int)(idx / n_out), n = (int)(idx % n_out);
+    const bf16* a = A + (size_t)m * lda;
+    auto dot = [&](const bf16* w) {
+        float acc = 0.f;
+        for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+        return acc;
+    };
+    if (epi == EPI_GATED_GELU) {
+        float g = bf16_round(dot(W + (size_t)n * ldw));
+        float u = bf16_round(dot(W + (size_t)(p.gate_up_offset + n) * ldw));
+        p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(bf16_round(act_gelu_new(g)) * u);
+        return;
+    }
+    float acc = dot(W + (size_t)n * ldw);
+    if (p.bias) acc += __bfloat162float(p.bias[n]);
+    float y = bf16_round(acc);
+    if (epi == EPI_QUICK_GELU) y = act_quick_gelu(y);
+    if (epi == EPI_GELU_ERF) y = act_gelu_erf(y);
+    if (epi == EPI_RELU) y = fmaxf(y, 0.f);
+    if (p.residual) y += __bfloat162float(p.residual[(size_t)m * p.ldr + n]);
+    p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(y);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+static bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && v[0]) ? atoi(v) : dflt;
+}
+
+template <int EPI>
+static cudaError_t gemm_dispatch_variant(const GemmLaunch& g, int variant, int num_sms, cudaStream_t st) {
+    switch (variant) {
+        case 2562: return launch_gemm_t<256, 2, EPI>(g, num_sms, st);
+        case 2561: return launch_gemm_t<256, 1, EPI>(g, num_sms, st);
+        case 1282: return launch_gemm_t<128, 2, EPI>(g, num_sms, st);
+        case 1281: return launch_gemm_t<128, 1, EPI>(g, num_sms, st);
+        case 641:  return launch_gemm_t<64, 1, EPI>(g, num_sms, st);
+        case 321:  return launch_gemm_t<32, 1, EPI>(g, num_sms, st);
+        default:   return cudaErrorInvalidValue;
+    }
+}
+
+static int pick_variant(int M, int N, int epi) {
+    static const int forced = env_int("VQA_GEMM_VARIANT", 0);
+    if (forced) return forced;
+    const int n_logical = N;
+    if (M <= 128) {
+        // skinny (decoder rows): weight streaming; favour many CTAs
+        if (n_logical <= 4096) return 321;
+        if (n_logical <= 12288) return 641;
+        return 1281;
+    }
+    if (M <= 256 * 16 && n_logical <= 1024) return 1281;
+    (void)epi;
+    return 2562;
+}
+
+// Launch C = epi(A W^T). Returns cudaError_t. `launch_counter` is incremented per kernel.
+static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M, int N,
+                            int K, const bf16* bias, const bf16* residual, int ldr, int epi, int gate_up_offset,
+                            int variant, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+    GemmLaunch g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = w_rows;
+    memset(&g.p, 0, sizeof(g.p));
+    g.p.M = M; g.p.N = N; g.p.K = K; g.p.C = C; g.p.ldc = ldc; g.p.bias = bias; g.p.residual = residual;
+    g.p.ldr = ldr; g.p.gate_up_offset = gate_up_offset;
+    if (launch_counter) ++*launch_counter;
+    static const bool simt = env_flag("VQA_GEMM_SIMT");
+    if (simt) {
+        const long total = (long)M * ((epi == EPI_GATED_GELU) ? N / 2 : N);
+        gemm_simt_debug_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, lda, W, ldw, g.p, epi);
+        return cudaGetLastError();
+    }
+    if (variant == 0) variant = pick_variant(M, N, epi);
+    switch (epi) {
+        case EPI_STORE:      return gemm_dispatch_variant<EPI_STORE>(g, variant, num_sms, st);
+        case EPI_QUICK_GELU: return gemm_dispatch_variant<EPI_QUICK_GELU>(g, variant, num_sms, st);
+        case EPI_GELU_ERF:   return gemm_dispatch_variant<EPI_GELU_ERF>(g, variant, num_sms, st);
+        case EPI_GATED_GELU: return gemm_dispatch_variant<EPI_GATED_GELU>(g, variant, num_sms, st);
+        case EPI_RELU:       return gemm_dispatch_variant<EPI_RELU>(g, variant, num_sms, st);
+        default:             return cudaErrorInvalidValue;
+    }
+}
+
+constexpr int LMHEAD_BN = 128;
+static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
+                              float* lse_max, float* lse_sum, float* label_logit, int num_sms, cudaStream_t st,
+                              int64_t* launch_counter) {
+    GemmLaunch g;
+    g.A = H; g.lda = ldh; g.W = W; g.ldw = ldw; g.w_rows = N;
+    memset(&g.p, 0, sizeof(g.p));
+    g.p.M = M; g.p.N = N; g.p.K = K;
+    g.p.lse_max = lse_max; g.p.lse_sum = lse_sum; g.p.labels = labels; g.p.label_logit = label_logit;
+    if (launch_counter) ++*launch_counter;
+    return launch_gemm_t<LMHEAD_BN, 1, EPI_LSE>(g, num_sms, st);
+}
+
+static cudaError_t run_rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, int D, float eps, cudaStream_t st,
+                               int64_t* lc) {
+    if (lc) ++*lc;
+    const int nvec = D / 8;
+    if (nvec <= 256)       t5_rmsnorm_kernel<1><<<rows, 256, 0, st>>>(x, w, y, D, eps);
+    else if (nvec <= 512)  t5_rmsnorm_kernel<2><<<rows, 256, 0, st>>>(x, w, y, D, eps);
+    else if (nvec <= 1024) t5_rmsnorm_kernel<4><<<rows, 256, 0, st>>>(x, w, y, D, eps);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+static cudaError_t run_layernorm(const bf16* x, const bf16* g, const bf16* b, bf16* y, int rows, int D, float eps,
+                                 cudaStream_t st, int64_t* lc) {
+    if (lc) ++*lc;
+    const int blocks = (rows + 7) / 8;
+    if (D == 1024)      layernorm_kernel<1024><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 256)  layernorm_kernel<256><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 512)  layernorm_kernel<512><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 768)  layernorm_kernel<768><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 1280) layernorm_kernel<1280><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+static cudaError_t run_flash(const bf16* q, const bf16* k, const bf16* v, int ldqkv, bf16* o, int ldo, int B, int S,
+                             int H, const int* seq_lens, const float* bias_table, float scale, int round_scores,
+                             cudaStream_t st, int64_t* lc) {
+    if (lc) ++*lc;
+    FlashParams p;
+    p.q = q; p.k = k; p.v = v; p.o = o;
+    p.ldq = p.ldk = p.ldv = ldqkv; p.ldo = ldo;
+    p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H; p.scale = scale; p.round_scores = round_scores;
+    const size_t smem = flash_smem_bytes(S, bias_table != nullptr);
+    static size_t max_set = 0;
+    if (smem > max_set) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set = smem;
+    }
+    dim3 grid((S + FA_BQ - 1) / FA_BQ, H, B);
+    flash_attn_d64_kernel<<<grid, 128, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI: lifecycle
+extern "C" const char* vqa_version(void) {
+    return "vqa_b200 abi=1 arch=sm_100a kernels=tcgen05-gemm,flash-d64,t5-norm,lmhead-lse";
+}
+
+// Host mirror of T5Attention._relative_position_bucket (modeling_t5.py:189-234), fp32 like torch.
+static int host_rel_bucket(int rel, bool bidirectional, int num_buckets, int max_distance) {
+    int bucket = 0;
+    if (bidirectional) {
+        num_buckets /= 2;
+        if (rel > 0) bucket += num_buckets;
+        rel = abs(rel);
+    } else {
+        rel = -std::min(rel, 0);
+    }
+    const int max_exact = num_buckets / 2;
+    if (rel < max_exact) return bucket + rel;
+    float v = logf((float)rel / (float)max_exact) / (float)log((double)max_distance / (double)max_exact) *
+              (float)(num_buckets - max_exact);
+    int large = max_exact + (int)v;
+    large = std::min(large, num_buckets - 1);
+    return bucket + large;
+}
+
+extern "C" int vqa_create_clipt5(const vqa_clipt5_config* cfg, int device, vqa_handle** out) {
+    if (!cfg || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null argument");
+    if (cfg->vit_hidden % cfg->vit_heads || cfg->vit_hidden / cfg->vit_heads != 64)
+        return fail(nullptr, VQA_ERR_UNSUPPORTED, "vision head_dim must be 64");
+    if (cfg->image_size % cfg->patch_size) return fail(nullptr, VQA_ERR_INVALID_ARG, "image_size % patch_size != 0");
+    if (cfg->d_model % 8 || cfg->d_ff % 64 || cfg->vit_hidden % 256)
+        return fail(nullptr, VQA_ERR_UNSUPPORTED, "d_model % 8, d_ff % 64, vit_hidden % 256 must be 0");
+    vqa_handle* h = new vqa_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_global_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        delete h;
+        return VQA_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess || prop.major != 10) {
+        g_global_err = "vqa_b200 requires an sm_100 (B200) device";
+        delete h;
+        return VQA_ERR_UNSUPPORTED;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    const int kreal = 3 * cfg->patch_size * cfg->patch_size;
+    h->kpad = (kreal + 63) / 64 * 64;
+    // bucket LUTs
+    const int md = cfg->rel_max_distance;
+    std::vector<int> lb(2 * md + 1), lu(2 * md + 1);
+    for (int r = -md; r <= md; ++r) {
+        lb[r + md] = host_rel_bucket(r, true, cfg->rel_buckets, md);
+        lu[r + md] = host_rel_bucket(r, false, cfg->rel_buckets, md);
+    }
+    if (cudaMalloc(&h->lut_bidir, lb.size() * 4) != cudaSuccess || cudaMalloc(&h->lut_unidir, lu.size() * 4) != cudaSuccess ||
+        cudaMemcpy(h->lut_bidir, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->lut_unidir, lu.data(), lu.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_global_err = "LUT allocation failed";
+        delete h;
+        return VQA_ERR_CUDA;
+    }
+    *out = h;
+    return VQA_OK;
+}
+
+extern "C" int vqa_bind_weights(vqa_handle* h, const vqa_tensor* tensors, int32_t n) {
+    if (!h || (!tensors && n > 0)) return fail(h, VQA_ERR_INVALID_ARG, "null argument");
+    for (int i = 0; i < n; ++i) {
+        const vqa_tensor& t = tensors[i];
+        if (!t.name || !t.data) return fail(h, VQA_ERR_INVALID_ARG, "tensor with null name/data");
+        if (t.dtype != VQA_DTYPE_BF16) return fail(h, VQA_ERR_UNSUPPORTED, std::string(t.name) + ": weights must be bf16");
+        if ((reinterpret_cast<uintptr_t>(t.data) & 15) != 0)
+            return fail(h, VQA_ERR_INVALID_ARG, std::string(t.name) + ": pointer not 16-byte aligned");
+        BoundTensor b;
+        b.data = t.data; b.ndim = t.ndim; b.dtype = t.dtype;
+        for (int d = 0; d < 4; ++d) b.shape[d] = (d < t.ndim) ? t.shape[d] : 1;
+        h->tensors[t.name] = b;
+    }
+    h->finalized = false;
+    return VQA_OK;
+}
+
+static const bf16* need(vqa_handle* h, const std::string& name, int64_t d0, int64_t d1, bool& ok) {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end()) {
+        if (ok) h->err = "missing weight: " + name;
+        ok = false;
+        return nullptr;
+    }
+    const BoundTensor& b = it->second;
+    int64_t numel = 1;
+    for (int d = 0; d < b.ndim; ++d) numel *= b.shape[d];
+    if (numel != d0 * d1) {
+        if (ok) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "weight %s: expected %lld x %lld elements, got %lld", name.c_str(), (long long)d0,
+                     (long long)d1, (long long)numel);
+            h->err = buf;
+        }
+        ok = false;
+        return nullptr;
+    }
+    return reinterpret_cast<const bf16*>(b.data);
+}
+
+extern "C" int vqa_finalize_weights(vqa_handle* h) {
+    if (!h) return VQA_ERR_INVALID_ARG;
+    const vqa_clipt5_config& c = h->cfg;
+    bool ok = true;
+    const int P = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
+    const int Dv = c.vit_hidden, Dm = c.d_model, inner = c.n_heads * 64;
+    h->patch_w = need(h, "vit.patch_embed.weight", Dv, h->kpad, ok);
+    h->cls = need(h, "vit.class_embedding", Dv, 1, ok);
+    h->pos = need(h, "vit.position_embedding", P + 1, Dv, ok);
+    h->pre_ln_w = need(h, "vit.pre_ln.weight", Dv, 1, ok);
+    h->pre_ln_b = need(h, "vit.pre_ln.bias", Dv, 1, ok);
+    h->vit.resize(c.vit_layers_run);
+    for (int i = 0; i < c.vit_layers_run; ++i) {
+        const std::string p = "vit.layers." + std::to_string(i) + ".";
+        VitLayerW& L = h->vit[i];
+        L.ln1_w = need(h, p + "ln1.weight", Dv, 1, ok); L.ln1_b = need(h, p + "ln1.bias", Dv, 1, ok);
+        L.qkv_w = need(h, p + "qkv.weight", 3 * Dv, Dv, ok); L.qkv_b = need(h, p + "qkv.bias", 3 * Dv, 1, ok);
+        L.out_w = need(h, p + "out.weight", Dv, Dv, ok); L.out_b = need(h, p + "out.bias", Dv, 1, ok);
+        L.ln2_w = need(h, p + "ln2.weight", Dv, 1, ok); L.ln2_b = need(h, p + "ln2.bias", Dv, 1, ok);
+        L.fc1_w = need(h, p + "fc1.weight", c.vit_mlp, Dv, ok); L.fc1_b = need(h, p + "fc1.bias", c.vit_mlp, 1, ok);
+        L.fc2_w = need(h, p + "fc2.weight", Dv, c.vit_mlp, ok); L.fc2_b = need(h, p + "fc2.bias", Dv, 1, ok);
+    }
+    h->proj0_w = need(h, "proj.0.weight", Dm, Dv, ok); h->proj0_b = need(h, "proj.0.bias", Dm, 1, ok);
+    h->proj2_w = need(h, "proj.2.weight", Dm, Dm, ok); h->proj2_b = need(h, "proj.2.bias", Dm, 1, ok);
+    h->shared = need(h, "t5.shared", c.vocab, Dm, ok);
+    h->enc_rel = need(h, "t5.enc.rel_bias", c.rel_buckets, c.n_heads, ok);
+    h->dec_rel = need(h, "t5.dec.rel_bias", c.rel_buckets, c.n_heads, ok);
+    h->enc_final_ln = need(h, "t5.enc.final_ln", Dm, 1, ok);
+    h->dec_final_ln = need(h, "t5.dec.final_ln", Dm, 1, ok);
+    h->lm_head = need(h, "t5.lm_head", c.vocab, Dm, ok);
+    h->enc.resize(c.enc_layers);
+    for (int i = 0; i < c.enc_layers; ++i) {
+        const std::string p = "t5.enc." + std::to_string(i) + ".";
+        T5EncLayerW& L = h->enc[i];
+        L.ln0 = need(h, p + "ln0", Dm, 1, ok); L.qkv = need(h, p + "qkv", 3 * inner, Dm, ok);
+        L.o = need(h, p + "o", Dm, inner, ok); L.ln1 = need(h, p + "ln1", Dm, 1, ok);
+        L.wi = need(h, p + "wi", 2 * c.d_ff, Dm, ok); L.wo = need(h, p + "wo", Dm, c.d_ff, ok);
+    }
+    h->dec.resize(c.dec_layers);
+    for (int i = 0; i < c.dec_layers; ++i) {
+        const std::string p = "t5.dec." + std::to_string(i) + ".";
+        T5DecLayerW& L = h->dec[i];
+        L.ln0 = need(h, p + "ln0", Dm, 1, ok); L.qkv = need(h, p + "qkv", 3 * inner, Dm, ok);
+        L.o = need(h, p + "o", Dm, inner, ok); L.ln1 = need(h, p + "ln1", Dm, 1, ok);
+        L.cq = need(h, p + "cq", inner, Dm, ok); L.ckv = need(h, p + "ckv", 2 * inner, Dm, ok);
+        L.co = need(h, p + "co", Dm, inner, ok); L.ln2 = need(h, p + "ln2", Dm, 1, ok);
+        L.wi = need(h, p + "wi", 2 * c.d_ff, Dm, ok); L.wo = need(h, p + "wo", Dm, c.d_ff, ok);
+    }
+    if (!ok) return VQA_ERR_MISSING_WEIGHT;
+    h->finalized = true;
+    return VQA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace plan
+struct Plan {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~size_t(255);
+        return o;
+    }
+};
+struct ClipT5Workspace {
+    // vision
+    size_t patches, patch_out, hv, vn, vqkv, vattn, vmlp, proj1, proj2;
+    // t5
+    size_t x, xn, qkv, attn, ff, bias_table, seq_lens, ckv;
+    size_t y, yn, dqkv, dattn, dq, dff;
+    size_t lse_max, lse_sum, label_logit;
+    size_t total;
+};
+static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L, int T) {
+    const vqa_clipt5_config& c = h->cfg;
+    const int P = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
+    const size_t Mv = (size_t)NI * (P + 1), Mp = (size_t)NI * P;
+    const int S = L - 1 + P;
+    const size_t M = (size_t)B * S, Md = (size_t)B * T;
+    const size_t inner = (size_t)c.n_heads * 64;
+    Plan pl;
+    ClipT5Workspace w;
+    w.patches = pl.take(Mp * h->kpad * 2);
+    w.patch_out = pl.take(Mp * c.vit_hidden * 2);
+    w.hv = pl.take(Mv * c.vit_hidden * 2);
+    w.vn = pl.take(Mv * c.vit_hidden * 2);
+    w.vqkv = pl.take(Mv * 3 * c.vit_hidden * 2);
+    w.vattn = pl.take(Mv * c.vit_hidden * 2);
+    w.vmlp = pl.take(Mv * c.vit_mlp * 2);
+    w.proj1 = pl.take(Mv * c.d_model * 2);
+    w.proj2 = pl.take(Mv * c.d_model * 2);
+    w.x = pl.take(M * c.d_model * 2);
+    w.xn = pl.take(M * c.d_model * 2);
+    w.qkv = pl.take(M * 3 * inner * 2);
+    w.attn = pl.take(M * inner * 2);
+    w.ff = pl.take(M * c.d_ff * 2);
+    w.bias_table = pl.take((size_t)c.n_heads * (2 * S - 1) * 4);
+    w.seq_lens = pl.take((size_t)B * 4);
+    w.ckv = pl.take(M * 2 * inner * 2);
+    w.y = pl.take(Md * c.d_model * 2);
+    w.yn = pl.take(Md * c.d_model * 2);
+    w.dqkv = pl.take(Md * 3 * inner * 2);
+    w.dattn = pl.take(Md * inner * 2);
+    w.dq = pl.take(Md * inner * 2);
+    w.dff = pl.take(Md * c.d_ff * 2);
+    const size_t ntiles = (c.vocab + LMHEAD_BN - 1) / LMHEAD_BN;
+    w.lse_max = pl.take(Md * ntiles * 4);
+    w.lse_sum = pl.take(Md * ntiles * 4);
+    w.label_logit = pl.take(Md * 4);
+    w.total = pl.off;
+    return w;
+}
+
+extern "C" size_t vqa_clipt5_workspace_bytes(vqa_handle* h, int32_t batch, int32_t n_images, int32_t text_len,
+                                             int32_t label_len) {
+    if (!h || batch <= 0 || n_images <= 0 || text_len <= 0 || label_len <= 0) return 0;
+    return plan_workspace(h, batch, n_images, text_len, label_len).total;
+}
+
+__global__ void identity_index_kernel(int* idx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel_dtype, int32_t n_images,
+                                const int32_t* image_index, const int32_t* input_ids, const int32_t* text_lens,
+                                const int32_t* labels, int32_t B, int32_t L, int32_t T, float* out_scores,
+                                float* out_logprobs, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return VQA_ERR_INVALID_ARG;
+    if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
+    if (!pixels || !input_ids || !text_lens || !labels || !out_scores || !workspace)
+        return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
+    if (B <= 0 || L <= 0 || T <= 0 || n_images <= 0) return fail(h, VQA_ERR_INVALID_ARG, "non-positive size");
+    if (T > 8) return fail(h, VQA_ERR_UNSUPPORTED, "label_len > 8 not supported by the decoder kernels");
+    if (!image_index && n_images != B) return fail(h, VQA_ERR_INVALID_ARG, "image_index == NULL requires n_images == batch");
+    if (pixel_dtype != VQA_DTYPE_F32 && pixel_dtype != VQA_DTYPE_BF16)
+        return fail(h, VQA_ERR_INVALID_ARG, "pixel_dtype must be F32 or BF16");
+    const vqa_clipt5_config& c = h->cfg;
+    const ClipT5Workspace w = plan_workspace(h, B, n_images, L, T);
+    if (workspace_bytes < w.total) return fail(h, VQA_ERR_WORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VQA_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    auto P_ = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
+    h->launches = 0;
+    int64_t* lc = &h->launches;
+    const int nsm = h->num_sms;
+    const int rnd = c.emulate_bf16_rounding;
+
+    const int grid_w = c.image_size / c.patch_size;
+    const int P = grid_w * grid_w;
+    const int Dv = c.vit_hidden, Dm = c.d_model, H = c.n_heads, inner = H * 64, Hv = c.vit_heads;
+    const int Mp = n_images * P, Mv = n_images * (P + 1);
+    const int S = L - 1 + P;
+    const int M = B * S, Md = B * T;
+
+    // ---------------- vision tower (CLIP ViT, layers 0 .. vit_layers_run-1; hidden_states[-2]) ----------------
+    ++*lc;
+    if (pixel_dtype == VQA_DTYPE_F32)
+        patchify_kernel<float><<<Mp, 128, 0, st>>>(reinterpret_cast<const float*>(pixels), P_(w.patches), n_images,
+                                                  c.image_size, c.image_size, c.patch_size, h->kpad);
+    else
+        patchify_kernel<bf16><<<Mp, 128, 0, st>>>(reinterpret_cast<const bf16*>(pixels), P_(w.patches), n_images,
+                                                 c.image_size, c.image_size, c.patch_size, h->kpad);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, run_gemm(P_(w.patches), h->kpad, h->patch_w, h->kpad, Dv, P_(w.patch_out), Dv, Mp, Dv, h->kpad, nullptr,
+                         nullptr, 0, EPI_STORE, 0, 0, nsm, st, lc));
+    ++*lc;
+    if (Dv == 1024)
+        clip_embed_ln_kernel<1024><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w, h->pre_ln_b,
+                                                                 P_(w.hv), n_images, P, c.vit_ln_eps);
+    else if (Dv == 256)
+        clip_embed_ln_kernel<256><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w, h->pre_ln_b,
+                                                                P_(w.hv), n_images, P, c.vit_ln_eps);
+    else
+        return fail(h, VQA_ERR_UNSUPPORTED, "vit_hidden must be 1024 or 256");
+    CUDA_TRY(h, cudaGetLastError());
+    for (int l = 0; l < c.vit_layers_run; ++l) {
+        const VitLayerW& Lw = h->vit[l];
+        CUDA_TRY(h, run_layernorm(P_(w.hv), Lw.ln1_w, Lw.ln1_b, P_(w.vn), Mv, Dv, c.vit_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.vn), Dv, Lw.qkv_w, Dv, 3 * Dv, P_(w.vqkv), 3 * Dv, Mv, 3 * Dv, Dv, Lw.qkv_b, nullptr, 0,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_flash(P_(w.vqkv), P_(w.vqkv) + Dv, P_(w.vqkv) + 2 * Dv, 3 * Dv, P_(w.vattn), Dv, n_images, P + 1,
+                              Hv, nullptr, nullptr, 0.125f, 0, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, P_(w.hv), Dv, Mv, Dv, Dv, Lw.out_b, P_(w.hv), Dv,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_layernorm(P_(w.hv), Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv, Dv, c.vit_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.vn), Dv, Lw.fc1_w, Dv, c.vit_mlp, P_(w.vmlp), c.vit_mlp, Mv, c.vit_mlp, Dv, Lw.fc1_b,
+                             nullptr, 0, EPI_QUICK_GELU, 0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.vmlp), c.vit_mlp, Lw.fc2_w, c.vit_mlp, Dv, P_(w.hv), Dv, Mv, Dv, c.vit_mlp, Lw.fc2_b,
+                             P_(w.hv), Dv, EPI_STORE, 0, 0, nsm, st, lc));
+    }
+    // mlp2x_gelu projector (Linear -> GELU(erf) -> Linear), applied to every row; the CLS rows are simply not spliced
+    CUDA_TRY(h, run_gemm(P_(w.hv), Dv, h->proj0_w, Dv, Dm, P_(w.proj1), Dm, Mv, Dm, Dv, h->proj0_b, nullptr, 0,
+                         EPI_GELU_ERF, 0, 0, nsm, st, lc));
+    CUDA_TRY(h, run_gemm(P_(w.proj1), Dm, h->proj2_w, Dm, Dm, P_(w.proj2), Dm, Mv, Dm, Dm, h->proj2_b, nullptr, 0,
+                         EPI_STORE, 0, 0, nsm, st, lc));
+
+    // ---------------- multimodal splice -> T5 encoder input ----------------
+    int* seq_lens = reinterpret_cast<int*>(ws + w.seq_lens);
+    ++*lc;
+    splice_embed_kernel<<<B * S, 128, 0, st>>>(input_ids, text_lens, image_index, h->shared, P_(w.proj2), Dm, 1,
+                                                       P + 1, P_(w.x), seq_lens, B, L, S, P, Dm, c.image_token_id);
+    CUDA_TRY(h, cudaGetLastError());
+
+    // ---------------- T5 encoder ----------------
+    float* bias_table = reinterpret_cast<float*>(ws + w.bias_table);
+    ++*lc;
+    bias_table_from_lut_kernel<<<(H * (2 * S - 1) + 255) / 256, 256, 0, st>>>(h->enc_rel, h->lut_bidir,
+                                                                              c.rel_max_distance, bias_table, H, S);
+    CUDA_TRY(h, cudaGetLastError());
+    for (int l = 0; l < c.enc_layers; ++l) {
+        const T5EncLayerW& Lw = h->enc[l];
+        CUDA_TRY(h, run_rmsnorm(P_(w.x), Lw.ln0, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, nullptr,
+                             0, EPI_STORE, 0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
+                              seq_lens, bias_table, 1.0f, rnd, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE,
+                             0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_rmsnorm(P_(w.x), Lw.ln1, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, nullptr, 0,
+                             EPI_GATED_GELU, c.d_ff, 0, nsm, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+    }
+    CUDA_TRY(h, run_rmsnorm(P_(w.x), h->enc_final_ln, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));  // encoder output in xn
+
+    // ---------------- T5 decoder (T target rows per pair) ----------------
+    ++*lc;
+    decoder_embed_kernel<<<Md, 128, 0, st>>>(labels, h->shared, P_(w.y), T, Dm, c.decoder_start_id, c.pad_token_id);
+    CUDA_TRY(h, cudaGetLastError());
+    for (int l = 0; l < c.dec_layers; ++l) {
+        const T5DecLayerW& Lw = h->dec[l];
+        // self-attention
+        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln0, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.dqkv), 3 * inner, Md, 3 * inner, Dm, nullptr, nullptr,
+                             0, EPI_STORE, 0, 0, nsm, st, lc));
+        ++*lc;
+        t5_decoder_self_attn_kernel<<<(B * H * T + 3) / 4, 128, 0, st>>>(P_(w.dqkv), P_(w.dattn), h->dec_rel,
+                                                                         h->lut_unidir, c.rel_max_distance, B, T, H, rnd);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, run_gemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+        // cross-attention: K/V projection of the encoder output (the reference recomputes it per layer,
+        // modeling_t5.py:297-299)
+        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln1, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE,
+                             0, 0, nsm, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr,
+                             0, EPI_STORE, 0, 0, nsm, st, lc));
+        ++*lc;
+        t5_cross_attn_kernel<8><<<B * H, 128, 0, st>>>(P_(w.dq), P_(w.ckv), P_(w.dattn), seq_lens, 2 * inner, B, T, S, H,
+                                                      rnd);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, run_gemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+        // gated FFN
+        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln2, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.dff), c.d_ff, Md, 2 * c.d_ff, Dm, nullptr, nullptr, 0,
+                             EPI_GATED_GELU, c.d_ff, 0, nsm, st, lc));
+        CUDA_TRY(h, run_gemm(P_(w.dff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.y), Dm, Md, Dm, c.d_ff, nullptr, P_(w.y), Dm,
+                             EPI_STORE, 0, 0, nsm, st, lc));
+    }
+    CUDA_TRY(h, run_rmsnorm(P_(w.y), h->dec_final_ln, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
+
+    // ---------------- lm_head x hidden, fused log-sum-exp + label gather; logits never reach HBM ----------------
+    float* lse_max = reinterpret_cast<float*>(ws + w.lse_max);
+    float* lse_sum = reinterpret_cast<float*>(ws + w.lse_sum);
+    float* label_logit = reinterpret_cast<float*>(ws + w.label_logit);
+    const int ntiles = (c.vocab + LMHEAD_BN - 1) / LMHEAD_BN;
+    CUDA_TRY(h, run_lmhead(P_(w.yn), Dm, h->lm_head, Dm, Md, c.vocab, Dm, labels, lse_max, lse_sum, label_logit, nsm, st, lc));
+    ++*lc;
+    lse_finalize_kernel<<<(B + 3) / 4, 128, 0, st>>>(lse_max, lse_sum, label_logit, labels, out_scores, out_logprobs, B, T,
+                                                    ntiles);
+    CUDA_TRY(h, cudaGetLastError());
+    return VQA_OK;
+}
+
+extern "C" int64_t vqa_last_launch_count(vqa_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* vqa_last_error(vqa_handle* h) { return h ? h->err.c_str() : g_global_err.c_str(); }
+extern "C" void vqa_destroy(vqa_handle* h) {
+    if (!h) return;
+    if (h->lut_bidir) cudaFree(h->lut_bidir);
+    if (h->lut_unidir) cudaFree(h->lut_unidir);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel-level ABI
+static int device_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C,
+                                int32_t ldc, int32_t M, int32_t N, int32_t K, const void* bias, const void* residual,
+                                int32_t ldr, int32_t epilogue, int32_t gate_up_offset, int32_t variant, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad gemm argument");
+    if (lda % 8 || ldw % 8 || ldc % 8 || N % 8 || K % 8) return fail(nullptr, VQA_ERR_INVALID_ARG, "gemm: ld/N/K must be multiples of 8");
+    cudaError_t e = run_gemm((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, (const bf16*)bias,
+                             (const bf16*)residual, ldr, epilogue, gate_up_offset, variant, device_sms(),
+                             (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+extern "C" int vqa_op_lmhead_logprob(const void* Hs, int32_t ldh, const void* W, int32_t ldw, int32_t M, int32_t N,
+                                     int32_t K, const int32_t* labels, float* logprob, float* scratch, void* stream) {
+    if (!Hs || !W || !labels || !logprob || !scratch) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    const int ntiles = (N + LMHEAD_BN - 1) / LMHEAD_BN;
+    float* lse_max = scratch;
+    float* lse_sum = scratch + (size_t)M * ntiles;
+    float* label_logit = scratch + 2 * (size_t)M * ntiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = run_lmhead((const bf16*)Hs, ldh, (const bf16*)W, ldw, M, N, K, labels, lse_max, lse_sum, label_logit,
+                               device_sms(), st, nullptr);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("lmhead launch: ") + cudaGetErrorString(e));
+    // T = 1: score buffer unused -> reuse finalize with logprobs output only
+    lse_finalize_kernel<<<(M + 3) / 4, 128, 0, st>>>(lse_max, lse_sum, label_logit, labels, lse_max /*scratch scores*/,
+                                                    logprob, M, 1, ntiles);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("lse finalize: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
+                                    const float* bias_table, float scale, int32_t round_scores, void* stream) {
+    if (!qkv || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    const bf16* q = (const bf16*)qkv;
+    cudaError_t e = run_flash(q, q + H * 64, q + 2 * H * 64, 3 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table,
+                              scale, round_scores, (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+extern "C" int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,
+                           void* stream) {
+    if (!x || !gamma || !y) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    cudaError_t e = beta ? run_layernorm((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, rows, D, eps,
+                                         (cudaStream_t)stream, nullptr)
+                         : run_rmsnorm((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, D, eps, (cudaStream_t)stream,
+                                       nullptr);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("norm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}

@@ -1,0 +1,243 @@
+"""Tensor-level entry to the B200 engine: PyTorch tensors in, PyTorch tensors out, everything in between is
+libvqa_b200.so (hand-written sm_100a kernels) reached through ctypes. PyTorch only supplies device memory and the
+current CUDA stream.
+
+`ClipT5Engine.score_tensors` is what `bench.py` and the plugin (`models/clip_t5_model.py`) call; it replaces the
+`self.model(input_ids, images=..., labels=...)` + CrossEntropy loop of the reference's v3.0 CLIPT5Model.forward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .config import ClipT5Config
+
+IMAGE_TOKEN_INDEX = -200  # t2v_metrics/constants.py:7
+IGNORE_INDEX = -100       # t2v_metrics/constants.py:6
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check(rc: int, handle=None, what: str = ""):
+    if rc != 0:
+        raise RuntimeError(f"libvqa_b200 {what} failed (status {rc}): {_lib.last_error(handle)}")
+
+
+def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device) -> Dict[str, torch.Tensor]:
+    """HF-named CLIP-FlanT5 weights (CLIPVisionModel under `vision_tower.`, `mm_projector.*`,
+    T5ForConditionalGeneration names) -> the engine's fused bf16 layout:
+      * q/k/v projections concatenated row-wise ([3*inner, d]) so one GEMM produces the packed QKV buffer;
+      * wi_0 / wi_1 concatenated ([2*d_ff, d]) for the gated-GELU epilogue; cross-attention k/v concatenated;
+      * the Conv2d patch embedding flattened to [D, 3*ps*ps] and zero-padded along K to a multiple of 64.
+    Mirrors `model.to(device, dtype=torch.bfloat16)` (mm_utils.py:228)."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def put(name, t):
+        out[name] = t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+    v = "vision_tower.vision_model."
+    D = cfg.vit_hidden
+    k_real = 3 * cfg.patch_size * cfg.patch_size
+    kpad = (k_real + 63) // 64 * 64
+    pw = sd[v + "embeddings.patch_embedding.weight"].reshape(D, k_real)
+    pw_pad = torch.zeros(D, kpad, dtype=pw.dtype, device=pw.device)
+    pw_pad[:, :k_real] = pw
+    put("vit.patch_embed.weight", pw_pad)
+    put("vit.class_embedding", sd[v + "embeddings.class_embedding"])
+    put("vit.position_embedding", sd[v + "embeddings.position_embedding.weight"])
+    put("vit.pre_ln.weight", sd[v + "pre_layrnorm.weight"])
+    put("vit.pre_ln.bias", sd[v + "pre_layrnorm.bias"])
+    for l in range(cfg.vit_layers - 1):
+        p, q = v + f"encoder.layers.{l}.", f"vit.layers.{l}."
+        put(q + "ln1.weight", sd[p + "layer_norm1.weight"]); put(q + "ln1.bias", sd[p + "layer_norm1.bias"])
+        put(q + "ln2.weight", sd[p + "layer_norm2.weight"]); put(q + "ln2.bias", sd[p + "layer_norm2.bias"])
+        put(q + "qkv.weight", torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0))
+        put(q + "qkv.bias", torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0))
+        put(q + "out.weight", sd[p + "self_attn.out_proj.weight"]); put(q + "out.bias", sd[p + "self_attn.out_proj.bias"])
+        put(q + "fc1.weight", sd[p + "mlp.fc1.weight"]); put(q + "fc1.bias", sd[p + "mlp.fc1.bias"])
+        put(q + "fc2.weight", sd[p + "mlp.fc2.weight"]); put(q + "fc2.bias", sd[p + "mlp.fc2.bias"])
+    for i in (0, 2):
+        put(f"proj.{i}.weight", sd[f"mm_projector.{i}.weight"]); put(f"proj.{i}.bias", sd[f"mm_projector.{i}.bias"])
+    put("t5.shared", sd["shared.weight"])
+    put("t5.lm_head", sd["lm_head.weight"])  # untied from `shared` for FlanT5
+    put("t5.enc.rel_bias", sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"])
+    put("t5.dec.rel_bias", sd["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"])
+    put("t5.enc.final_ln", sd["encoder.final_layer_norm.weight"])
+    put("t5.dec.final_ln", sd["decoder.final_layer_norm.weight"])
+    for l in range(cfg.enc_layers):
+        p, q = f"encoder.block.{l}.layer.", f"t5.enc.{l}."
+        a = p + "0.SelfAttention."
+        put(q + "ln0", sd[p + "0.layer_norm.weight"])
+        put(q + "qkv", torch.cat([sd[a + f"{n}.weight"] for n in "qkv"], dim=0))
+        put(q + "o", sd[a + "o.weight"])
+        put(q + "ln1", sd[p + "1.layer_norm.weight"])
+        put(q + "wi", torch.cat([sd[p + "1.DenseReluDense.wi_0.weight"], sd[p + "1.DenseReluDense.wi_1.weight"]], dim=0))
+        put(q + "wo", sd[p + "1.DenseReluDense.wo.weight"])
+    for l in range(cfg.dec_layers):
+        p, q = f"decoder.block.{l}.layer.", f"t5.dec.{l}."
+        a, c = p + "0.SelfAttention.", p + "1.EncDecAttention."
+        put(q + "ln0", sd[p + "0.layer_norm.weight"])
+        put(q + "qkv", torch.cat([sd[a + f"{n}.weight"] for n in "qkv"], dim=0))
+        put(q + "o", sd[a + "o.weight"])
+        put(q + "ln1", sd[p + "1.layer_norm.weight"])
+        put(q + "cq", sd[c + "q.weight"])
+        put(q + "ckv", torch.cat([sd[c + "k.weight"], sd[c + "v.weight"]], dim=0))
+        put(q + "co", sd[c + "o.weight"])
+        put(q + "ln2", sd[p + "2.layer_norm.weight"])
+        put(q + "wi", torch.cat([sd[p + "2.DenseReluDense.wi_0.weight"], sd[p + "2.DenseReluDense.wi_1.weight"]], dim=0))
+        put(q + "wo", sd[p + "2.DenseReluDense.wo.weight"])
+    return out
+
+
+class ClipT5Engine:
+    """One engine = one model replica on one GPU (one process per GPU)."""
+
+    def __init__(self, cfg: ClipT5Config, device="cuda:0", emulate_bf16_rounding: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ClipT5Engine needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c = _lib.VqaClipT5Config(
+            image_size=cfg.image_size, patch_size=cfg.patch_size, vit_hidden=cfg.vit_hidden, vit_heads=cfg.vit_heads,
+            vit_mlp=cfg.vit_mlp, vit_layers_run=cfg.vit_layers - 1, vit_ln_eps=cfg.vit_ln_eps, d_model=cfg.d_model,
+            n_heads=cfg.n_heads, d_ff=cfg.d_ff, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, vocab=cfg.vocab,
+            rel_buckets=cfg.rel_buckets, rel_max_distance=cfg.rel_max_distance, t5_ln_eps=cfg.t5_ln_eps,
+            image_token_id=IMAGE_TOKEN_INDEX, pad_token_id=cfg.pad_token_id, decoder_start_id=cfg.decoder_start_id,
+            emulate_bf16_rounding=1 if emulate_bf16_rounding else 0)
+        if cfg.d_kv != 64:
+            raise ValueError("the engine's attention kernels are specialised for d_kv == 64")
+        self._h = C.c_void_p()
+        with torch.cuda.device(idx):
+            _check(self.lib.vqa_create_clipt5(C.byref(c), idx, C.byref(self._h)), None, "vqa_create_clipt5")
+        self._weights: Dict[str, torch.Tensor] = {}
+        self._workspace: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.vqa_destroy(h)
+            self._h = C.c_void_p()
+
+    # ---- weights
+    def bind_engine_tensors(self, tensors: Dict[str, torch.Tensor]):
+        arr = (_lib.VqaTensor * len(tensors))()
+        keep = []
+        for i, (name, t) in enumerate(tensors.items()):
+            assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous(), name
+            nb = name.encode()
+            keep.append(nb)
+            arr[i].name = nb
+            arr[i].data = t.data_ptr()
+            for d in range(4):
+                arr[i].shape[d] = t.shape[d] if d < t.dim() else 1
+            arr[i].ndim = t.dim()
+            arr[i].dtype = _lib.VQA_DTYPE_BF16
+        _check(self.lib.vqa_bind_weights(self._h, arr, len(tensors)), self._h, "vqa_bind_weights")
+        self._weights.update(tensors)  # keep the borrowed memory alive
+        _check(self.lib.vqa_finalize_weights(self._h), self._h, "vqa_finalize_weights")
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        self.bind_engine_tensors(convert_state_dict(sd, self.cfg, self.device))
+
+    # ---- forward
+    def workspace_bytes(self, batch: int, n_images: int, text_len: int, label_len: int) -> int:
+        return int(self.lib.vqa_clipt5_workspace_bytes(self._h, batch, n_images, text_len, label_len))
+
+    def score_tensors(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, text_lens: torch.Tensor,
+                      labels: torch.Tensor, image_index: Optional[torch.Tensor] = None,
+                      out: Optional[torch.Tensor] = None, return_logprobs: bool = False):
+        """pixel_values [NI,3,H,W] fp32/bf16 cuda; input_ids [B,L] int32 (-200 = image slot); text_lens [B] int32;
+        labels [B,T] int32 (-100 = ignore); image_index [B] int32 or None. Returns scores [B] fp32 on the device
+        (enqueued on the current stream; no synchronisation)."""
+        dev = self.device
+        assert pixel_values.is_cuda and pixel_values.dim() == 4 and pixel_values.is_contiguous()
+        assert pixel_values.dtype in (torch.float32, torch.bfloat16)
+        for t in (input_ids, text_lens, labels):
+            assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()
+        B, L = input_ids.shape
+        T = labels.shape[1]
+        NI = pixel_values.shape[0]
+        if image_index is not None:
+            assert image_index.is_cuda and image_index.dtype == torch.int32 and image_index.shape == (B,)
+        need = self.workspace_bytes(B, NI, L, T)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, device=dev)
+        logp = torch.empty(B, T, dtype=torch.float32, device=dev) if return_logprobs else None
+        pdt = _lib.VQA_DTYPE_F32 if pixel_values.dtype == torch.float32 else _lib.VQA_DTYPE_BF16
+        rc = self.lib.vqa_clipt5_score(self._h, _ptr(pixel_values), pdt, NI, _ptr(image_index), _ptr(input_ids),
+                                       _ptr(text_lens), _ptr(labels), B, L, T, _ptr(out), _ptr(logp),
+                                       _ptr(self._workspace), self._workspace.numel(), _stream_ptr(dev))
+        _check(rc, self._h, "vqa_clipt5_score")
+        return (out, logp) if return_logprobs else out
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.vqa_last_launch_count(self._h))
+
+
+# ------------------------------------------------------------------------------------------------ single-kernel ops
+class ops:
+    """Kernel-level calls through the same C ABI (used by tests and bench.py's roofline probe)."""
+
+    EPI = dict(store=0, quick_gelu=1, gelu=2, gated_gelu=3, relu=5)
+
+    @staticmethod
+    def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, epilogue="store", variant=0, out=None,
+             gate_up_offset=0):
+        lib = _lib.load()
+        M, K = a.shape
+        n_rows = w.shape[0]
+        epi = ops.EPI[epilogue]
+        n_out = n_rows // 2 if epi == 3 else n_rows
+        if out is None:
+            out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
+        rc = lib.vqa_op_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), n_rows, _ptr(out), out.stride(0), M, n_rows,
+                                  K, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, epi,
+                                  gate_up_offset if epi == 3 else 0, variant, _stream_ptr(a.device))
+        _check(rc, None, "vqa_op_gemm_bf16")
+        return out
+
+    @staticmethod
+    def lmhead_logprob(h: torch.Tensor, w: torch.Tensor, labels: torch.Tensor):
+        lib = _lib.load()
+        M, K = h.shape
+        N = w.shape[0]
+        ntiles = (N + 127) // 128
+        scratch = torch.empty(2 * M * ntiles + M, dtype=torch.float32, device=h.device)
+        out = torch.empty(M, dtype=torch.float32, device=h.device)
+        rc = lib.vqa_op_lmhead_logprob(_ptr(h), h.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(labels), _ptr(out),
+                                       _ptr(scratch), _stream_ptr(h.device))
+        _check(rc, None, "vqa_op_lmhead_logprob")
+        return out
+
+    @staticmethod
+    def attention(qkv: torch.Tensor, B: int, S: int, H: int, seq_lens=None, bias_table=None, scale=1.0,
+                  round_scores=False):
+        lib = _lib.load()
+        out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device=qkv.device)
+        rc = lib.vqa_op_attention_d64(_ptr(qkv), _ptr(out), B, S, H, _ptr(seq_lens), _ptr(bias_table), float(scale),
+                                      1 if round_scores else 0, _stream_ptr(qkv.device))
+        _check(rc, None, "vqa_op_attention_d64")
+        return out
+
+    @staticmethod
+    def norm(x: torch.Tensor, gamma: torch.Tensor, beta=None, eps=1e-6):
+        lib = _lib.load()
+        y = torch.empty_like(x)
+        rc = lib.vqa_op_norm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.shape[0], x.shape[1], float(eps),
+                             _stream_ptr(x.device))
+        _check(rc, None, "vqa_op_norm")
+        return y
