@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvqa_b200.so"
 
 ABI_SYMBOLS = [
     "vqa_version", "vqa_create_clipt5", "vqa_bind_weights", "vqa_finalize_weights", "vqa_clipt5_workspace_bytes",
-    "vqa_clipt5_score", "vqa_last_launch_count", "vqa_last_error", "vqa_destroy", "vqa_op_gemm_bf16",
+    "vqa_clipt5_score", "vqa_set_profile", "vqa_profile_read", "vqa_last_launch_count", "vqa_last_error", "vqa_destroy", "vqa_op_gemm_bf16",
     "vqa_op_lmhead_logprob", "vqa_op_attention_d64", "vqa_op_norm",
 ]
 
@@ -66,6 +66,10 @@ def load() -> C.CDLL:
     lib.vqa_clipt5_workspace_bytes.restype = C.c_size_t
     lib.vqa_clipt5_score.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     lib.vqa_clipt5_score.restype = C.c_int
+    lib.vqa_set_profile.argtypes = [vp, i32]
+    lib.vqa_set_profile.restype = C.c_int
+    lib.vqa_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.vqa_profile_read.restype = C.c_int
     lib.vqa_last_launch_count.argtypes = [vp]
     lib.vqa_last_launch_count.restype = i64
     lib.vqa_last_error.argtypes = [vp]

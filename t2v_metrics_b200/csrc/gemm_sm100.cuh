@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(192, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmParams p) {
     using Cfg = GemmConfig<BLOCK_N, CG>;
+    static_assert(EPI != EPI_GATED_GELU || BLOCK_N >= 64, "gated epilogue pairs two >=32-column half tiles");
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BLOCK_M = Cfg::BLOCK_M;
     constexpr int BLOCK_K = Cfg::BLOCK_K;

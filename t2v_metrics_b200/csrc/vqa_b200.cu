@@ -56,6 +56,35 @@ struct vqa_handle {
     // relative-position bucket LUTs (device), index rel + max_dist, rel clamped to [-max_dist, max_dist]
     int* lut_bidir = nullptr;
     int* lut_unidir = nullptr;
+    // optional per-category device timing (vqa_set_profile): CUDA events around every launch of the forward
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct ProfRec { int cat; double flops; int ev0, ev1; };
+    std::vector<ProfRec> prof;
+    size_t ev_used = 0;
+};
+
+enum ProfCat { CAT_GEMM = 0, CAT_ATTENTION = 1, CAT_NORM = 2, CAT_OTHER = 3, CAT_COUNT = 4 };
+
+// Records an event pair around the launches issued in its lifetime (only in profile mode).
+struct ProfScope {
+    vqa_handle* h; cudaStream_t st; int idx = -1;
+    ProfScope(vqa_handle* h_, int cat, double flops, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->profile) return;
+        while (h->ev_pool.size() < h->ev_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            h->ev_pool.push_back(e);
+        }
+        vqa_handle::ProfRec r{cat, flops, (int)h->ev_used, (int)h->ev_used + 1};
+        h->ev_used += 2;
+        cudaEventRecord(h->ev_pool[r.ev0], st);
+        idx = (int)h->prof.size();
+        h->prof.push_back(r);
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(h->ev_pool[h->prof[idx].ev1], st);
+    }
 };
 
 static thread_local std::string g_global_err;
@@ -64,6 +93,11 @@ static int fail(vqa_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_global_err = msg;
     return code;
 }
+#define PROF(h, cat, flops, st, expr)              \
+    do {                                           \
+        ProfScope _ps(h, cat, flops, st);          \
+        CUDA_TRY(h, expr);                         \
+    } while (0)
 #define CUDA_TRY(h, expr)                                                                          \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \
@@ -119,7 +153,9 @@ static cudaError_t gemm_dispatch_variant(const GemmLaunch& g, int variant, int n
         case 1282: return launch_gemm_t<128, 2, EPI>(g, num_sms, st);
         case 1281: return launch_gemm_t<128, 1, EPI>(g, num_sms, st);
         case 641:  return launch_gemm_t<64, 1, EPI>(g, num_sms, st);
-        case 321:  return launch_gemm_t<32, 1, EPI>(g, num_sms, st);
+        case 321:
+            if constexpr (EPI == EPI_GATED_GELU) return cudaErrorInvalidValue;
+            else return launch_gemm_t<32, 1, EPI>(g, num_sms, st);
         default:   return cudaErrorInvalidValue;
     }
 }
@@ -127,15 +163,15 @@ static cudaError_t gemm_dispatch_variant(const GemmLaunch& g, int variant, int n
 static int pick_variant(int M, int N, int epi) {
     static const int forced = env_int("VQA_GEMM_VARIANT", 0);
     if (forced) return forced;
-    const int n_logical = N;
     if (M <= 128) {
-        // skinny (decoder rows): weight streaming; favour many CTAs
-        if (n_logical <= 4096) return 321;
-        if (n_logical <= 12288) return 641;
+        // skinny (decoder rows): pure weight streaming; favour many CTAs. The gated epilogue pairs two half tiles of
+        // BLOCK_N/2 >= 32 columns, so it needs BLOCK_N >= 64.
+        if (epi == EPI_GATED_GELU) return N <= 16384 ? 641 : 1281;
+        if (N <= 4096) return 321;
+        if (N <= 12288) return 641;
         return 1281;
     }
-    if (M <= 256 * 16 && n_logical <= 1024) return 1281;
-    (void)epi;
+    if (M <= 256 * 16 && N <= 1024) return 1281;
     return 2562;
 }
 
@@ -485,126 +521,187 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     const int S = L - 1 + P;
     const int M = B * S, Md = B * T;
 
+    h->prof.clear();
+    h->ev_used = 0;
+#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+    auto cuda_ok = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(h, VQA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return 0;
+    };
+    auto gemm = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M_, int N_, int K_,
+                    const bf16* bias, const bf16* res, int ldr, int epi, int gate_off) -> int {
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st);
+        return cuda_ok(run_gemm(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, bias, res, ldr, epi, gate_off, 0, nsm, st, lc), "gemm");
+    };
+    auto rms = [&](const bf16* x, const bf16* wgt, bf16* y, int rows) -> int {
+        ProfScope ps(h, CAT_NORM, 0, st);
+        return cuda_ok(run_rmsnorm(x, wgt, y, rows, Dm, c.t5_ln_eps, st, lc), "rmsnorm");
+    };
+    auto lnorm = [&](const bf16* x, const bf16* g, const bf16* b_, bf16* y, int rows) -> int {
+        ProfScope ps(h, CAT_NORM, 0, st);
+        return cuda_ok(run_layernorm(x, g, b_, y, rows, Dv, c.vit_ln_eps, st, lc), "layernorm");
+    };
+
     // ---------------- vision tower (CLIP ViT, layers 0 .. vit_layers_run-1; hidden_states[-2]) ----------------
-    ++*lc;
-    if (pixel_dtype == VQA_DTYPE_F32)
-        patchify_kernel<float><<<Mp, 128, 0, st>>>(reinterpret_cast<const float*>(pixels), P_(w.patches), n_images,
-                                                  c.image_size, c.image_size, c.patch_size, h->kpad);
-    else
-        patchify_kernel<bf16><<<Mp, 128, 0, st>>>(reinterpret_cast<const bf16*>(pixels), P_(w.patches), n_images,
-                                                 c.image_size, c.image_size, c.patch_size, h->kpad);
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, run_gemm(P_(w.patches), h->kpad, h->patch_w, h->kpad, Dv, P_(w.patch_out), Dv, Mp, Dv, h->kpad, nullptr,
-                         nullptr, 0, EPI_STORE, 0, 0, nsm, st, lc));
-    ++*lc;
-    if (Dv == 1024)
-        clip_embed_ln_kernel<1024><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w, h->pre_ln_b,
-                                                                 P_(w.hv), n_images, P, c.vit_ln_eps);
-    else if (Dv == 256)
-        clip_embed_ln_kernel<256><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w, h->pre_ln_b,
-                                                                P_(w.hv), n_images, P, c.vit_ln_eps);
-    else
-        return fail(h, VQA_ERR_UNSUPPORTED, "vit_hidden must be 1024 or 256");
-    CUDA_TRY(h, cudaGetLastError());
+    {
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        ++*lc;
+        if (pixel_dtype == VQA_DTYPE_F32)
+            patchify_kernel<float><<<Mp, 128, 0, st>>>(reinterpret_cast<const float*>(pixels), P_(w.patches), n_images,
+                                                      c.image_size, c.image_size, c.patch_size, h->kpad);
+        else
+            patchify_kernel<bf16><<<Mp, 128, 0, st>>>(reinterpret_cast<const bf16*>(pixels), P_(w.patches), n_images,
+                                                     c.image_size, c.image_size, c.patch_size, h->kpad);
+        TRY(cuda_ok(cudaSuccess, "patchify"));
+    }
+    TRY(gemm(P_(w.patches), h->kpad, h->patch_w, h->kpad, Dv, P_(w.patch_out), Dv, Mp, Dv, h->kpad, nullptr, nullptr, 0,
+             EPI_STORE, 0));
+    {
+        ProfScope ps(h, CAT_NORM, 0, st);
+        ++*lc;
+        if (Dv == 1024)
+            clip_embed_ln_kernel<1024><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w,
+                                                                     h->pre_ln_b, P_(w.hv), n_images, P, c.vit_ln_eps);
+        else if (Dv == 256)
+            clip_embed_ln_kernel<256><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w,
+                                                                    h->pre_ln_b, P_(w.hv), n_images, P, c.vit_ln_eps);
+        else
+            return fail(h, VQA_ERR_UNSUPPORTED, "vit_hidden must be 1024 or 256");
+        TRY(cuda_ok(cudaSuccess, "clip_embed_ln"));
+    }
     for (int l = 0; l < c.vit_layers_run; ++l) {
         const VitLayerW& Lw = h->vit[l];
-        CUDA_TRY(h, run_layernorm(P_(w.hv), Lw.ln1_w, Lw.ln1_b, P_(w.vn), Mv, Dv, c.vit_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.vn), Dv, Lw.qkv_w, Dv, 3 * Dv, P_(w.vqkv), 3 * Dv, Mv, 3 * Dv, Dv, Lw.qkv_b, nullptr, 0,
-                             EPI_STORE, 0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_flash(P_(w.vqkv), P_(w.vqkv) + Dv, P_(w.vqkv) + 2 * Dv, 3 * Dv, P_(w.vattn), Dv, n_images, P + 1,
-                              Hv, nullptr, nullptr, 0.125f, 0, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, P_(w.hv), Dv, Mv, Dv, Dv, Lw.out_b, P_(w.hv), Dv,
-                             EPI_STORE, 0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_layernorm(P_(w.hv), Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv, Dv, c.vit_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.vn), Dv, Lw.fc1_w, Dv, c.vit_mlp, P_(w.vmlp), c.vit_mlp, Mv, c.vit_mlp, Dv, Lw.fc1_b,
-                             nullptr, 0, EPI_QUICK_GELU, 0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.vmlp), c.vit_mlp, Lw.fc2_w, c.vit_mlp, Dv, P_(w.hv), Dv, Mv, Dv, c.vit_mlp, Lw.fc2_b,
-                             P_(w.hv), Dv, EPI_STORE, 0, 0, nsm, st, lc));
+        TRY(lnorm(P_(w.hv), Lw.ln1_w, Lw.ln1_b, P_(w.vn), Mv));
+        TRY(gemm(P_(w.vn), Dv, Lw.qkv_w, Dv, 3 * Dv, P_(w.vqkv), 3 * Dv, Mv, 3 * Dv, Dv, Lw.qkv_b, nullptr, 0, EPI_STORE, 0));
+        {
+            ProfScope ps(h, CAT_ATTENTION, 4.0 * n_images * (double)Hv * (P + 1) * (P + 1) * 64, st);
+            TRY(cuda_ok(run_flash(P_(w.vqkv), P_(w.vqkv) + Dv, P_(w.vqkv) + 2 * Dv, 3 * Dv, P_(w.vattn), Dv, n_images, P + 1,
+                                  Hv, nullptr, nullptr, 0.125f, 0, st, lc), "vit attention"));
+        }
+        TRY(gemm(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, P_(w.hv), Dv, Mv, Dv, Dv, Lw.out_b, P_(w.hv), Dv, EPI_STORE, 0));
+        TRY(lnorm(P_(w.hv), Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv));
+        TRY(gemm(P_(w.vn), Dv, Lw.fc1_w, Dv, c.vit_mlp, P_(w.vmlp), c.vit_mlp, Mv, c.vit_mlp, Dv, Lw.fc1_b, nullptr, 0,
+                 EPI_QUICK_GELU, 0));
+        TRY(gemm(P_(w.vmlp), c.vit_mlp, Lw.fc2_w, c.vit_mlp, Dv, P_(w.hv), Dv, Mv, Dv, c.vit_mlp, Lw.fc2_b, P_(w.hv), Dv,
+                 EPI_STORE, 0));
     }
     // mlp2x_gelu projector (Linear -> GELU(erf) -> Linear), applied to every row; the CLS rows are simply not spliced
-    CUDA_TRY(h, run_gemm(P_(w.hv), Dv, h->proj0_w, Dv, Dm, P_(w.proj1), Dm, Mv, Dm, Dv, h->proj0_b, nullptr, 0,
-                         EPI_GELU_ERF, 0, 0, nsm, st, lc));
-    CUDA_TRY(h, run_gemm(P_(w.proj1), Dm, h->proj2_w, Dm, Dm, P_(w.proj2), Dm, Mv, Dm, Dm, h->proj2_b, nullptr, 0,
-                         EPI_STORE, 0, 0, nsm, st, lc));
+    TRY(gemm(P_(w.hv), Dv, h->proj0_w, Dv, Dm, P_(w.proj1), Dm, Mv, Dm, Dv, h->proj0_b, nullptr, 0, EPI_GELU_ERF, 0));
+    TRY(gemm(P_(w.proj1), Dm, h->proj2_w, Dm, Dm, P_(w.proj2), Dm, Mv, Dm, Dm, h->proj2_b, nullptr, 0, EPI_STORE, 0));
 
     // ---------------- multimodal splice -> T5 encoder input ----------------
     int* seq_lens = reinterpret_cast<int*>(ws + w.seq_lens);
-    ++*lc;
-    splice_embed_kernel<<<B * S, 128, 0, st>>>(input_ids, text_lens, image_index, h->shared, P_(w.proj2), Dm, 1,
-                                                       P + 1, P_(w.x), seq_lens, B, L, S, P, Dm, c.image_token_id);
-    CUDA_TRY(h, cudaGetLastError());
+    float* bias_table = reinterpret_cast<float*>(ws + w.bias_table);
+    {
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        *lc += 2;
+        // feature block of an image = P + 1 rows, first patch row = 1 (drop CLS: mm_vision_select_feature='patch')
+        splice_embed_kernel<<<B * S, 128, 0, st>>>(input_ids, text_lens, image_index, h->shared, P_(w.proj2), Dm, 1, P + 1,
+                                                   P_(w.x), seq_lens, B, L, S, P, Dm, c.image_token_id);
+        bias_table_from_lut_kernel<<<(H * (2 * S - 1) + 255) / 256, 256, 0, st>>>(h->enc_rel, h->lut_bidir,
+                                                                                  c.rel_max_distance, bias_table, H, S);
+        TRY(cuda_ok(cudaSuccess, "splice / bias table"));
+    }
 
     // ---------------- T5 encoder ----------------
-    float* bias_table = reinterpret_cast<float*>(ws + w.bias_table);
-    ++*lc;
-    bias_table_from_lut_kernel<<<(H * (2 * S - 1) + 255) / 256, 256, 0, st>>>(h->enc_rel, h->lut_bidir,
-                                                                              c.rel_max_distance, bias_table, H, S);
-    CUDA_TRY(h, cudaGetLastError());
     for (int l = 0; l < c.enc_layers; ++l) {
         const T5EncLayerW& Lw = h->enc[l];
-        CUDA_TRY(h, run_rmsnorm(P_(w.x), Lw.ln0, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, nullptr,
-                             0, EPI_STORE, 0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
-                              seq_lens, bias_table, 1.0f, rnd, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE,
-                             0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_rmsnorm(P_(w.x), Lw.ln1, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, nullptr, 0,
-                             EPI_GATED_GELU, c.d_ff, 0, nsm, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm,
-                             EPI_STORE, 0, 0, nsm, st, lc));
+        TRY(rms(P_(w.x), Lw.ln0, P_(w.xn), M));
+        TRY(gemm(P_(w.xn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        {
+            ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * S * S * 64, st);
+            TRY(cuda_ok(run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
+                                  seq_lens, bias_table, 1.0f, rnd, st, lc), "t5 encoder attention"));
+        }
+        TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
+        TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
+        TRY(gemm(P_(w.xn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, nullptr, 0, EPI_GATED_GELU,
+                 c.d_ff));
+        TRY(gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm, EPI_STORE, 0));
     }
-    CUDA_TRY(h, run_rmsnorm(P_(w.x), h->enc_final_ln, P_(w.xn), M, Dm, c.t5_ln_eps, st, lc));  // encoder output in xn
+    TRY(rms(P_(w.x), h->enc_final_ln, P_(w.xn), M));  // encoder output lives in xn from here on
 
     // ---------------- T5 decoder (T target rows per pair) ----------------
-    ++*lc;
-    decoder_embed_kernel<<<Md, 128, 0, st>>>(labels, h->shared, P_(w.y), T, Dm, c.decoder_start_id, c.pad_token_id);
-    CUDA_TRY(h, cudaGetLastError());
+    {
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        ++*lc;
+        decoder_embed_kernel<<<Md, 128, 0, st>>>(labels, h->shared, P_(w.y), T, Dm, c.decoder_start_id, c.pad_token_id);
+        TRY(cuda_ok(cudaSuccess, "decoder embed"));
+    }
     for (int l = 0; l < c.dec_layers; ++l) {
         const T5DecLayerW& Lw = h->dec[l];
         // self-attention
-        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln0, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.dqkv), 3 * inner, Md, 3 * inner, Dm, nullptr, nullptr,
-                             0, EPI_STORE, 0, 0, nsm, st, lc));
-        ++*lc;
-        t5_decoder_self_attn_kernel<<<(B * H * T + 3) / 4, 128, 0, st>>>(P_(w.dqkv), P_(w.dattn), h->dec_rel,
-                                                                         h->lut_unidir, c.rel_max_distance, B, T, H, rnd);
-        CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, run_gemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm,
-                             EPI_STORE, 0, 0, nsm, st, lc));
-        // cross-attention: K/V projection of the encoder output (the reference recomputes it per layer,
+        TRY(rms(P_(w.y), Lw.ln0, P_(w.yn), Md));
+        TRY(gemm(P_(w.yn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.dqkv), 3 * inner, Md, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        {
+            ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * T * T * 64, st);
+            ++*lc;
+            t5_decoder_self_attn_kernel<<<(B * H * T + 3) / 4, 128, 0, st>>>(P_(w.dqkv), P_(w.dattn), h->dec_rel, h->lut_unidir,
+                                                                             c.rel_max_distance, B, T, H, rnd);
+            TRY(cuda_ok(cudaSuccess, "decoder self attention"));
+        }
+        TRY(gemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
+        // cross-attention: K/V projection of the encoder output (the reference recomputes it in every layer,
         // modeling_t5.py:297-299)
-        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln1, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE,
-                             0, 0, nsm, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr,
-                             0, EPI_STORE, 0, 0, nsm, st, lc));
-        ++*lc;
-        t5_cross_attn_kernel<8><<<B * H, 128, 0, st>>>(P_(w.dq), P_(w.ckv), P_(w.dattn), seq_lens, 2 * inner, B, T, S, H,
-                                                      rnd);
-        CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, run_gemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm,
-                             EPI_STORE, 0, 0, nsm, st, lc));
+        TRY(rms(P_(w.y), Lw.ln1, P_(w.yn), Md));
+        TRY(gemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        TRY(gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        {
+            ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * T * S * 64, st);
+            ++*lc;
+            t5_cross_attn_kernel<8><<<B * H, 128, 0, st>>>(P_(w.dq), P_(w.ckv), P_(w.dattn), seq_lens, 2 * inner, B, T, S, H, rnd);
+            TRY(cuda_ok(cudaSuccess, "cross attention"));
+        }
+        TRY(gemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
         // gated FFN
-        CUDA_TRY(h, run_rmsnorm(P_(w.y), Lw.ln2, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.yn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.dff), c.d_ff, Md, 2 * c.d_ff, Dm, nullptr, nullptr, 0,
-                             EPI_GATED_GELU, c.d_ff, 0, nsm, st, lc));
-        CUDA_TRY(h, run_gemm(P_(w.dff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.y), Dm, Md, Dm, c.d_ff, nullptr, P_(w.y), Dm,
-                             EPI_STORE, 0, 0, nsm, st, lc));
+        TRY(rms(P_(w.y), Lw.ln2, P_(w.yn), Md));
+        TRY(gemm(P_(w.yn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.dff), c.d_ff, Md, 2 * c.d_ff, Dm, nullptr, nullptr, 0, EPI_GATED_GELU,
+                 c.d_ff));
+        TRY(gemm(P_(w.dff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.y), Dm, Md, Dm, c.d_ff, nullptr, P_(w.y), Dm, EPI_STORE, 0));
     }
-    CUDA_TRY(h, run_rmsnorm(P_(w.y), h->dec_final_ln, P_(w.yn), Md, Dm, c.t5_ln_eps, st, lc));
+    TRY(rms(P_(w.y), h->dec_final_ln, P_(w.yn), Md));
 
     // ---------------- lm_head x hidden, fused log-sum-exp + label gather; logits never reach HBM ----------------
     float* lse_max = reinterpret_cast<float*>(ws + w.lse_max);
     float* lse_sum = reinterpret_cast<float*>(ws + w.lse_sum);
     float* label_logit = reinterpret_cast<float*>(ws + w.label_logit);
     const int ntiles = (c.vocab + LMHEAD_BN - 1) / LMHEAD_BN;
-    CUDA_TRY(h, run_lmhead(P_(w.yn), Dm, h->lm_head, Dm, Md, c.vocab, Dm, labels, lse_max, lse_sum, label_logit, nsm, st, lc));
-    ++*lc;
-    lse_finalize_kernel<<<(B + 3) / 4, 128, 0, st>>>(lse_max, lse_sum, label_logit, labels, out_scores, out_logprobs, B, T,
-                                                    ntiles);
-    CUDA_TRY(h, cudaGetLastError());
+    {
+        ProfScope ps(h, CAT_GEMM, 2.0 * Md * (double)c.vocab * Dm, st);
+        TRY(cuda_ok(run_lmhead(P_(w.yn), Dm, h->lm_head, Dm, Md, c.vocab, Dm, labels, lse_max, lse_sum, label_logit, nsm, st, lc),
+                    "lm_head"));
+    }
+    {
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        ++*lc;
+        lse_finalize_kernel<<<(B + 3) / 4, 128, 0, st>>>(lse_max, lse_sum, label_logit, labels, out_scores, out_logprobs, B, T,
+                                                        ntiles);
+        TRY(cuda_ok(cudaSuccess, "lse finalize"));
+    }
+#undef TRY
+    return VQA_OK;
+}
+
+extern "C" int vqa_set_profile(vqa_handle* h, int32_t enable) {
+    if (!h) return VQA_ERR_INVALID_ARG;
+    h->profile = enable != 0;
+    return VQA_OK;
+}
+
+// After the stream has been synchronised by the caller: device milliseconds, algorithmic FLOPs and launch-scope counts of
+// the last vqa_clipt5_score call per category {0 gemm, 1 attention, 2 norm, 3 other}.
+extern "C" int vqa_profile_read(vqa_handle* h, float* ms, double* flops, int64_t* scopes) {
+    if (!h || !ms || !flops || !scopes) return VQA_ERR_INVALID_ARG;
+    for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.f; flops[i] = 0.0; scopes[i] = 0; }
+    for (const auto& r : h->prof) {
+        float t = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&t, h->ev_pool[r.ev0], h->ev_pool[r.ev1]);
+        if (e != cudaSuccess) return fail(h, VQA_ERR_CUDA, std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e));
+        ms[r.cat] += t;
+        flops[r.cat] += r.flops;
+        scopes[r.cat] += 1;
+    }
     return VQA_OK;
 }
 
@@ -614,6 +711,7 @@ extern "C" void vqa_destroy(vqa_handle* h) {
     if (!h) return;
     if (h->lut_bidir) cudaFree(h->lut_bidir);
     if (h->lut_unidir) cudaFree(h->lut_unidir);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 

@@ -184,8 +184,30 @@ class ClipT5Engine:
         _check(rc, self._h, "vqa_clipt5_score")
         return (out, logp) if return_logprobs else out
 
+    def score_host(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, text_lens: torch.Tensor,
+                   labels: torch.Tensor, image_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host tensors in, host tensor out: H2D copies of this step's inputs (use pinned memory for async copies),
+        one engine call, D2H of the scores. This is the end-to-end call bench.py's `e2e` times."""
+        dev = self.device
+        d = [t.to(dev, non_blocking=True) if t is not None else None
+             for t in (pixel_values, input_ids, text_lens, labels, image_index)]
+        scores = self.score_tensors(d[0], d[1], d[2], d[3], image_index=d[4])
+        return scores.cpu()
+
     def last_launch_count(self) -> int:
         return int(self.lib.vqa_last_launch_count(self._h))
+
+    def set_profile(self, enable: bool):
+        _check(self.lib.vqa_set_profile(self._h, 1 if enable else 0), self._h, "vqa_set_profile")
+
+    def read_profile(self):
+        """After torch.cuda.synchronize(): {category: (device_ms, algorithmic_flops, scopes)} of the last call."""
+        ms = (C.c_float * 4)()
+        fl = (C.c_double * 4)()
+        sc = (C.c_int64 * 4)()
+        _check(self.lib.vqa_profile_read(self._h, ms, fl, sc), self._h, "vqa_profile_read")
+        names = ("gemm", "attention", "norm", "other")
+        return {n: (float(ms[i]), float(fl[i]), int(sc[i])) for i, n in enumerate(names)}
 
 
 # ------------------------------------------------------------------------------------------------ single-kernel ops

@@ -1,0 +1,39 @@
+"""World-size-2 gloo test of the N>1 path: contiguous sharding + the single all-gather of scores."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from t2v_metrics_b200.parallel import gather_scores, shard_bounds
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n, dtype=torch.float32) * 0.5 + 1.0          # the scores a single process would produce
+    s, e, _ = shard_bounds(n, world, rank)
+    got = gather_scores(full[s:e].clone(), n)
+    q.put((rank, torch.equal(got, full)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_matches_single_process():
+    ctx = mp.get_context("spawn")
+    for n in (10, 7, 1):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+        [p.start() for p in procs]
+        [p.join(60) for p in procs]
+        res = sorted(q.get(timeout=5) for _ in range(2))
+        assert res == [(0, True), (1, True)], (n, res)

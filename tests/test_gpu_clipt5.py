@@ -1,0 +1,166 @@
+"""End-to-end parity of the B200 engine (through the C ABI) against the oracle, the committed golden HF vectors and the
+real transformers modules run on the same GPU. Tolerances are on the final score (north star: 1e-3):
+
+  * vs the oracle's bf16-rounding restatement of the reference (what the reference computes under autocast): <= 1e-3;
+  * vs the fp32 oracle / golden HF fp32 vectors: within the reference's own bf16-vs-fp32 gap (measured per case), since the
+    reference's autocast run itself sits up to ~3e-3 away from fp32 on these shallow models.
+"""
+import dataclasses
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clipt5_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def load_case(name, golden_dir):
+    blob = torch.load(os.path.join(golden_dir, f"clipt5_{name}.pt"), weights_only=False)
+    cfg = orc.ClipT5Config.tiny(**blob["config"])
+    if "state_dict" in blob:
+        sd = blob["state_dict"]
+    else:
+        sd = orc.make_synthetic_state_dict(cfg, seed=blob["seed_weights"], label_ids=blob["label_ids"])
+        lm = sd["lm_head.weight"].float()
+        for t, row in zip(blob["label_ids"], blob["label_rows"]):
+            lm[t] = row
+        sd["lm_head.weight"] = lm.to(torch.bfloat16)
+    return blob, cfg, sd
+
+
+def make_engine(cfg, sd, dev, **kw):
+    from t2v_metrics_b200.config import ClipT5Config
+    from t2v_metrics_b200.engine import ClipT5Engine
+    eng = ClipT5Engine(ClipT5Config(**dataclasses.asdict(cfg)), dev, **kw)
+    eng.load_state_dict(sd)
+    return eng
+
+
+def run_engine(eng, inp, dev):
+    i32 = lambda t: None if t is None else t.to(dev, torch.int32)
+    s, lp = eng.score_tensors(inp["pixels"].to(dev), i32(inp["input_ids"]), i32(inp["text_lens"]), i32(inp["labels"]),
+                              image_index=i32(inp.get("image_index")), return_logprobs=True)
+    torch.cuda.synchronize()
+    return s.cpu(), lp.cpu()
+
+
+@pytest.mark.parametrize("name", ["micro", "tiny", "tiny_shared_image", "mid"])
+def test_engine_matches_oracle_and_golden(name, golden_dir, dev):
+    blob, cfg, sd = load_case(name, golden_dir)
+    inp = blob["inputs"]
+    eng = make_engine(cfg, sd, dev)
+    s, lp = run_engine(eng, inp, dev)
+    o16 = orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], inp["image_index"],
+                           mode="bf16", return_all=True)
+    g32, g16 = blob["hf_fp32"], blob["hf_bf16"]
+    ref_gap = float((g16["scores"] - g32["scores"]).abs().max())              # the reference's own autocast-vs-fp32 gap
+    e_bf16 = float((s - o16["scores"]).abs().max())
+    e_fp32 = float((s - g32["scores"]).abs().max())
+    e_hf16 = float((s - g16["scores"]).abs().max())
+    print(f"\n[{name}] engine {s.tolist()}\n   vs oracle-bf16 {e_bf16:.2e} | vs HF fp32 golden {e_fp32:.2e} | vs HF bf16 golden {e_hf16:.2e} "
+          f"| HF bf16-vs-fp32 {ref_gap:.2e} | launches {eng.last_launch_count()}")
+    assert e_bf16 <= 1e-3
+    assert e_fp32 <= 2.0 * ref_gap + 1e-3
+    assert float((lp - o16["logprobs"]).abs().max()) <= 2e-2
+    assert bool(((s >= 0) & (s <= 1)).all())
+
+
+def test_engine_vs_transformers_on_the_same_gpu(golden_dir, dev):
+    """The reference forward (HF CLIPVisionModel + T5ForConditionalGeneration, bf16 weights, autocast) on cuda vs the engine."""
+    import hf_reference as hf
+    blob, cfg, sd = load_case("mid", golden_dir)
+    inp = blob["inputs"]
+    sd32 = {k: v.float() for k, v in sd.items()}
+    mods = hf.build_hf_modules(cfg, sd32, dtype=torch.bfloat16, device=dev)
+    ref = hf.hf_clipt5_forward(cfg, mods, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], autocast_bf16=True)
+    eng = make_engine(cfg, sd, dev)
+    s, _ = run_engine(eng, inp, dev)
+    gap = float((blob["hf_bf16"]["scores"] - blob["hf_fp32"]["scores"]).abs().max())
+    print(f"\nengine {s.tolist()} | HF-on-GPU {ref.tolist()} | diff {float((s - ref).abs().max()):.2e} | HF bf16-vs-fp32 {gap:.2e}")
+    assert float((s - ref).abs().max()) <= 2.0 * gap + 1e-3
+
+
+def test_batch_padding_and_dedupe_invariance(golden_dir, dev):
+    """Properties the domain offers: a pair's score does not depend on (a) what else is in the batch, (b) how much right
+    padding its row carries, (c) whether its image is shared through image_index."""
+    blob, cfg, sd = load_case("tiny", golden_dir)
+    inp = blob["inputs"]
+    eng = make_engine(cfg, sd, dev)
+    full, _ = run_engine(eng, inp, dev)
+    for b in range(inp["input_ids"].shape[0]):
+        one = {k: (v[b:b + 1] if torch.is_tensor(v) else v) for k, v in inp.items()}
+        one["image_index"] = None
+        s1, _ = run_engine(eng, one, dev)
+        assert float((s1[0] - full[b]).abs()) <= 2e-4, b
+    padded = dict(inp)
+    padded["input_ids"] = torch.nn.functional.pad(inp["input_ids"], (0, 5), value=0)
+    sp, _ = run_engine(eng, padded, dev)
+    assert float((sp - full).abs().max()) <= 2e-4
+    dup = dict(inp)
+    dup["pixels"] = inp["pixels"][[0, 0, 1, 1]]
+    a, _ = run_engine(eng, dup, dev)
+    shared = dict(inp)
+    shared["pixels"] = inp["pixels"][[0, 1]]
+    shared["image_index"] = torch.tensor([0, 0, 1, 1])
+    b_, _ = run_engine(eng, shared, dev)
+    assert torch.equal(a, b_)
+
+
+def test_full_size_xxl_properties(dev):
+    """BASELINE config-2 size (clip-flant5-xxl dims, B=64, S_enc=672): determinism, finite scores in [0,1], and batch
+    invariance of the first pairs (B=64 vs B=4), which exercises every kernel at its production shape."""
+    from t2v_metrics_b200.config import ClipT5Config
+    from t2v_metrics_b200.engine import ClipT5Engine
+    from t2v_metrics_b200.synthetic import synthetic_engine_weights, synthetic_batch
+    cfg = ClipT5Config.xxl()
+    eng = ClipT5Engine(cfg, dev)
+    eng.bind_engine_tensors(synthetic_engine_weights(cfg, dev, seed=0))
+    host = synthetic_batch(cfg, 64, 97, seed=1, ragged=True)
+    d = {k: v.to(dev) for k, v in host.items()}
+    s1, lp1 = eng.score_tensors(d["pixels"], d["input_ids"], d["text_lens"], d["labels"], return_logprobs=True)
+    s1, lp1 = s1.clone(), lp1.clone()
+    s2 = eng.score_tensors(d["pixels"], d["input_ids"], d["text_lens"], d["labels"]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2)
+    assert bool(torch.isfinite(lp1).all()) and bool(((s1 >= 0) & (s1 <= 1)).all())
+    s4, lp4 = eng.score_tensors(d["pixels"][:4], d["input_ids"][:4], d["text_lens"][:4], d["labels"][:4], return_logprobs=True)
+    torch.cuda.synchronize()
+    assert float((lp4 - lp1[:4]).abs().max()) <= 5e-2, (lp4, lp1[:4])     # same rows through differently tiled GEMMs
+
+
+def test_plugin_forward_contract(tmp_path, golden_dir, dev):
+    """VQAScore(model)(images=[...], texts=[...]) surface: [M, N] tensor on the device, values in [0, 1] (reference test.py:106-144)."""
+    import types
+    import numpy as np
+    from PIL import Image
+    import t2v_metrics_b200 as t2v
+    from t2v_metrics_b200.config import ClipT5Config
+    blob, cfg, sd = load_case("tiny", golden_dir)
+
+    class Tok:
+        pad_token_id = 0
+        def __call__(self, chunk):
+            return types.SimpleNamespace(input_ids=[3 + (sum(map(ord, w)) % 400) for w in chunk.split()] + [1])
+
+    rng = np.random.RandomState(0)
+    paths = []
+    for i, (w, h) in enumerate([(80, 60), (64, 64)]):
+        p = str(tmp_path / f"img{i}.png")
+        Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8)).save(p)
+        paths.append(p)
+    scorer = t2v.VQAScore(model="clip-flant5-xl", device="cuda", cache_dir=str(tmp_path), tokenizer=Tok(), state_dict=sd,
+                          config=ClipT5Config(**dataclasses.asdict(cfg)))
+    out = scorer(images=paths, texts=["a dog", "two cats on a sofa"])
+    assert out.shape == (2, 2) and out.is_cuda and bool(((out >= 0) & (out <= 1)).all())
+    single = scorer.model.forward([paths[1]], ["two cats on a sofa"])
+    assert single.device.type == "cpu" and single.dtype == torch.float32
+    assert float((single[0] - out[1, 1].cpu()).abs()) <= 2e-4

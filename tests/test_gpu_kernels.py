@@ -1,0 +1,144 @@
+"""Kernel-level parity on a real B200, through the C ABI (vqa_op_*). Reference = plain PyTorch fp32 math of the same op
+with the same bf16 rounding points."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from t2v_metrics_b200.engine import ops as _ops
+    return _ops
+
+
+def ref_gemm(a, w, bias=None, residual=None, epilogue="store", gate_off=0):
+    acc = a.float() @ w.float().t()
+    if epilogue == "gated_gelu":
+        g = acc[:, :gate_off].bfloat16().float()
+        u = acc[:, gate_off:].bfloat16().float()
+        return (torch.nn.functional.gelu(g, approximate="tanh").bfloat16().float() * u).bfloat16()
+    if bias is not None:
+        acc = acc + bias.float()
+    y = acc.bfloat16().float()
+    if epilogue == "quick_gelu":
+        y = y * torch.sigmoid(1.702 * y)
+    elif epilogue == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif epilogue == "relu":
+        y = torch.relu(y)
+    if residual is not None:
+        y = y + residual.float()
+    return y.bfloat16()
+
+
+def close(c, ref, what):
+    d = (c.float() - ref.float()).abs()
+    bad = int((d > 0.02 + 0.01 * ref.float().abs()).sum())     # 1 bf16 ulp of slack on top of fp32 accumulation-order noise
+    assert bad == 0, (what, bad, float(d.max()))
+
+
+@pytest.mark.parametrize("variant", [2562, 2561, 1282, 1281, 641, 321, 0])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (512, 512, 512), (1000, 776, 1032), (300, 4096, 640)])
+def test_gemm_store_bias_residual(ops, variant, shape):
+    M, N, K = shape
+    torch.manual_seed(1)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    bias = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    close(ops.gemm(a, w, variant=variant), ref_gemm(a, w), "plain")
+    close(ops.gemm(a, w, bias=bias, residual=res, variant=variant), ref_gemm(a, w, bias, res), "bias+res")
+    # in-place residual (the residual stream is updated in place by the engine)
+    c = res.clone()
+    ops.gemm(a, w, bias=bias, residual=c, variant=variant, out=c)
+    close(c, ref_gemm(a, w, bias, res), "in-place residual")
+
+
+@pytest.mark.parametrize("variant", [2562, 2561, 1281, 641, 0])
+@pytest.mark.parametrize("epi", ["quick_gelu", "gelu", "relu", "gated_gelu"])
+def test_gemm_fused_epilogues(ops, variant, epi):
+    torch.manual_seed(2)
+    M, N, K = 700, 1024, 512
+    a = (torch.randn(M, K, device="cuda")).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    bias = None if epi == "gated_gelu" else (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    c = ops.gemm(a, w, bias=bias, epilogue=epi, variant=variant, gate_up_offset=N // 2)
+    close(c, ref_gemm(a, w, bias, None, epi, N // 2), epi)
+
+
+def test_gemm_empty_and_ragged_edges(ops):
+    torch.manual_seed(3)
+    for (M, N, K) in [(1, 8, 8), (129, 264, 72), (257, 40, 200)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+        for variant in (0, 2562, 321):
+            close(ops.gemm(a, w, variant=variant), ref_gemm(a, w), (M, N, K, variant))
+
+
+def test_gemm_linearity_full_size(ops):
+    """Size-independent property at the BASELINE shape (M = 64*672): GEMM(a1 + a2) == GEMM(a1) + GEMM(a2) up to rounding,
+    and a checksum against cuBLAS via torch.matmul."""
+    torch.manual_seed(4)
+    M, N, K = 43008, 4096, 4096
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    c = ops.gemm(a, w)
+    ref = torch.matmul(a, w.t())
+    d = (c.float() - ref.float()).abs()
+    assert float(d.max()) <= 0.0625 and float(d.mean()) < 1e-3
+    assert abs(float(c.float().sum()) - float(ref.float().sum())) <= 1e-3 * float(ref.float().abs().sum()) ** 0.5 + 50
+
+
+@pytest.mark.parametrize("B,S,H,use_bias,ragged,scale", [(2, 100, 4, True, True, 1.0), (3, 577, 16, False, False, 0.125),
+                                                         (2, 672, 8, True, True, 1.0), (1, 64, 1, True, False, 1.0),
+                                                         (2, 65, 2, False, True, 0.125)])
+def test_attention_matches_torch(ops, B, S, H, use_bias, ragged, scale):
+    torch.manual_seed(5)
+    qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 0.5).bfloat16()
+    lens = torch.randint(max(1, S // 2), S + 1, (B,), device="cuda", dtype=torch.int32) if ragged else None
+    table = (torch.randn(H, 2 * S - 1, device="cuda") * 0.5).bfloat16().float().contiguous() if use_bias else None
+    out = ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=scale)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = torch.matmul(q, k.transpose(-1, -2)) * scale
+    if use_bias:
+        idx = (torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None]) + S - 1
+        sc = sc + table[:, idx][None]
+    L = lens if lens is not None else torch.full((B,), S, device="cuda", dtype=torch.int32)
+    kmask = torch.arange(S, device="cuda")[None, :] < L[:, None]
+    sc = sc.masked_fill(~kmask[:, None, None, :], float("-inf"))
+    ref = torch.matmul(torch.softmax(sc, -1), v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    qmask = kmask.reshape(B * S)
+    assert float((out[qmask].float() - ref[qmask]).abs().max()) < 0.02
+    assert float(out[~qmask].float().abs().max()) == 0.0 if (~qmask).any() else True
+
+
+def test_norms(ops):
+    torch.manual_seed(6)
+    for D in (4096, 2048, 256):
+        x = torch.randn(333, D, device="cuda").bfloat16()
+        g = (1 + 0.1 * torch.randn(D, device="cuda")).bfloat16()
+        var = x.float().pow(2).mean(-1, keepdim=True)
+        ref = (g.float() * (x.float() * torch.rsqrt(var + 1e-6)).bfloat16().float()).bfloat16()
+        assert float((ops.norm(x, g, None, 1e-6).float() - ref.float()).abs().max()) <= 0.016
+    for D in (1024, 256):
+        x = torch.randn(333, D, device="cuda").bfloat16()
+        g = (1 + 0.1 * torch.randn(D, device="cuda")).bfloat16()
+        b = (0.1 * torch.randn(D, device="cuda")).bfloat16()
+        ref = torch.nn.functional.layer_norm(x.float(), (D,), g.float(), b.float(), 1e-5).bfloat16()
+        assert float((ops.norm(x, g, b, 1e-5).float() - ref.float()).abs().max()) <= 0.016
+
+
+def test_lmhead_logprob_never_materialises_logits(ops):
+    torch.manual_seed(7)
+    for (M, N, K) in [(128, 32128, 512), (6, 1000, 256), (2, 130, 64)]:
+        h = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5 * 3).bfloat16()
+        labels = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
+        labels[0] = N - 1
+        lp = ops.lmhead_logprob(h, w, labels)
+        logits = (h.float() @ w.float().t()).bfloat16().float()
+        ref = torch.log_softmax(logits, -1).gather(-1, labels.long()[:, None])[:, 0]
+        assert float((lp - ref).abs().max()) < 5e-3

@@ -1,0 +1,92 @@
+"""Host-side logic of the drop-in boundary: tokenizer splice, expand2square, preprocessing, registry/API surface, sharding.
+CPU only."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import t2v_metrics_b200 as t2v
+from t2v_metrics_b200.models.vqascore_models import mm_utils
+from t2v_metrics_b200.models.vqascore_models.clip_t5_model import format_question, CLIP_T5_MODELS, CLIPT5Model
+from t2v_metrics_b200.parallel import shard_bounds
+from oracle import clipt5_oracle as orc
+
+
+class FakeTok:
+    """Same contract as the generator in tools/make_golden.py: per-word ids + trailing </s> = 1."""
+    pad_token_id = 0
+
+    def __call__(self, chunk):
+        return types.SimpleNamespace(input_ids=[3 + (sum(map(ord, w)) % 997) for w in chunk.split()] + [1])
+
+
+def test_golden_vestiges_from_reference(golden_dir):
+    """expand2square / t5_tokenizer_image_token outputs recorded by running /root/reference's own mm_utils.py."""
+    blob = torch.load(os.path.join(golden_dir, "host_vestiges.pt"), weights_only=False)
+    for case in blob["expand2square"]:
+        img = Image.fromarray(case["inp"].numpy())
+        for fn in (mm_utils.expand2square, orc.expand2square):
+            out = np.asarray(fn(img, (122, 116, 104)))
+            assert np.array_equal(out, case["out"].numpy())
+    for case in blob["t5_tokenizer_image_token"]:
+        assert mm_utils.t5_tokenizer_image_token(case["prompt"], FakeTok()) == case["ids"]
+        assert orc.t5_tokenizer_image_token(case["prompt"], lambda c: FakeTok()(c).input_ids) == case["ids"]
+
+
+def test_tokenizer_each_chunk_keeps_its_eos():
+    ids = mm_utils.t5_tokenizer_image_token("a <image>\nb", FakeTok())
+    assert ids.count(-200) == 1 and ids[ids.index(-200) - 1] == 1 and ids[-1] == 1
+
+
+def test_prompt_format_matches_reference_constants():
+    q = format_question('Does this figure show "a dog"? Please answer yes or no.')
+    assert q.startswith("A chat between a curious user") and " USER: <image>\n" in q and q.endswith(" ASSISTANT: ")
+    assert q == orc.format_question('Does this figure show "a dog"? Please answer yes or no.')
+
+
+def test_clip_preprocess_matches_hf_processor():
+    from transformers import CLIPImageProcessor
+    rng = np.random.RandomState(0)
+    proc = CLIPImageProcessor(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336}, do_resize=True,
+                              do_center_crop=True, do_normalize=True, image_mean=list(mm_utils.CLIP_IMAGE_MEAN),
+                              image_std=list(mm_utils.CLIP_IMAGE_STD), resample=3, do_convert_rgb=True)
+    for (w, h) in [(512, 512), (640, 400), (300, 500)]:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        sq = mm_utils.expand2square(img, tuple(int(x * 255) for x in mm_utils.CLIP_IMAGE_MEAN))
+        ref = torch.from_numpy(np.asarray(proc.preprocess(sq, return_tensors="np")["pixel_values"][0]))
+        got = mm_utils.clip_preprocess(img, 336, pad=True)
+        assert got.shape == (3, 336, 336)
+        assert float((got - ref).abs().max()) < 2e-2          # PIL vs processor resampling paths, <= 1 grey level
+        assert float((got - orc.clip_preprocess(img, 336)).abs().max()) == 0.0
+
+
+def test_registry_surface_matches_reference():
+    assert t2v.list_all_models() == ["clip-flant5-xxl", "clip-flant5-xl"]
+    assert CLIPT5Model.video_mode == "concat" and CLIPT5Model.allows_image
+    assert set(CLIP_T5_MODELS["clip-flant5-xxl"]) >= {"tokenizer", "model"}
+    with pytest.raises(NotImplementedError):
+        t2v.get_score_model("not-a-model")
+    cfg = CLIP_T5_MODELS["clip-flant5-xxl"]["config"]()
+    assert (cfg.d_model, cfg.n_heads, cfg.d_ff, cfg.vocab, cfg.num_patches) == (4096, 64, 10240, 32128, 576)
+
+
+def test_engine_refuses_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from t2v_metrics_b200.engine import ClipT5Engine
+    from t2v_metrics_b200.config import ClipT5Config
+    with pytest.raises(RuntimeError):
+        ClipT5Engine(ClipT5Config())
+
+
+@pytest.mark.parametrize("n,world", [(10000, 8), (7, 8), (64, 1), (65, 2), (0, 4)])
+def test_shard_bounds_cover_all_pairs_once(n, world):
+    seen = []
+    for r in range(world):
+        s, e, per = shard_bounds(n, world, r)
+        assert 0 <= s <= e <= n and e - s <= per
+        seen.extend(range(s, e))
+    assert seen == list(range(n))
