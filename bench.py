@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--text-len", type=int, default=97)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling pass: 2 device steps only, no JSON (run under ncu)")
     return ap.parse_args()
 
 
@@ -97,9 +98,12 @@ def cpu_reference_pairs_per_s(model: str, text_len: int):
         sd = orc.make_synthetic_state_dict(cfg, seed=0)
         inp = orc.make_synthetic_inputs(cfg, 1, text_len, seed=1)
         orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32")  # warm-up
-        t0 = time.perf_counter()
-        orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32")
-        times[depth] = time.perf_counter() - t0
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32")
+            best = min(best, time.perf_counter() - t0)
+        times[depth] = best
         del sd
     per_layer = max(times[2] - times[1], 1e-9)
     full = times[1] + (base.enc_layers - 1) * per_layer
@@ -166,6 +170,13 @@ def run_engine(args, rank, local_rank, world):
             s = gather_scores(s.to(dev), total_pairs).cpu()
         return s
 
+    if args.ncu:
+        for _ in range(2):
+            step_device()
+        sync_all()
+        if rank == 0:
+            print(f"ncu pass: {eng.last_launch_count()} launches per step", flush=True)
+        return
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     sync_all()
