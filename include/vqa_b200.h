@@ -64,6 +64,8 @@ typedef struct {
     int32_t pad_token_id;     /* 0 */
     int32_t decoder_start_id; /* 0 */
     int32_t emulate_bf16_rounding; /* 1: round scores/bias adds to bf16 where the reference's eager path does */
+    int32_t cross_attention_mode;  /* 0: absorbed (q.(Wk x) = (Wk^T q).x, needs t5.dec.{i}.ckT); 1: project K/V of all
+                                      encoder rows in every decoder layer, as modeling_t5.py:297-299 does */
 } vqa_clipt5_config;
 
 /* A named device tensor handed to vqa_bind_weights (borrowed pointer, bf16, row-major contiguous). */

@@ -28,7 +28,7 @@ class VqaClipT5Config(C.Structure):
         ("d_model", C.c_int32), ("n_heads", C.c_int32), ("d_ff", C.c_int32), ("enc_layers", C.c_int32),
         ("dec_layers", C.c_int32), ("vocab", C.c_int32), ("rel_buckets", C.c_int32), ("rel_max_distance", C.c_int32),
         ("t5_ln_eps", C.c_float), ("image_token_id", C.c_int32), ("pad_token_id", C.c_int32),
-        ("decoder_start_id", C.c_int32), ("emulate_bf16_rounding", C.c_int32),
+        ("decoder_start_id", C.c_int32), ("emulate_bf16_rounding", C.c_int32), ("cross_attention_mode", C.c_int32),
     ]
 
 

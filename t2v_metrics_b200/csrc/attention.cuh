@@ -353,4 +353,47 @@ __global__ void __launch_bounds__(128) t5_cross_attn_kernel(const __nv_bfloat16*
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Absorbed cross-attention helpers (see vqa_b200.cu: q.(Wk h) == (Wk^T q).h and sum p (Wv h) == Wv (sum p h)).
+
+// [B, S, D] -> [B, D, Sp] (Sp >= S, multiple of 8; columns >= S are zero). 32x32 tiles through shared memory.
+__global__ void transpose_bsd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xt, int S, int D,
+                                     int Sp) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int s = s0 + i, d = d0 + tx;
+        tile[i][tx] = (s < S && d < D) ? x[((size_t)b * S + s) * D + d] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int d = d0 + i, s = s0 + tx;
+        if (d < D && s < Sp) xt[((size_t)b * D + d) * Sp + s] = tile[tx][i];
+    }
+}
+
+// In-place masked softmax over the key axis of scores [B*rows_per_b, Sp] (bf16): keys >= seq_len[b] get probability 0.
+// fp32 softmax, probabilities cast back to bf16 (modeling_t5.py:331). One warp per row.
+__global__ void cross_softmax_kernel(__nv_bfloat16* __restrict__ sc, const int* __restrict__ seq_lens, int rows_per_b,
+                                     int total_rows, int S, int Sp) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int b = row / rows_per_b;
+    const int len = seq_lens ? min(seq_lens[b], S) : S;
+    __nv_bfloat16* r = sc + (size_t)row * Sp;
+    float mx = -INFINITY;
+    for (int i = lane; i < len; i += 32) mx = fmaxf(mx, __bfloat162float(r[i]));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int i = lane; i < len; i += 32) sum += __expf(__bfloat162float(r[i]) - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int i = lane; i < Sp; i += 32)
+        r[i] = __float2bfloat16_rn(i < len ? __expf(__bfloat162float(r[i]) - mx) * inv : 0.f);
+}
+
 }  // namespace vqa

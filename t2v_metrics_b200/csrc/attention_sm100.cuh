@@ -1,0 +1,347 @@
+// tcgen05 flash attention for head_dim 64 (T5 encoder self-attention with relative-position bias + key padding mask,
+// CLIP ViT self-attention with 1/sqrt(d) scale). One CTA = one (sample, head, 128-query tile); the score tile never
+// leaves the SM:
+//
+//   warp 0   TMA producer : Q tile once, then K/V tiles (128 keys x 64) through a 2-stage smem ring
+//   warp 1   MMA issuer   : S = Q K^T   (UMMA 128x128x16, SS: both operands in 128B-swizzled smem, D in TMEM)
+//                           O += P V    (UMMA 128x64x16,  TS: P read from TMEM as bf16, V from smem MN-major)
+//   warps 2-5 softmax     : one thread per query row: tcgen05.ld the 128 scores, + bias (log2 domain), online max with
+//                           lazy rescale of O in TMEM, exp2, P -> bf16 -> tcgen05.st; final O / l -> HBM
+//
+// Two CTAs are resident per SM (<= 96 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Replaces the eager attention of transformers/models/t5/modeling_t5.py:308-334 (which materialises [B,H,S,S] scores in
+// HBM) and transformers/models/clip/modeling_clip.py:261-336.
+#pragma once
+#include "ptx.cuh"
+#include "gemm_sm100.cuh"   // make_tmap_bf16_2d
+
+namespace vqa {
+
+struct AttnTcParams {
+    __nv_bfloat16* o;         // [B*S, ldo], column h*64 + d
+    int ldo;
+    const int* seq_lens;      // [B] or nullptr
+    const float* bias_table;  // [H, 2S-1] or nullptr; index = key - query + S - 1
+    int S, H;
+    int q_col0, k_col0, v_col0;  // column of head 0 inside the packed [B*S, ld] buffer
+    float scale_log2e;        // (softmax scale) * log2(e)
+};
+
+constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
+constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
+constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
+constexpr int AT_BIAS_PAD = 128;
+
+inline size_t attn_tc_smem_bytes(int S) {
+    return 1024 + 5 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 128;
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem, bf16 pairs] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// MN-major operand tile: rows = K index (keys), 64 contiguous bf16 (128 B) of the MN index (head dim) per row, 128B
+// swizzle as written by TMA. SBO = 8 rows * 128 B between 8-row groups along K; LBO = distance between 64-wide MN atoms.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(192, 2)
+attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * AT_BQ;
+    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const size_t row_base = (size_t)b * p.S;
+
+    if (q0 >= len) {  // fully padded query tile: deterministic zeros, no TMEM/barrier set-up
+        for (int i = threadIdx.x; i < AT_BQ * 8; i += blockDim.x) {
+            const int r = i >> 3, c = i & 7;
+            if (q0 + r < p.S)
+                *reinterpret_cast<uint4*>(p.o + (row_base + q0 + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + AT_TILE_BYTES;          // [2]
+    uint8_t* sV = smem + 3 * AT_TILE_BYTES;      // [2]
+    float* sBias = reinterpret_cast<float*>(smem + 5 * AT_TILE_BYTES);   // [2S-1 + 2*PAD], entry i <-> rel = i - PAD
+    const int bias_n = 2 * p.S - 1 + 2 * AT_BIAS_PAD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
+    uint64_t* q_full = bars;          // 1
+    uint64_t* kv_full = bars + 1;     // [2]
+    uint64_t* kv_empty = bars + 3;    // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* o_done = bars + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int nkt = (len + AT_BK - 1) / AT_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        mbar_init(q_full, 1);
+        mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+        mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    if (HAS_BIAS) {
+        const float LOG2E = 1.4426950408889634f;
+        const int width = 2 * p.S - 1;
+        for (int i = threadIdx.x; i < bias_n; i += blockDim.x) {
+            const int r = i - AT_BIAS_PAD;
+            sBias[i] = (r >= 0 && r < width) ? p.bias_table[(size_t)h * width + r] * LOG2E : 0.f;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+            tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col0 + h * AT_D, (int)(row_base + q0));
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+                tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
+            const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ));
+            auto issue_pv = [&](int i) {
+                mbar_wait(p_full, (uint32_t)i & 1u);
+                tcgen05_fence_after();
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (i & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < AT_BK / 16; ++ks)
+                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
+                                (i > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[i & 1]);
+                umma_commit<1>(o_done);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_full[st], ((uint32_t)j >> 1) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k)
+                    umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit<1>(s_full);
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(nkt - 1);
+        }
+    } else {
+        // ===================== softmax / correction / epilogue: one thread per query row =====================
+        const uint32_t quad = warp & 3u;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (quad * 32u) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        const int bias_base = AT_BIAS_PAD + (p.S - 1) - (q0 + row);   // + kcol
+        for (int j = 0; j < nkt; ++j) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tcgen05_fence_after();
+            float t[128];
+            {
+                uint32_t v[32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[c * 32 + i] = __uint_as_float(v[i]);
+                }
+            }
+            // S has been copied to registers: hand the TMEM columns back so the next QK^T can start
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+
+            const int k0 = j * AT_BK;
+            float tile_max = -INFINITY;
+            if (HAS_BIAS) {
+                const float* bp = sBias + bias_base + k0;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    t[i] = fmaf(t[i], p.scale_log2e, bp[i]);
+                    tile_max = fmaxf(tile_max, t[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    t[i] *= p.scale_log2e;
+                    tile_max = fmaxf(tile_max, t[i]);
+                }
+            }
+            if (k0 + AT_BK > len) {   // last tile: keys beyond the sample's length
+                tile_max = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    if (k0 + i >= len) t[i] = -INFINITY;
+                    tile_max = fmaxf(tile_max, t[i]);
+                }
+            }
+            // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
+            float corr = 1.f;
+            bool rescale = false;
+            if (j == 0) {
+                m_run = tile_max;
+            } else {
+                const bool need = tile_max > m_run + 8.f;
+                rescale = __any_sync(0xffffffffu, need);
+                if (rescale) {
+                    const float m_new = fmaxf(m_run, tile_max);
+                    corr = fast_exp2(m_run - m_new);
+                    m_run = m_new;
+                }
+            }
+            uint32_t pk_lo[32], pk_hi[32];   // bf16 pairs: keys [0,64) and [64,128)
+            float psum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float e0 = fast_exp2(t[2 * i] - m_run);
+                const float e1 = fast_exp2(t[2 * i + 1] - m_run);
+                const float e2 = fast_exp2(t[64 + 2 * i] - m_run);
+                const float e3 = fast_exp2(t[64 + 2 * i + 1] - m_run);
+                psum += (e0 + e1) + (e2 + e3);
+                pk_lo[i] = pack_bf16x2(e0, e1);
+                pk_hi[i] = pack_bf16x2(e2, e3);
+            }
+            l_run = l_run * corr + psum;
+
+            if (j > 0) {
+                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // P_{j-1} consumed, O_{j-1} complete
+                tcgen05_fence_after();
+                if (rescale) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                    }
+                }
+            }
+            tmem_st_32x32b_x32(tmem_P + lane_off, pk_lo);
+            tmem_st_32x32b_x32(tmem_P + lane_off + 32, pk_hi);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l
+        mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
+        tcgen05_fence_after();
+        const int qrow = q0 + row;
+        const float inv = (qrow < len) ? 1.f / l_run : 0.f;
+        __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+            tmem_ld_wait();
+            if (qrow < p.S) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pack_bf16x2(__uint_as_float(ov[g * 8 + 2 * e]) * inv, __uint_as_float(ov[g * 8 + 2 * e + 1]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
+}
+
+// qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
+inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
+                                  int B, int S, int H, const int* seq_lens, const float* bias_table, float scale,
+                                  cudaStream_t stream) {
+    CUtensorMap tm;
+    if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    AttnTcParams p;
+    p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    const size_t smem = attn_tc_smem_bytes(S);
+    static size_t max_set[2] = {0, 0};
+    const int which = bias_table ? 1 : 0;
+    if (smem > max_set[which]) {
+        cudaError_t e = bias_table ? cudaFuncSetAttribute(attn_tc_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(attn_tc_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[which] = smem;
+    }
+    dim3 grid((S + AT_BQ - 1) / AT_BQ, H, B);
+    if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
+    else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
+    return cudaGetLastError();
+}
+
+}  // namespace vqa

@@ -38,6 +38,11 @@ struct GemmParams {
     float* lse_sum;           // [M, num_n_tiles]
     const int* labels;        // [M]
     float* label_logit;       // [M]
+    // batching: `num_batches` independent GEMMs of the same M,N,K share one launch; batch b reads A at
+    // (row + b*a_row_off, k + b*a_k_off), W at (row + b*w_row_off, k + b*w_k_off) and writes C + b*c_batch_stride.
+    int num_batches;
+    int a_row_off, a_k_off, w_row_off, w_k_off;
+    long long c_batch_stride;
     // scheduling
     int num_m_tiles, num_n_tiles, group_m;
 };
@@ -123,12 +128,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tiles_per_batch = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = tiles_per_batch * p.num_batches;
     const int num_workers = gridDim.x / CG;
     const int worker = blockIdx.x / CG;
     const int tiles_per_group = p.group_m * p.num_n_tiles;
 
-    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+    auto tile_coords = [&](int t, int& batch, int& m_blk, int& n_blk) {
+        batch = t / tiles_per_batch;
+        t -= batch * tiles_per_batch;
         int g = t / tiles_per_group;
         int r = t - g * tiles_per_group;
         int m_first = g * p.group_m;
@@ -143,14 +151,16 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = worker; t < num_tiles; t += num_workers) {
-                int m_blk, n_blk;
-                tile_coords(t, m_blk, n_blk);
-                const int m_row = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+                int batch, m_blk, n_blk;
+                tile_coords(t, batch, m_blk, n_blk);
+                const int m_row = (m_blk * CG + (int)cta_rank) * BLOCK_M + batch * p.a_row_off;
+                const int w_row_base = batch * p.w_row_off;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-                    const int k0 = kb * BLOCK_K;
+                    const int k0 = kb * BLOCK_K + batch * p.a_k_off;
+                    const int k0w = kb * BLOCK_K + batch * p.w_k_off;
                     if constexpr (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m_row);
@@ -158,15 +168,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         for (int h = 0; h < 2; ++h) {
                             int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                                 : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
-                            tma_load_2d(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0,
-                                        n_row);
+                            tma_load_2d(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0w,
+                                        n_row + w_row_base);
                         }
                     } else {
                         const int h = (int)cta_rank;
                         int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                             : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
                         tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m_row);
-                        tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0, n_row);
+                        tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0w, n_row + w_row_base);
                         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         else           mbar_arrive_cluster(&full_bar[stage], 0);
                     }
@@ -209,8 +219,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int row_in_tile = q * 32 + lane;
         int it = 0;
         for (int t = worker; t < num_tiles; t += num_workers, ++it) {
-            int m_blk, n_blk;
-            tile_coords(t, m_blk, n_blk);
+            int batch, m_blk, n_blk;
+            tile_coords(t, batch, m_blk, n_blk);
+            const long long c_off = (long long)batch * p.c_batch_stride;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
             mbar_wait(&tmem_full_bar[as], aphase);
@@ -229,7 +240,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     tmem_ld_32x32b_x32(taddr + OUT_COLS + c * 32, u);
                     tmem_ld_wait();
                     if (row_ok) {
-                        __nv_bfloat16* crow = p.C + (size_t)m * p.ldc + n_out0 + c * 32;
+                        __nv_bfloat16* crow = p.C + c_off + (size_t)m * p.ldc + n_out0 + c * 32;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t w[4];
@@ -289,8 +300,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     tmem_ld_wait();
                     const int nc = n0 + c * 32;
                     if (row_ok && nc < p.N) {
-                        __nv_bfloat16* crow = p.C + (size_t)m * p.ldc + nc;
-                        const __nv_bfloat16* rrow = p.residual ? p.residual + (size_t)m * p.ldr + nc : nullptr;
+                        __nv_bfloat16* crow = p.C + c_off + (size_t)m * p.ldc + nc;
+                        const __nv_bfloat16* rrow = p.residual ? p.residual + c_off + (size_t)m * p.ldr + nc : nullptr;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (nc + j * 8 < p.N) {
@@ -378,9 +389,10 @@ inline bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows,
 }
 
 struct GemmLaunch {
-    const __nv_bfloat16* A; int lda;   // [M, K]
-    const __nv_bfloat16* W; int ldw;   // [w_rows, K]
-    int w_rows;                        // rows of W visible to TMA (N, or 2*d_ff for GATED)
+    const __nv_bfloat16* A; int lda;   // [a_rows, a_cols] visible to TMA (defaults: M x K)
+    const __nv_bfloat16* W; int ldw;   // [w_rows, w_cols] visible to TMA (defaults: N x K; 2*d_ff rows for GATED)
+    int w_rows;
+    long long a_rows = 0, a_cols = 0, w_cols = 0;   // 0 = default
     GemmParams p;
 };
 
@@ -395,16 +407,19 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
         attr_set = true;
     }
     CUtensorMap ta, tb;
-    if (!make_tmap_bf16_2d(&ta, g.A, (uint64_t)g.p.M, (uint64_t)g.p.K, (uint64_t)g.lda, Cfg::BLOCK_M))
-        return cudaErrorInvalidValue;
-    if (!make_tmap_bf16_2d(&tb, g.W, (uint64_t)g.w_rows, (uint64_t)g.p.K, (uint64_t)g.ldw, Cfg::B_HALF_ROWS))
+    const uint64_t a_rows = g.a_rows ? (uint64_t)g.a_rows : (uint64_t)g.p.M;
+    const uint64_t a_cols = g.a_cols ? (uint64_t)g.a_cols : (uint64_t)g.p.K;
+    const uint64_t w_cols = g.w_cols ? (uint64_t)g.w_cols : (uint64_t)g.p.K;
+    if (!make_tmap_bf16_2d(&ta, g.A, a_rows, a_cols, (uint64_t)g.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&tb, g.W, (uint64_t)g.w_rows, w_cols, (uint64_t)g.ldw, Cfg::B_HALF_ROWS))
         return cudaErrorInvalidValue;
     GemmParams p = g.p;
+    if (p.num_batches < 1) p.num_batches = 1;
     const int rows_per_tile = Cfg::BLOCK_M * CG;
     p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     p.group_m = max(1, 2048 / rows_per_tile);
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_batches;
     int workers = num_sms / CG;
     if (workers > num_tiles) workers = num_tiles;
     if (workers < 1) workers = 1;

@@ -14,6 +14,7 @@
 #include "gemm_sm100.cuh"
 #include "elementwise.cuh"
 #include "attention.cuh"
+#include "attention_sm100.cuh"
 
 using namespace vqa;
 typedef __nv_bfloat16 bf16;
@@ -34,6 +35,7 @@ struct T5EncLayerW {
 };
 struct T5DecLayerW {
     const bf16 *ln0, *qkv, *o, *ln1, *cq, *ckv, *co, *ln2, *wi, *wo;
+    const bf16* ckT;   // Wk^T [d_model, inner] for the absorbed cross-attention (optional)
 };
 
 struct vqa_handle {
@@ -202,6 +204,24 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
     }
 }
 
+// Batched launch: `nb` independent GEMMs sharing one tensor map per operand (see GemmParams::num_batches).
+struct BatchSpec {
+    int nb; int a_row_off, a_k_off, w_row_off, w_k_off; long long c_stride;
+    long long a_rows, a_cols, w_rows, w_cols;   // full extents visible to TMA
+};
+static cudaError_t run_gemm_batched(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
+                                    const BatchSpec& bs, int variant, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+    GemmLaunch g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = (int)bs.w_rows;
+    g.a_rows = bs.a_rows; g.a_cols = bs.a_cols; g.w_cols = bs.w_cols;
+    memset(&g.p, 0, sizeof(g.p));
+    g.p.M = M; g.p.N = N; g.p.K = K; g.p.C = C; g.p.ldc = ldc;
+    g.p.num_batches = bs.nb; g.p.a_row_off = bs.a_row_off; g.p.a_k_off = bs.a_k_off; g.p.w_row_off = bs.w_row_off;
+    g.p.w_k_off = bs.w_k_off; g.p.c_batch_stride = bs.c_stride;
+    if (launch_counter) ++*launch_counter;
+    return gemm_dispatch_variant<EPI_STORE>(g, variant, num_sms, st);
+}
+
 constexpr int LMHEAD_BN = 128;
 static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
                               float* lse_max, float* lse_sum, float* label_logit, int num_sms, cudaStream_t st,
@@ -241,6 +261,12 @@ static cudaError_t run_flash(const bf16* q, const bf16* k, const bf16* v, int ld
                              int H, const int* seq_lens, const float* bias_table, float scale, int round_scores,
                              cudaStream_t st, int64_t* lc) {
     if (lc) ++*lc;
+    static const bool legacy = env_flag("VQA_ATTN_MMA_SYNC");
+    if (!legacy) {
+        // tcgen05 kernel: q, k, v must be column slices of one packed buffer (they always are on this path)
+        const int q_col0 = 0, k_col0 = (int)(k - q), v_col0 = (int)(v - q);
+        return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, st);
+    }
     FlashParams p;
     p.q = q; p.k = k; p.v = v; p.o = o;
     p.ldq = p.ldk = p.ldv = ldqkv; p.ldo = ldo;
@@ -413,6 +439,8 @@ extern "C" int vqa_finalize_weights(vqa_handle* h) {
         L.cq = need(h, p + "cq", inner, Dm, ok); L.ckv = need(h, p + "ckv", 2 * inner, Dm, ok);
         L.co = need(h, p + "co", Dm, inner, ok); L.ln2 = need(h, p + "ln2", Dm, 1, ok);
         L.wi = need(h, p + "wi", 2 * c.d_ff, Dm, ok); L.wo = need(h, p + "wo", Dm, c.d_ff, ok);
+        L.ckT = nullptr;
+        if (c.cross_attention_mode == 0) L.ckT = need(h, p + "ckT", Dm, inner, ok);
     }
     if (!ok) return VQA_ERR_MISSING_WEIGHT;
     h->finalized = true;
@@ -434,6 +462,7 @@ struct ClipT5Workspace {
     // t5
     size_t x, xn, qkv, attn, ff, bias_table, seq_lens, ckv;
     size_t y, yn, dqkv, dattn, dq, dff;
+    size_t xt, qt, csc, cctx;   // absorbed cross-attention: Xenc^T, q~ = Wk^T q, scores/probs, context sum p.h
     size_t lse_max, lse_sum, label_logit;
     size_t total;
 };
@@ -462,7 +491,18 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     w.ff = pl.take(M * c.d_ff * 2);
     w.bias_table = pl.take((size_t)c.n_heads * (2 * S - 1) * 4);
     w.seq_lens = pl.take((size_t)B * 4);
-    w.ckv = pl.take(M * 2 * inner * 2);
+    const size_t Sp = (size_t)(S + 7) / 8 * 8;
+    const size_t TH = (size_t)T * c.n_heads;
+    if (c.cross_attention_mode == 0) {
+        w.ckv = 0;
+        w.xt = pl.take((size_t)B * c.d_model * Sp * 2);
+        w.qt = pl.take((size_t)B * TH * c.d_model * 2);
+        w.csc = pl.take(((size_t)B * TH + 256) * Sp * 2);
+        w.cctx = pl.take((size_t)B * TH * c.d_model * 2);
+    } else {
+        w.ckv = pl.take(M * 2 * inner * 2);
+        w.xt = w.qt = w.csc = w.cctx = 0;
+    }
     w.y = pl.take(Md * c.d_model * 2);
     w.yn = pl.take(Md * c.d_model * 2);
     w.dqkv = pl.take(Md * 3 * inner * 2);
@@ -621,6 +661,13 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         TRY(gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm, EPI_STORE, 0));
     }
     TRY(rms(P_(w.x), h->enc_final_ln, P_(w.xn), M));  // encoder output lives in xn from here on
+    const int Sp = (S + 7) / 8 * 8;
+    if (c.cross_attention_mode == 0) {
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        ++*lc;
+        transpose_bsd_kernel<<<dim3((Sp + 31) / 32, (Dm + 31) / 32, B), dim3(32, 8), 0, st>>>(P_(w.xn), P_(w.xt), S, Dm, Sp);
+        TRY(cuda_ok(cudaSuccess, "encoder transpose"));
+    }
 
     // ---------------- T5 decoder (T target rows per pair) ----------------
     {
@@ -642,16 +689,43 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
             TRY(cuda_ok(cudaSuccess, "decoder self attention"));
         }
         TRY(gemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
-        // cross-attention: K/V projection of the encoder output (the reference recomputes it in every layer,
-        // modeling_t5.py:297-299)
         TRY(rms(P_(w.y), Lw.ln1, P_(w.yn), Md));
         TRY(gemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
-        TRY(gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
-        {
+        if (c.cross_attention_mode != 0) {
+            // reference association: K/V projection of all S encoder rows in every layer (modeling_t5.py:297-299)
+            TRY(gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * T * S * 64, st);
             ++*lc;
             t5_cross_attn_kernel<8><<<B * H, 128, 0, st>>>(P_(w.dq), P_(w.ckv), P_(w.dattn), seq_lens, 2 * inner, B, T, S, H, rnd);
             TRY(cuda_ok(cudaSuccess, "cross attention"));
+        } else {
+            // absorbed association (exact in real arithmetic; 30x fewer FLOPs because only T rows per pair attend):
+            //   q.(Wk x_s) = (Wk^T q).x_s          sum_s p_s (Wv x_s) = Wv (sum_s p_s x_s)
+            const int TH = T * H;
+            auto bgemm = [&](const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M_, int N_, int K_,
+                             const BatchSpec& bs, int variant) -> int {
+                ProfScope ps(h, CAT_GEMM, 2.0 * bs.nb * (double)M_ * N_ * K_, st);
+                return cuda_ok(run_gemm_batched(A, lda, W, ldw, C, ldc, M_, N_, K_, bs, variant, nsm, st, lc), "batched gemm");
+            };
+            // (1) q~[b,t,h,:] = Wk[h]^T q[b,t,h,:]   -- per head: [B*T, 64] x ckT[:, h*64:(h+1)*64]^T -> rows (b*T+t)*H + h
+            TRY(bgemm(P_(w.dq), inner, Lw.ckT, inner, P_(w.qt), H * Dm, Md, Dm, 64,
+                      BatchSpec{H, 0, 64, 0, 64, (long long)Dm, Md, inner, Dm, inner}, Dm >= 256 ? 2561 : 1281));
+            // (2) scores[b,(t,h),s] = q~[b,(t,h),:] . x[b,s,:]   -- per pair: [T*H, d] x [S, d]^T
+            TRY(bgemm(P_(w.qt), Dm, P_(w.xn), Dm, P_(w.csc), Sp, TH, Sp, Dm,
+                      BatchSpec{B, TH, 0, S, 0, (long long)TH * Sp, (long long)B * TH, Dm, (long long)B * S, Dm}, 1281));
+            {
+                ProfScope ps(h, CAT_ATTENTION, 0, st);
+                ++*lc;
+                cross_softmax_kernel<<<(B * TH + 7) / 8, 256, 0, st>>>(P_(w.csc), seq_lens, TH, B * TH, S, Sp);
+                TRY(cuda_ok(cudaSuccess, "cross softmax"));
+            }
+            // (3) ctx[b,(t,h),:] = sum_s p[b,(t,h),s] x[b,s,:]   -- per pair: [T*H, Sp] x (x[b]^T)[d, Sp]^T
+            TRY(bgemm(P_(w.csc), Sp, P_(w.xt), Sp, P_(w.cctx), Dm, TH, Dm, Sp,
+                      BatchSpec{B, TH, 0, Dm, 0, (long long)TH * Dm, (long long)B * TH, Sp, (long long)B * Dm, Sp},
+                      Dm >= 256 ? 2561 : 1281));
+            // (4) o[b,t,h,:] = Wv[h] ctx[b,t,h,:]   -- per head: [B*T, d] (cols h*d..) x Wv[h*64:(h+1)*64, :]^T -> cols h*64..
+            TRY(bgemm(P_(w.cctx), H * Dm, Lw.ckv + (size_t)inner * Dm, Dm, P_(w.dattn), inner, Md, 64, Dm,
+                      BatchSpec{H, 0, Dm, 64, 0, 64, Md, (long long)H * Dm, inner, Dm}, 641));
         }
         TRY(gemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
         // gated FFN

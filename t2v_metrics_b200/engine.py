@@ -91,6 +91,7 @@ def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device) -
         put(q + "ln1", sd[p + "1.layer_norm.weight"])
         put(q + "cq", sd[c + "q.weight"])
         put(q + "ckv", torch.cat([sd[c + "k.weight"], sd[c + "v.weight"]], dim=0))
+        put(q + "ckT", sd[c + "k.weight"].t())   # Wk^T for the absorbed cross-attention
         put(q + "co", sd[c + "o.weight"])
         put(q + "ln2", sd[p + "2.layer_norm.weight"])
         put(q + "wi", torch.cat([sd[p + "2.DenseReluDense.wi_0.weight"], sd[p + "2.DenseReluDense.wi_1.weight"]], dim=0))
@@ -101,7 +102,8 @@ def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device) -
 class ClipT5Engine:
     """One engine = one model replica on one GPU (one process per GPU)."""
 
-    def __init__(self, cfg: ClipT5Config, device="cuda:0", emulate_bf16_rounding: bool = True):
+    def __init__(self, cfg: ClipT5Config, device="cuda:0", emulate_bf16_rounding: bool = True,
+                 cross_attention_mode: str = "absorbed"):
         if not torch.cuda.is_available():
             raise RuntimeError("ClipT5Engine needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -114,7 +116,8 @@ class ClipT5Engine:
             n_heads=cfg.n_heads, d_ff=cfg.d_ff, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, vocab=cfg.vocab,
             rel_buckets=cfg.rel_buckets, rel_max_distance=cfg.rel_max_distance, t5_ln_eps=cfg.t5_ln_eps,
             image_token_id=IMAGE_TOKEN_INDEX, pad_token_id=cfg.pad_token_id, decoder_start_id=cfg.decoder_start_id,
-            emulate_bf16_rounding=1 if emulate_bf16_rounding else 0)
+            emulate_bf16_rounding=1 if emulate_bf16_rounding else 0,
+            cross_attention_mode={"absorbed": 0, "reference": 1}[cross_attention_mode])
         if cfg.d_kv != 64:
             raise ValueError("the engine's attention kernels are specialised for d_kv == 64")
         self._h = C.c_void_p()

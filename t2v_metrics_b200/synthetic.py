@@ -68,6 +68,7 @@ def synthetic_engine_weights(cfg: ClipT5Config, device, seed: int = 0) -> Dict[s
         nrm(p + "o", Dm, inner, std=inner ** -0.5)
         nrm(p + "cq", inner, Dm, std=(Dm * cfg.d_kv) ** -0.5)
         nrm(p + "ckv", 2 * inner, Dm, std=Dm ** -0.5)
+        out[p + "ckT"] = out[p + "ckv"][:inner].t().contiguous()
         nrm(p + "co", Dm, inner, std=inner ** -0.5)
         nrm(p + "wi", 2 * dff, Dm, std=Dm ** -0.5)
         nrm(p + "wo", Dm, dff, std=dff ** -0.5)

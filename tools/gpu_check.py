@@ -152,6 +152,27 @@ def t_attention():
              ok=bool(mx < 0.03))
 
 
+def t_attention_perf(B=64, S=672, H=64, use_bias=1):
+    from t2v_metrics_b200.engine import ops
+    B, S, H, use_bias = int(B), int(S), int(H), int(use_bias)
+    dev = "cuda:0"
+    qkv = (torch.randn(B * S, 3 * H * 64, device=dev) * 0.5).bfloat16()
+    table = (torch.randn(H, 2 * S - 1, device=dev) * 0.5).contiguous() if use_bias else None
+    scale = 1.0 if use_bias else 0.125
+    for _ in range(3):
+        ops.attention(qkv, B, S, H, bias_table=table, scale=scale)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(10):
+        ops.attention(qkv, B, S, H, bias_table=table, scale=scale)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 10
+    emit(test="attention_perf", B=B, S=S, H=H, bias=use_bias, ms=ms, tflops=4.0 * B * H * S * S * 64 / ms / 1e9,
+         mma_sync=os.environ.get("VQA_ATTN_MMA_SYNC", "0"))
+
+
 def t_lmhead():
     from t2v_metrics_b200.engine import ops
     dev = "cuda:0"
@@ -188,6 +209,7 @@ def t_pipeline(kind="tiny", batch=3):
     labels_ids = (37 % ocfg.vocab, 1)
     sd = orc.make_synthetic_state_dict(ocfg, seed=0, label_ids=labels_ids)
     inp = orc.make_synthetic_inputs(ocfg, batch, L, seed=1, ragged=True, label_ids=labels_ids)
+    orc.calibrate_lm_head(sd, ocfg, inp)
     t0 = time.time()
     ref32 = orc.clipt5_score(sd, ocfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32",
                              return_all=True)
@@ -195,14 +217,15 @@ def t_pipeline(kind="tiny", batch=3):
                              return_all=True)
     t_or = time.time() - t0
     dev = "cuda:0"
-    eng = ClipT5Engine(cfg, dev)
+    eng = ClipT5Engine(cfg, dev, cross_attention_mode=os.environ.get("VQA_CROSS", "absorbed"))
     eng.load_state_dict(sd)
     scores, logp = eng.score_tensors(inp["pixels"].to(dev), inp["input_ids"].to(dev, torch.int32),
                                      inp["text_lens"].to(dev, torch.int32), inp["labels"].to(dev, torch.int32),
                                      return_logprobs=True)
     torch.cuda.synchronize()
     s = scores.cpu()
-    emit(test="pipeline", kind=kind, gemm_simt=os.environ.get("VQA_GEMM_SIMT", "0"),
+    emit(test="pipeline", kind=kind, gemm_simt=os.environ.get("VQA_GEMM_SIMT", "0"), cross=os.environ.get("VQA_CROSS", "absorbed"),
+         attn_mma_sync=os.environ.get("VQA_ATTN_MMA_SYNC", "0"),
          variant=os.environ.get("VQA_GEMM_VARIANT", "auto"),
          scores=[round(float(x), 5) for x in s], ref_fp32=[round(float(x), 5) for x in ref32["scores"]],
          ref_bf16=[round(float(x), 5) for x in ref16["scores"]],
