@@ -136,7 +136,7 @@ int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, int
                      int32_t epilogue, int32_t gate_up_offset, int32_t variant, void* stream);
 
 /* Fused lm_head + log-softmax gather: logprob[m] = (h[m].W[label[m]]) - logsumexp_n(h[m].W[n]); logits never stored.
- * scratch: DEVICE float, >= 2*M*ceil(N/128) + M floats. */
+ * scratch: DEVICE float, >= 4*M*ceil(N/128) + M floats. */
 int vqa_op_lmhead_logprob(const void* H, int32_t ldh, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
                           const int32_t* labels, float* logprob, float* scratch, void* stream);
 

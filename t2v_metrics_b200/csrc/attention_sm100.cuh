@@ -33,7 +33,7 @@ constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf1
 constexpr int AT_BIAS_PAD = 128;
 
 inline size_t attn_tc_smem_bytes(int S) {
-    return 1024 + 5 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 128;
+    return 1024 + 5 * AT_TILE_BYTES + (size_t)(((S + AT_BK - 1) / AT_BK + 1) * AT_BK + AT_BQ) * 4 + 128;
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -45,6 +45,23 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -78,6 +95,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// index into the bias slice for (query row, key 0): rel = key - query + S - 1, slice starts at rel = bias_lo
+__device__ __forceinline__ int row_bias_base(int qrow, int S, int bias_lo) { return (S - 1) - qrow - bias_lo; }
+
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(192, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
@@ -101,8 +121,8 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     uint8_t* sQ = smem;
     uint8_t* sK = smem + AT_TILE_BYTES;          // [2]
     uint8_t* sV = smem + 3 * AT_TILE_BYTES;      // [2]
-    float* sBias = reinterpret_cast<float*>(smem + 5 * AT_TILE_BYTES);   // [2S-1 + 2*PAD], entry i <-> rel = i - PAD
-    const int bias_n = 2 * p.S - 1 + 2 * AT_BIAS_PAD;
+    float* sBias = reinterpret_cast<float*>(smem + 5 * AT_TILE_BYTES);   // [S + 2*128 + slack] slice of the bias table
+    const int bias_n = ((p.S + AT_BK - 1) / AT_BK + 1) * AT_BK + AT_BQ;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
     uint64_t* q_full = bars;          // 1
     uint64_t* kv_full = bars + 1;     // [2]
@@ -130,12 +150,27 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
         tmem_relinquish<1>();
     }
+    // sBias[i] holds bias(rel) * log2(e) for rel = i + bias_lo, the slice of the [2S-1] table this query tile can touch:
+    // rel = key - query + S - 1 with key in [0, nkt*128), query in [q0, q0+127].
+    const int bias_lo = (p.S - 1) - (q0 + AT_BQ - 1);
     if (HAS_BIAS) {
         const float LOG2E = 1.4426950408889634f;
         const int width = 2 * p.S - 1;
-        for (int i = threadIdx.x; i < bias_n; i += blockDim.x) {
-            const int r = i - AT_BIAS_PAD;
-            sBias[i] = (r >= 0 && r < width) ? p.bias_table[(size_t)h * width + r] * LOG2E : 0.f;
+        const int n_slice = min(AT_BQ + nkt * AT_BK, bias_n);
+        const float* src = p.bias_table + (size_t)h * width;
+        for (int i0 = threadIdx.x; i0 < n_slice; i0 += 4 * blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                const int r = i + bias_lo;
+                v[u] = (i < n_slice && r >= 0 && r < width) ? __ldg(src + r) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n_slice) sBias[i] = v[u] * LOG2E;
+            }
         }
     }
     tcgen05_fence_before();
@@ -193,52 +228,72 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         // ===================== softmax / correction / epilogue: one thread per query row =====================
         const uint32_t quad = warp & 3u;
         const int row = quad * 32 + lane;
+        const int qrow = q0 + row;
         const uint32_t lane_off = (quad * 32u) << 16;
+        __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+        if (q0 + (int)quad * 32 >= len) {
+            // every row of this warp is padding: keep the barrier protocol in lock-step, do no math, write zeros
+            for (int j = 0; j < nkt; ++j) {
+                mbar_wait(s_full, (uint32_t)j & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
+                if (j > 0) mbar_wait(p_full, (uint32_t)(j - 1) & 1u);   // previous phase must be closed before arriving again
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            if (qrow < p.S) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(0, 0, 0, 0);
+            }
+        } else {
         float m_run = -INFINITY, l_run = 0.f;
-        const int bias_base = AT_BIAS_PAD + (p.S - 1) - (q0 + row);   // + kcol
+        const int bias_base = row_bias_base(qrow, p.S, bias_lo);   // + kcol
         for (int j = 0; j < nkt; ++j) {
+            const int k0 = j * AT_BK;
+            const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
             mbar_wait(s_full, (uint32_t)j & 1u);
             tcgen05_fence_after();
-            float t[128];
-            {
-                uint32_t v[32];
+            float t[4][32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch) {
+                    uint32_t v[32];
                     tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) t[c * 32 + i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
                 }
             }
-            // S has been copied to registers: hand the TMEM columns back so the next QK^T can start
+            // S is in registers: hand the TMEM columns back so the next QK^T can start
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty);
 
-            const int k0 = j * AT_BK;
-            float tile_max = -INFINITY;
-            if (HAS_BIAS) {
-                const float* bp = sBias + bias_base + k0;
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    t[i] = fmaf(t[i], p.scale_log2e, bp[i]);
-                    tile_max = fmaxf(tile_max, t[i]);
-                }
-            } else {
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch) {
+                    if (HAS_BIAS) {
+                        const float* bp = sBias + bias_base + k0 + c * 32;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    t[i] *= p.scale_log2e;
-                    tile_max = fmaxf(tile_max, t[i]);
+                        for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
+                    }
+                    if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (k0 + c * 32 + i >= len) t[c][i] = -INFINITY;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
+                        mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
+                    }
                 }
             }
-            if (k0 + AT_BK > len) {   // last tile: keys beyond the sample's length
-                tile_max = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    if (k0 + i >= len) t[i] = -INFINITY;
-                    tile_max = fmaxf(tile_max, t[i]);
-                }
-            }
+            const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
             float corr = 1.f;
             bool rescale = false;
@@ -253,37 +308,42 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                     m_run = m_new;
                 }
             }
-            uint32_t pk_lo[32], pk_hi[32];   // bf16 pairs: keys [0,64) and [64,128)
-            float psum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float e0 = fast_exp2(t[2 * i] - m_run);
-                const float e1 = fast_exp2(t[2 * i + 1] - m_run);
-                const float e2 = fast_exp2(t[64 + 2 * i] - m_run);
-                const float e3 = fast_exp2(t[64 + 2 * i + 1] - m_run);
-                psum += (e0 + e1) + (e2 + e3);
-                pk_lo[i] = pack_bf16x2(e0, e1);
-                pk_hi[i] = pack_bf16x2(e2, e3);
-            }
-            l_run = l_run * corr + psum;
-
             if (j > 0) {
                 mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // P_{j-1} consumed, O_{j-1} complete
                 tcgen05_fence_after();
                 if (rescale) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t ov[32];
-                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                    for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
+                        uint32_t ov[16];
+                        tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                        for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                        tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                     }
                 }
             }
-            tmem_st_32x32b_x32(tmem_P + lane_off, pk_lo);
-            tmem_st_32x32b_x32(tmem_P + lane_off + 32, pk_hi);
+            // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
+            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+                if (c < nch) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                        const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
+                        ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+                        pk[i] = pack_bf16x2(e0, e1);
+                        pk[i + 1] = pack_bf16x2(e2, e3);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+                tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+            }
+            l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -292,9 +352,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         // ---- epilogue: O / l
         mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
         tcgen05_fence_after();
-        const int qrow = q0 + row;
         const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-        __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t ov[32];
@@ -312,6 +370,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             }
         }
         tcgen05_fence_before();
+        }
     }
 
     __syncthreads();

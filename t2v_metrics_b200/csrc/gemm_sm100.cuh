@@ -60,7 +60,11 @@ struct GemmConfig {
     static constexpr int SMEM_BUDGET = 200 * 1024;
     static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int NUM_THREADS = 192;       // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+    static constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..9 epilogue
+    // the second epilogue warp group takes half of the 32-column chunks when a tile has at least two of them
+    static constexpr bool EPI_SPLIT = BLOCK_N >= 128;   // >= 2 chunks also for the gated epilogue (BLOCK_N/2 >= 64)
+    static constexpr int EPI_ARRIVALS = EPI_SPLIT ? 8 : 4;
+    static constexpr int LSE_PARTS = EPI_SPLIT ? 2 : 1;
     static constexpr int TMEM_COLS = 2 * BLOCK_N; // two accumulator stages
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(BLOCK_N >= 32 && BLOCK_N <= 256 && (BLOCK_N & (BLOCK_N - 1)) == 0, "BLOCK_N must be 32..256, pow2");
@@ -68,17 +72,19 @@ struct GemmConfig {
     static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float act_gelu_new(float x) {
     // 0.5 * x * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- transformers/activations.py NewGELUActivation
     const float k = 0.7978845608028654f;
-    float inner = k * (x + 0.044715f * x * x * x);
-    return 0.5f * x * (1.0f + tanhf(inner));
+    const float inner = k * (x + 0.044715f * x * x * x);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));   // MUFU.TANH, |err| ~ 2^-11: below the bf16 rounding that follows
+    return 0.5f * x * (1.0f + th);
 }
 
 template <int BLOCK_N, int CG, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmParams p) {
     using Cfg = GemmConfig<BLOCK_N, CG>;
@@ -114,7 +120,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);        // one tcgen05.commit
-            mbar_init(&tmem_empty_bar[s], CG * 4);  // one arrive per epilogue warp (of both CTAs for CG==2)
+            mbar_init(&tmem_empty_bar[s], CG * Cfg::EPI_ARRIVALS);  // one arrive per active epilogue warp (both CTAs)
         }
         fence_barrier_init();
     }
@@ -215,8 +221,17 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
     } else {
         // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
-        const uint32_t q = warp & 3u;                 // TMEM lane quadrant this warp may access
+        // Eight warps: warp w may only touch TMEM lanes 32*(w%4).., so warps {2..5} and {6..9} each cover all four lane
+        // quadrants; the first group drains the first half of the tile's column chunks, the second group the rest.
+        const uint32_t q = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
         const int row_in_tile = q * 32 + lane;
+        constexpr int OUT_TILE_COLS = (EPI == EPI_GATED_GELU) ? BLOCK_N / 2 : BLOCK_N;
+        constexpr int NCH = OUT_TILE_COLS / 32;                    // 32-column chunks per tile
+        constexpr bool SPLIT = Cfg::EPI_SPLIT;
+        constexpr int NCH_PER = SPLIT ? NCH / 2 : NCH;
+        const int c_begin = SPLIT ? (int)half * NCH_PER : 0;
+        if (SPLIT || half == 0) {
         int it = 0;
         for (int t = worker; t < num_tiles; t += num_workers, ++it) {
             int batch, m_blk, n_blk;
@@ -224,20 +239,19 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const long long c_off = (long long)batch * p.c_batch_stride;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tcgen05_fence_after();
             const int m = (m_blk * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
             const bool row_ok = m < p.M;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
 
             if constexpr (EPI == EPI_GATED_GELU) {
-                constexpr int OUT_COLS = BLOCK_N / 2;
-                const int n_out0 = n_blk * OUT_COLS;
+                const int n_out0 = n_blk * OUT_TILE_COLS;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tcgen05_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < OUT_COLS / 32; ++c) {
+                for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(taddr + c * 32, g);
-                    tmem_ld_32x32b_x32(taddr + OUT_COLS + c * 32, u);
+                    tmem_ld_32x32b_x32(taddr + OUT_TILE_COLS + c * 32, u);
                     tmem_ld_wait();
                     if (row_ok) {
                         __nv_bfloat16* crow = p.C + c_off + (size_t)m * p.ldc + n_out0 + c * 32;
@@ -263,8 +277,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const int n0 = n_blk * BLOCK_N;
                 const int label = row_ok ? p.labels[m] : -1;
                 float run_max = -INFINITY, run_sum = 0.f;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tcgen05_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c * 32, v);
                     tmem_ld_wait();
@@ -280,38 +296,59 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                     if (cmax > -INFINITY) {
                         const float new_max = fmaxf(run_max, cmax);
-                        float s = 0.f;
+                        float sacc = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) s += __expf(x[j] - new_max);
-                        run_sum = run_sum * __expf(run_max - new_max) + s;
+                        for (int j = 0; j < 32; ++j) sacc += __expf(x[j] - new_max);
+                        run_sum = run_sum * __expf(run_max - new_max) + sacc;
                         run_max = new_max;
                     }
                 }
                 if (row_ok) {
-                    p.lse_max[(size_t)m * p.num_n_tiles + n_blk] = run_max;
-                    p.lse_sum[(size_t)m * p.num_n_tiles + n_blk] = run_sum;
+                    // one partial per (row, n tile, column half): Cfg::LSE_PARTS partials per tile
+                    const size_t slot = ((size_t)m * p.num_n_tiles + n_blk) * Cfg::LSE_PARTS + (SPLIT ? half : 0);
+                    p.lse_max[slot] = run_max;
+                    p.lse_sum[slot] = run_sum;
                 }
             } else {
                 const int n0 = n_blk * BLOCK_N;
+                // Bias and residual for the FIRST chunk are requested before waiting for the accumulator, and the next
+                // chunk's while the current one is being converted, so their L2 latency overlaps the TMEM traffic.
+                uint4 bq[4], rq[4];
+                auto prefetch = [&](int c) {
+                    const int nc = n0 + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = (nc + j * 8) < p.N;
+                        bq[j] = (p.bias && ok) ? __ldg(reinterpret_cast<const uint4*>(p.bias + nc + j * 8)) : make_uint4(0, 0, 0, 0);
+                        rq[j] = (p.residual && ok && row_ok)
+                                    ? *reinterpret_cast<const uint4*>(p.residual + c_off + (size_t)m * p.ldr + nc + j * 8)
+                                    : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                prefetch(c_begin);
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tcgen05_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    uint4 bcur[4], rcur[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { bcur[j] = bq[j]; rcur[j] = rq[j]; }
+                    if (c + 1 < c_begin + NCH_PER) prefetch(c + 1);
                     tmem_ld_wait();
                     const int nc = n0 + c * 32;
                     if (row_ok && nc < p.N) {
                         __nv_bfloat16* crow = p.C + c_off + (size_t)m * p.ldc + nc;
-                        const __nv_bfloat16* rrow = p.residual ? p.residual + c_off + (size_t)m * p.ldr + nc : nullptr;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (nc + j * 8 < p.N) {
                                 float f[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
-                                if (p.bias) {
-                                    uint4 bq = __ldg(reinterpret_cast<const uint4*>(p.bias + nc + j * 8));
-                                    float2 b0 = unpack_bf16x2(bq.x), b1 = unpack_bf16x2(bq.y);
-                                    float2 b2 = unpack_bf16x2(bq.z), b3 = unpack_bf16x2(bq.w);
+                                {
+                                    float2 b0 = unpack_bf16x2(bcur[j].x), b1 = unpack_bf16x2(bcur[j].y);
+                                    float2 b2 = unpack_bf16x2(bcur[j].z), b3 = unpack_bf16x2(bcur[j].w);
                                     f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
                                     f[4] += b2.x; f[5] += b2.y; f[6] += b3.x; f[7] += b3.y;
                                 }
@@ -323,10 +360,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                     if constexpr (EPI == EPI_RELU) y = fmaxf(y, 0.f);
                                     f[e] = y;
                                 }
-                                if (rrow) {
-                                    uint4 rq = *reinterpret_cast<const uint4*>(rrow + j * 8);
-                                    float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y);
-                                    float2 r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+                                {
+                                    float2 r0 = unpack_bf16x2(rcur[j].x), r1 = unpack_bf16x2(rcur[j].y);
+                                    float2 r2 = unpack_bf16x2(rcur[j].z), r3 = unpack_bf16x2(rcur[j].w);
                                     f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
                                     f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
                                 }
@@ -345,6 +381,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
                 else                   mbar_arrive_cluster(&tmem_empty_bar[as], 0);
             }
+        }
         }
     }
 

@@ -223,6 +223,7 @@ static cudaError_t run_gemm_batched(const bf16* A, int lda, const bf16* W, int l
 }
 
 constexpr int LMHEAD_BN = 128;
+constexpr int LMHEAD_PARTS = GemmConfig<LMHEAD_BN, 1>::LSE_PARTS;   // (max, sum) partials per (row, n tile)
 static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
                               float* lse_max, float* lse_sum, float* label_logit, int num_sms, cudaStream_t st,
                               int64_t* launch_counter) {
@@ -509,7 +510,7 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     w.dattn = pl.take(Md * inner * 2);
     w.dq = pl.take(Md * inner * 2);
     w.dff = pl.take(Md * c.d_ff * 2);
-    const size_t ntiles = (c.vocab + LMHEAD_BN - 1) / LMHEAD_BN;
+    const size_t ntiles = (size_t)LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
     w.lse_max = pl.take(Md * ntiles * 4);
     w.lse_sum = pl.take(Md * ntiles * 4);
     w.label_logit = pl.take(Md * 4);
@@ -740,7 +741,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     float* lse_max = reinterpret_cast<float*>(ws + w.lse_max);
     float* lse_sum = reinterpret_cast<float*>(ws + w.lse_sum);
     float* label_logit = reinterpret_cast<float*>(ws + w.label_logit);
-    const int ntiles = (c.vocab + LMHEAD_BN - 1) / LMHEAD_BN;
+    const int ntiles = LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
     {
         ProfScope ps(h, CAT_GEMM, 2.0 * Md * (double)c.vocab * Dm, st);
         TRY(cuda_ok(run_lmhead(P_(w.yn), Dm, h->lm_head, Dm, Md, c.vocab, Dm, labels, lse_max, lse_sum, label_logit, nsm, st, lc),
@@ -816,7 +817,7 @@ extern "C" int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32
 extern "C" int vqa_op_lmhead_logprob(const void* Hs, int32_t ldh, const void* W, int32_t ldw, int32_t M, int32_t N,
                                      int32_t K, const int32_t* labels, float* logprob, float* scratch, void* stream) {
     if (!Hs || !W || !labels || !logprob || !scratch) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
-    const int ntiles = (N + LMHEAD_BN - 1) / LMHEAD_BN;
+    const int ntiles = LMHEAD_PARTS * ((N + LMHEAD_BN - 1) / LMHEAD_BN);
     float* lse_max = scratch;
     float* lse_sum = scratch + (size_t)M * ntiles;
     float* label_logit = scratch + 2 * (size_t)M * ntiles;

@@ -241,7 +241,7 @@ class ops:
         M, K = h.shape
         N = w.shape[0]
         ntiles = (N + 127) // 128
-        scratch = torch.empty(2 * M * ntiles + M, dtype=torch.float32, device=h.device)
+        scratch = torch.empty(4 * M * ntiles + M, dtype=torch.float32, device=h.device)
         out = torch.empty(M, dtype=torch.float32, device=h.device)
         rc = lib.vqa_op_lmhead_logprob(_ptr(h), h.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(labels), _ptr(out),
                                        _ptr(scratch), _stream_ptr(h.device))
