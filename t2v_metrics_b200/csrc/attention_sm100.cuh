@@ -33,7 +33,7 @@ constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf1
 constexpr int AT_BIAS_PAD = 128;
 
 inline size_t attn_tc_smem_bytes(int S) {
-    return 1024 + 5 * AT_TILE_BYTES + (size_t)(((S + AT_BK - 1) / AT_BK + 1) * AT_BK + AT_BQ) * 4 + 128;
+    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -95,81 +95,85 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-// index into the bias slice for (query row, key 0): rel = key - query + S - 1, slice starts at rel = bias_lo
-__device__ __forceinline__ int row_bias_base(int qrow, int S, int bias_lo) { return (S - 1) - qrow - bias_lo; }
-
+// One CTA owns one (sample, head) and walks its 128-row query tiles back to back: TMEM allocation, barrier set-up and the
+// bias table are paid once, and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered),
+// so only the very first tile of a CTA sees the full HBM/L2 latency.
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(192, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qt * AT_BQ;
+    const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const size_t row_base = (size_t)b * p.S;
+    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
+    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
 
-    if (q0 >= len) {  // fully padded query tile: deterministic zeros, no TMEM/barrier set-up
-        for (int i = threadIdx.x; i < AT_BQ * 8; i += blockDim.x) {
-            const int r = i >> 3, c = i & 7;
-            if (q0 + r < p.S)
-                *reinterpret_cast<uint4*>(p.o + (row_base + q0 + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
-        }
-        return;
+    // rows past the last valid query tile: deterministic zeros
+    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
+        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
+        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
     }
+    if (nq == 0) return;
 
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + AT_TILE_BYTES;          // [2]
-    uint8_t* sV = smem + 3 * AT_TILE_BYTES;      // [2]
-    float* sBias = reinterpret_cast<float*>(smem + 5 * AT_TILE_BYTES);   // [S + 2*128 + slack] slice of the bias table
-    const int bias_n = ((p.S + AT_BK - 1) / AT_BK + 1) * AT_BK + AT_BQ;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
-    uint64_t* q_full = bars;          // 1
-    uint64_t* kv_full = bars + 1;     // [2]
-    uint64_t* kv_empty = bars + 3;    // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_empty = bars + 6;
-    uint64_t* p_full = bars + 7;
-    uint64_t* o_done = bars + 8;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-
-    const int nkt = (len + AT_BK - 1) / AT_BK;
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
+    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
+    float* sBias = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES);   // entry i <-> rel = i - AT_BIAS_PAD, rel = key - query + S - 1
+    const int bias_n = 2 * p.S - 1 + 2 * AT_BIAS_PAD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
+    uint64_t* q_full = bars;          // [2]
+    uint64_t* q_empty = bars + 2;     // [2]
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
-        mbar_init(q_full, 1);
-        mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
-        mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+        }
         mbar_init(s_full, 1);
         mbar_init(s_empty, 4);
         mbar_init(p_full, 4);
         mbar_init(o_done, 1);
+        mbar_init(o_free, 4);
         fence_barrier_init();
+        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
+        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
+        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
+        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
+        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
     }
     if (warp == 1) {
         tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
         tmem_relinquish<1>();
     }
-    // sBias[i] holds bias(rel) * log2(e) for rel = i + bias_lo, the slice of the [2S-1] table this query tile can touch:
-    // rel = key - query + S - 1 with key in [0, nkt*128), query in [q0, q0+127].
-    const int bias_lo = (p.S - 1) - (q0 + AT_BQ - 1);
     if (HAS_BIAS) {
         const float LOG2E = 1.4426950408889634f;
         const int width = 2 * p.S - 1;
-        const int n_slice = min(AT_BQ + nkt * AT_BK, bias_n);
         const float* src = p.bias_table + (size_t)h * width;
-        for (int i0 = threadIdx.x; i0 < n_slice; i0 += 4 * blockDim.x) {
+        for (int i0 = threadIdx.x; i0 < bias_n; i0 += 4 * blockDim.x) {
             float v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * blockDim.x;
-                const int r = i + bias_lo;
-                v[u] = (i < n_slice && r >= 0 && r < width) ? __ldg(src + r) : 0.f;
+                const int r = i - AT_BIAS_PAD;
+                v[u] = (i < bias_n && r >= 0 && r < width) ? __ldg(src + r) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * blockDim.x;
-                if (i < n_slice) sBias[i] = v[u] * LOG2E;
+                if (i < bias_n) sBias[i] = v[u] * LOG2E;
             }
         }
     }
@@ -178,18 +182,27 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-            tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col0 + h * AT_D, (int)(row_base + q0));
-            for (int j = 0; j < nkt; ++j) {
-                const int st = j & 1;
-                mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
-                tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
-                tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                if (qi > 0) {   // (tile 0 was issued during set-up)
+                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+                }
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    if (g == 0) continue;
+                    const int st = g & 1;
+                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                }
             }
         }
     } else if (warp == 1) {
@@ -197,180 +210,199 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
             constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
-            const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ));
-            auto issue_pv = [&](int i) {
-                mbar_wait(p_full, (uint32_t)i & 1u);
+            auto issue_pv = [&](int g) {
+                const int j = g % nkt, qi = g / nkt;
+                mbar_wait(p_full, (uint32_t)g & 1u);
+                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
                 tcgen05_fence_after();
-                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (i & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < AT_BK / 16; ++ks)
                     umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
-                                (i > 0 || ks > 0) ? 1u : 0u);
-                umma_commit<1>(&kv_empty[i & 1]);
+                                (j > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[g & 1]);
                 umma_commit<1>(o_done);
             };
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < nkt; ++j) {
-                const int st = j & 1;
-                mbar_wait(&kv_full[st], ((uint32_t)j >> 1) & 1u);
-                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
-                tcgen05_fence_after();
-                const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
+                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    const int st = g & 1;
+                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
+                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k)
-                    umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit<1>(s_full);
-                if (j > 0) issue_pv(j - 1);
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit<1>(s_full);
+                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
+                    if (g > 0) issue_pv(g - 1);
+                }
             }
-            issue_pv(nkt - 1);
+            issue_pv(total_tiles - 1);
         }
     } else {
         // ===================== softmax / correction / epilogue: one thread per query row =====================
         const uint32_t quad = warp & 3u;
         const int row = quad * 32 + lane;
-        const int qrow = q0 + row;
         const uint32_t lane_off = (quad * 32u) << 16;
-        __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
-        if (q0 + (int)quad * 32 >= len) {
-            // every row of this warp is padding: keep the barrier protocol in lock-step, do no math, write zeros
-            for (int j = 0; j < nkt; ++j) {
-                mbar_wait(s_full, (uint32_t)j & 1u);
+        int g = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q0 = qi * AT_BQ;
+            const int qrow = q0 + row;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+            if (q0 + (int)quad * 32 >= len) {
+                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
+                for (int j = 0; j < nkt; ++j, ++g) {
+                    mbar_wait(s_full, (uint32_t)g & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full);
+                }
+                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            float m_run = -INFINITY, l_run = 0.f;
+            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow;   // + kcol
+            for (int j = 0; j < nkt; ++j, ++g) {
+                const int k0 = j * AT_BK;
+                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
+                mbar_wait(s_full, (uint32_t)g & 1u);
+                tcgen05_fence_after();
+                float t[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
+                    }
+                }
+                // S is in registers: hand the TMEM columns back so the next QK^T can start
+                tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);
-                if (j > 0) mbar_wait(p_full, (uint32_t)(j - 1) & 1u);   // previous phase must be closed before arriving again
+
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        if (HAS_BIAS) {
+                            const float* bp = sBias + bias_base + k0 + c * 32;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
+                        }
+                        if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (k0 + c * 32 + i >= len) t[c][i] = -INFINITY;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
+                            mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
+                        }
+                    }
+                }
+                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
+                float corr = 1.f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_run = tile_max;
+                } else {
+                    const bool need = tile_max > m_run + 8.f;
+                    rescale = __any_sync(0xffffffffu, need);
+                    if (rescale) {
+                        const float m_new = fmaxf(m_run, tile_max);
+                        corr = fast_exp2(m_run - m_new);
+                        m_run = m_new;
+                    }
+                }
+                if (j > 0) {
+                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                    tcgen05_fence_after();
+                    if (rescale) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                        }
+                    }
+                }
+                // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
+                float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+                    if (c < nch) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                            const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
+                            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+                            pk[i] = pack_bf16x2(e0, e1);
+                            pk[i + 1] = pack_bf16x2(e2, e3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    }
+                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                }
+                l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
+                tmem_st_wait();
+                tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
-            if (qrow < p.S) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(0, 0, 0, 0);
-            }
-        } else {
-        float m_run = -INFINITY, l_run = 0.f;
-        const int bias_base = row_bias_base(qrow, p.S, bias_lo);   // + kcol
-        for (int j = 0; j < nkt; ++j) {
-            const int k0 = j * AT_BK;
-            const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
-            mbar_wait(s_full, (uint32_t)j & 1u);
+            // ---- epilogue of this query tile: O / l
+            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
             tcgen05_fence_after();
-            float t[4][32];
+            const float inv = (qrow < len) ? 1.f / l_run : 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < nch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_wait();
+                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_free);
                 }
-            }
-            // S is in registers: hand the TMEM columns back so the next QK^T can start
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
-
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                if (qrow < p.S) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < nch) {
-                    if (HAS_BIAS) {
-                        const float* bp = sBias + bias_base + k0 + c * 32;
+                    for (int gq = 0; gq < 4; ++gq) {
+                        uint32_t w[4];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                    if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (k0 + c * 32 + i >= len) t[c][i] = -INFINITY;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
-                        mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
-                    }
-                }
-            }
-            const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
-            float corr = 1.f;
-            bool rescale = false;
-            if (j == 0) {
-                m_run = tile_max;
-            } else {
-                const bool need = tile_max > m_run + 8.f;
-                rescale = __any_sync(0xffffffffu, need);
-                if (rescale) {
-                    const float m_new = fmaxf(m_run, tile_max);
-                    corr = fast_exp2(m_run - m_new);
-                    m_run = m_new;
-                }
-            }
-            if (j > 0) {
-                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // P_{j-1} consumed, O_{j-1} complete
-                tcgen05_fence_after();
-                if (rescale) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
-                        uint32_t ov[16];
-                        tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                        tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                    }
-                }
-            }
-            // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
-            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t pk[16];
-                if (c < nch) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
-                        const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
-                        ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-                        pk[i] = pack_bf16x2(e0, e1);
-                        pk[i + 1] = pack_bf16x2(e2, e3);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
-                }
-                tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-            }
-            l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
-            tmem_st_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // ---- epilogue: O / l
-        mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
-        tcgen05_fence_after();
-        const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-            tmem_ld_wait();
-            if (qrow < p.S) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        w[e] = pack_bf16x2(__uint_as_float(ov[g * 8 + 2 * e]) * inv, __uint_as_float(ov[g * 8 + 2 * e + 1]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
         tcgen05_fence_before();
-        }
     }
 
     __syncthreads();
@@ -397,7 +429,7 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         if (e != cudaSuccess) return e;
         max_set[which] = smem;
     }
-    dim3 grid((S + AT_BQ - 1) / AT_BQ, H, B);
+    dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
     if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
     else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
     return cudaGetLastError();

@@ -23,7 +23,9 @@ enum GemmEpilogue : int {
     EPI_GATED_GELU = 3,  // C = gelu_new(bf16(acc_gate)) * bf16(acc_up)      (T5 DenseGatedActDense wi_0/wi_1)
     EPI_LSE = 4,         // no C; per-row (max, sum exp) partials + label-logit gather (lm_head + CE)
     EPI_RELU = 5,        // C = relu(bf16(acc + bias))
+    EPI_GATED_SILU = 6,  // C = silu(bf16(acc_gate + b_gate)) * bf16(acc_up + b_up)   (Qwen2.5-VL SwiGLU MLPs)
 };
+__host__ __device__ constexpr bool epi_is_gated(int epi) { return epi == EPI_GATED_GELU || epi == EPI_GATED_SILU; }
 
 struct GemmParams {
     int M, N, K;              // N = number of OUTPUT columns of the logical GEMM (for GATED: 2 * out columns)
@@ -73,6 +75,7 @@ struct GemmConfig {
 };
 
 __device__ __forceinline__ float act_quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float act_gelu_new(float x) {
     // 0.5 * x * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- transformers/activations.py NewGELUActivation
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(320, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmParams p) {
     using Cfg = GemmConfig<BLOCK_N, CG>;
-    static_assert(EPI != EPI_GATED_GELU || BLOCK_N >= 64, "gated epilogue pairs two >=32-column half tiles");
+    static_assert(!epi_is_gated(EPI) || BLOCK_N >= 64, "gated epilogue pairs two >=32-column half tiles");
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BLOCK_M = Cfg::BLOCK_M;
     constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -172,14 +175,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m_row);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
+                            int n_row = epi_is_gated(EPI) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                                 : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
                             tma_load_2d(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0w,
                                         n_row + w_row_base);
                         }
                     } else {
                         const int h = (int)cta_rank;
-                        int n_row = (EPI == EPI_GATED_GELU) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
+                        int n_row = epi_is_gated(EPI) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                             : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
                         tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m_row);
                         tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0w, n_row + w_row_base);
@@ -226,7 +229,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const uint32_t q = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;
         const int row_in_tile = q * 32 + lane;
-        constexpr int OUT_TILE_COLS = (EPI == EPI_GATED_GELU) ? BLOCK_N / 2 : BLOCK_N;
+        constexpr int OUT_TILE_COLS = epi_is_gated(EPI) ? BLOCK_N / 2 : BLOCK_N;
         constexpr int NCH = OUT_TILE_COLS / 32;                    // 32-column chunks per tile
         constexpr bool SPLIT = Cfg::EPI_SPLIT;
         constexpr int NCH_PER = SPLIT ? NCH / 2 : NCH;
@@ -243,7 +246,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const bool row_ok = m < p.M;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
 
-            if constexpr (EPI == EPI_GATED_GELU) {
+            if constexpr (epi_is_gated(EPI)) {
                 const int n_out0 = n_blk * OUT_TILE_COLS;
                 mbar_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
@@ -260,12 +263,25 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             uint32_t w[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                float g0 = bf16_round(__uint_as_float(g[j * 8 + 2 * e]));
-                                float g1 = bf16_round(__uint_as_float(g[j * 8 + 2 * e + 1]));
-                                float u0 = bf16_round(__uint_as_float(u[j * 8 + 2 * e]));
-                                float u1 = bf16_round(__uint_as_float(u[j * 8 + 2 * e + 1]));
-                                float h0 = bf16_round(act_gelu_new(g0)) * u0;
-                                float h1 = bf16_round(act_gelu_new(g1)) * u1;
+                                float g0 = __uint_as_float(g[j * 8 + 2 * e]), g1 = __uint_as_float(g[j * 8 + 2 * e + 1]);
+                                float u0 = __uint_as_float(u[j * 8 + 2 * e]), u1 = __uint_as_float(u[j * 8 + 2 * e + 1]);
+                                if (p.bias) {   // [gate bias | up bias], `gate_up_offset` apart like the weight rows
+                                    const int n = n_out0 + c * 32 + j * 8 + 2 * e;
+                                    if (n < p.N / 2) {
+                                        const float2 bg = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.bias + n));
+                                        const float2 bu = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.bias + p.gate_up_offset + n));
+                                        g0 += bg.x; g1 += bg.y; u0 += bu.x; u1 += bu.y;
+                                    }
+                                }
+                                g0 = bf16_round(g0); g1 = bf16_round(g1); u0 = bf16_round(u0); u1 = bf16_round(u1);
+                                float h0, h1;
+                                if constexpr (EPI == EPI_GATED_GELU) {
+                                    h0 = bf16_round(act_gelu_new(g0)) * u0;
+                                    h1 = bf16_round(act_gelu_new(g1)) * u1;
+                                } else {
+                                    h0 = bf16_round(act_silu(g0)) * u0;
+                                    h1 = bf16_round(act_silu(g1)) * u1;
+                                }
                                 w[e] = pack_bf16x2(h0, h1);
                             }
                             if (n_out0 + c * 32 + j * 8 < p.N / 2)

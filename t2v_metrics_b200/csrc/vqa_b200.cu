@@ -111,7 +111,7 @@ static int fail(vqa_handle* h, int code, const std::string& msg) {
 // One thread per output element; used only when VQA_GEMM_SIMT=1 (bring-up aid to separate pipeline bugs from
 // tensor-core bugs). Same epilogue semantics as the tcgen05 kernel.
 __global__ void gemm_simt_debug_kernel(const bf16* A, int lda, const bf16* W, int ldw, GemmParams p, int epi) {
-    const int n_out = (epi == EPI_GATED_GELU) ? p.N / 2 : p.N;
+    const int n_out = epi_is_gated(epi) ? p.N / 2 : p.N;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)p.M * n_out) return;
     const int m = (int)(idx / n_out), n = (int)(idx % n_out);
@@ -121,10 +121,12 @@ __global__ void gemm_simt_debug_kernel(const bf16* A, int lda, const bf16* W, in
         for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
         return acc;
     };
-    if (epi == EPI_GATED_GELU) {
-        float g = bf16_round(dot(W + (size_t)n * ldw));
-        float u = bf16_round(dot(W + (size_t)(p.gate_up_offset + n) * ldw));
-        p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(bf16_round(act_gelu_new(g)) * u);
+    if (epi_is_gated(epi)) {
+        float g = dot(W + (size_t)n * ldw), u = dot(W + (size_t)(p.gate_up_offset + n) * ldw);
+        if (p.bias) { g += __bfloat162float(p.bias[n]); u += __bfloat162float(p.bias[p.gate_up_offset + n]); }
+        g = bf16_round(g); u = bf16_round(u);
+        const float a = (epi == EPI_GATED_GELU) ? act_gelu_new(g) : act_silu(g);
+        p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(bf16_round(a) * u);
         return;
     }
     float acc = dot(W + (size_t)n * ldw);
@@ -156,7 +158,7 @@ static cudaError_t gemm_dispatch_variant(const GemmLaunch& g, int variant, int n
         case 1281: return launch_gemm_t<128, 1, EPI>(g, num_sms, st);
         case 641:  return launch_gemm_t<64, 1, EPI>(g, num_sms, st);
         case 321:
-            if constexpr (EPI == EPI_GATED_GELU) return cudaErrorInvalidValue;
+            if constexpr (epi_is_gated(EPI)) return cudaErrorInvalidValue;
             else return launch_gemm_t<32, 1, EPI>(g, num_sms, st);
         default:   return cudaErrorInvalidValue;
     }
@@ -168,7 +170,7 @@ static int pick_variant(int M, int N, int epi) {
     if (M <= 128) {
         // skinny (decoder rows): pure weight streaming; favour many CTAs. The gated epilogue pairs two half tiles of
         // BLOCK_N/2 >= 32 columns, so it needs BLOCK_N >= 64.
-        if (epi == EPI_GATED_GELU) return N <= 16384 ? 641 : 1281;
+        if (epi_is_gated(epi)) return N <= 16384 ? 641 : 1281;
         if (N <= 4096) return 321;
         if (N <= 12288) return 641;
         return 1281;
@@ -189,7 +191,7 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
     if (launch_counter) ++*launch_counter;
     static const bool simt = env_flag("VQA_GEMM_SIMT");
     if (simt) {
-        const long total = (long)M * ((epi == EPI_GATED_GELU) ? N / 2 : N);
+        const long total = (long)M * (epi_is_gated(epi) ? N / 2 : N);
         gemm_simt_debug_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, lda, W, ldw, g.p, epi);
         return cudaGetLastError();
     }
@@ -200,6 +202,7 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
         case EPI_GELU_ERF:   return gemm_dispatch_variant<EPI_GELU_ERF>(g, variant, num_sms, st);
         case EPI_GATED_GELU: return gemm_dispatch_variant<EPI_GATED_GELU>(g, variant, num_sms, st);
         case EPI_RELU:       return gemm_dispatch_variant<EPI_RELU>(g, variant, num_sms, st);
+        case EPI_GATED_SILU: return gemm_dispatch_variant<EPI_GATED_SILU>(g, variant, num_sms, st);
         default:             return cudaErrorInvalidValue;
     }
 }
