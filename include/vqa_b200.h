@@ -77,6 +77,30 @@ typedef struct {
     int32_t dtype;     /* vqa_dtype; weights must be VQA_DTYPE_BF16 */
 } vqa_tensor;
 
+/* Qwen2.5-VL architecture description (vision tower + language model; transformers/models/qwen2_5_vl/
+ * configuration_qwen2_5_vl.py:51-64,106-125; 7B values in comments). The vision tower's 80-wide heads are laid out
+ * zero-padded to 128 columns per head in the fused qkv / proj weights, and its MLP width is padded to a multiple of 128
+ * (both done by the host when it fuses the checkpoint tensors, engine.convert_qwen_state_dict). */
+typedef struct {
+    int32_t vit_depth;        /* 32 */
+    int32_t vit_hidden;       /* 1280 */
+    int32_t vit_heads;        /* 16 */
+    int32_t vit_head_dim;     /* 80 (real head width; stored padded to 128) */
+    int32_t vit_mlp;          /* 3420 (stored padded to 3456) */
+    int32_t patch_dim;        /* 3 * temporal_patch(2) * 14 * 14 = 1176 */
+    int32_t spatial_merge;    /* 2 */
+    int32_t out_hidden;       /* 3584 */
+    uint64_t fullatt_mask;    /* bit l set: vision block l attends over whole frames (7,15,23,31), else 112-px windows */
+    int32_t hidden;           /* 3584 */
+    int32_t layers;           /* 28 */
+    int32_t heads;            /* 28 (head_dim must be 128) */
+    int32_t kv_heads;         /* 4 */
+    int32_t mlp;              /* 18944 */
+    int32_t vocab;            /* 152064 */
+    float   rms_eps;          /* 1e-6 */
+    int32_t emulate_bf16_rounding;
+} vqa_qwen25vl_config;
+
 typedef struct vqa_handle vqa_handle;
 
 /* ABI / build info ("vqa_b200 abi=1 sm_100a ..."). Never fails. */
@@ -113,6 +137,38 @@ int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel_dtype, int
                      const int32_t* labels, int32_t batch, int32_t text_len, int32_t label_len, float* out_scores,
                      float* out_logprobs, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Qwen2.5-VL (replaces Qwen2VLModel.forward's per-sample generate(max_new_tokens=1, output_scores=True) +
+ * softmax(scores / T)[answer_id], t2v_metrics/models/vqascore_models/qwen2vl_model.py:160-167,190-289) ---- */
+int vqa_create_qwen25vl(const vqa_qwen25vl_config* cfg, int device, vqa_handle** out);
+
+/* Rotary metadata (HOST arrays, copied): for frequency index i < n_half the rotation angle of a token is
+ * position[axis[i]] * inv_freq[i]. Text: n_half = 64, axis = mrope sections (t,h,w) (modeling_qwen2_5_vl.py:650-662),
+ * inv_freq = rope_theta^(-2i/128). Vision: n_half = head_dim/2 = 40, axis = [h]*20 + [w]*20, inv_freq = 10000^(-2i/40). */
+int vqa_qwen25vl_set_rope(vqa_handle* h, const float* text_inv_freq, const int32_t* text_axis, int32_t text_half,
+                          const float* vis_inv_freq, const int32_t* vis_axis, int32_t vis_half);
+
+size_t vqa_qwen25vl_workspace_bytes(vqa_handle* h, int32_t batch, int32_t seq_len, int32_t n_patches);
+
+/* Score `batch` prompts in one prefill. All index arrays are DEVICE int32 and are produced by the host's mirror of the
+ * reference's index logic (rot_pos_emb :382-409, get_window_index :411-451, get_rope_index :1024-1133):
+ *   pixel_patches  [n_patches, patch_dim] (F32 or BF16), all images concatenated, processor (merge-block) order
+ *   vis_pos_hw     [2, n_patches]  (h, w) index of every patch, already in WINDOW order
+ *   window_index   [n_patches / merge^2]  window order of the 2x2 patch groups;  reverse_index = argsort(window_index)
+ *   cu_window      [n_windows + 1], cu_frames [n_frames + 1]  cumulative patch counts (window order)
+ *   input_ids      [batch, seq_len] right-padded; seq_lens [batch]
+ *   feat_index     [batch, seq_len] row of the merged vision features for image-token positions, -1 elsewhere
+ *   position_ids   [3, batch*seq_len] (t, h, w) mRoPE positions
+ *   answer_ids     [batch] the answer's first token id
+ *   out_probs      [batch] softmax(last-position logits / temperature)[answer_id]; out_logprobs optional
+ */
+int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int32_t pixel_dtype, int32_t n_patches,
+                       const int32_t* vis_pos_hw, const int32_t* window_index, const int32_t* reverse_index,
+                       const int32_t* cu_window, int32_t n_windows, int32_t max_window_len, const int32_t* cu_frames,
+                       int32_t n_frames, int32_t max_frame_len, const int32_t* input_ids, const int32_t* seq_lens,
+                       const int32_t* feat_index, const int32_t* position_ids, const int32_t* answer_ids, int32_t batch,
+                       int32_t seq_len, float temperature, float* out_probs, float* out_logprobs, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last vqa_clipt5_score call launched (for bench.py's gpu_launches). */
 int64_t vqa_last_launch_count(vqa_handle* h);
 
@@ -148,6 +204,12 @@ int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32
 /* T5LayerNorm / nn.LayerNorm on [rows, D] bf16. beta == NULL selects T5 RMS norm. */
 int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,
                 void* stream);
+
+/* head_dim-128 attention on a packed buffer [rows, ld]: q heads at q_col0 + h*128, k/v heads at k_col0/v_col0 + (h/kv_group)*128.
+ * cu_seqlens [n_seq+1] (variable-length sequences) or NULL with fixed stride S and optional seq_lens [n_seq]. */
+int vqa_op_attention_d128(const void* qkv, int32_t ld, int64_t rows, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out,
+                          int32_t ldo, int32_t n_seq, int32_t max_len, int32_t S, int32_t q_heads, int32_t kv_group,
+                          const int32_t* cu_seqlens, const int32_t* seq_lens, float scale, int32_t causal, void* stream);
 
 #ifdef __cplusplus
 }

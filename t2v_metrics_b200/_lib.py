@@ -15,7 +15,8 @@ LIB_PATH = _HERE / "libvqa_b200.so"
 ABI_SYMBOLS = [
     "vqa_version", "vqa_create_clipt5", "vqa_bind_weights", "vqa_finalize_weights", "vqa_clipt5_workspace_bytes",
     "vqa_clipt5_score", "vqa_set_profile", "vqa_profile_read", "vqa_last_launch_count", "vqa_last_error", "vqa_destroy", "vqa_op_gemm_bf16",
-    "vqa_op_lmhead_logprob", "vqa_op_attention_d64", "vqa_op_norm",
+    "vqa_op_lmhead_logprob", "vqa_op_attention_d64", "vqa_op_norm", "vqa_op_attention_d128",
+    "vqa_create_qwen25vl", "vqa_qwen25vl_set_rope", "vqa_qwen25vl_workspace_bytes", "vqa_qwen25vl_score",
 ]
 
 VQA_DTYPE_BF16, VQA_DTYPE_F32, VQA_DTYPE_I32 = 0, 1, 2
@@ -29,6 +30,16 @@ class VqaClipT5Config(C.Structure):
         ("dec_layers", C.c_int32), ("vocab", C.c_int32), ("rel_buckets", C.c_int32), ("rel_max_distance", C.c_int32),
         ("t5_ln_eps", C.c_float), ("image_token_id", C.c_int32), ("pad_token_id", C.c_int32),
         ("decoder_start_id", C.c_int32), ("emulate_bf16_rounding", C.c_int32), ("cross_attention_mode", C.c_int32),
+    ]
+
+
+class VqaQwen25VLConfig(C.Structure):
+    _fields_ = [
+        ("vit_depth", C.c_int32), ("vit_hidden", C.c_int32), ("vit_heads", C.c_int32), ("vit_head_dim", C.c_int32),
+        ("vit_mlp", C.c_int32), ("patch_dim", C.c_int32), ("spatial_merge", C.c_int32), ("out_hidden", C.c_int32),
+        ("fullatt_mask", C.c_uint64), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
+        ("kv_heads", C.c_int32), ("mlp", C.c_int32), ("vocab", C.c_int32), ("rms_eps", C.c_float),
+        ("emulate_bf16_rounding", C.c_int32),
     ]
 
 
@@ -84,6 +95,17 @@ def load() -> C.CDLL:
     lib.vqa_op_attention_d64.restype = C.c_int
     lib.vqa_op_norm.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp]
     lib.vqa_op_norm.restype = C.c_int
+    lib.vqa_op_attention_d128.argtypes = [vp, i32, i64, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp]
+    lib.vqa_op_attention_d128.restype = C.c_int
+    lib.vqa_create_qwen25vl.argtypes = [C.POINTER(VqaQwen25VLConfig), C.c_int, C.POINTER(vp)]
+    lib.vqa_create_qwen25vl.restype = C.c_int
+    lib.vqa_qwen25vl_set_rope.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32), i32, C.POINTER(C.c_float), C.POINTER(i32), i32]
+    lib.vqa_qwen25vl_set_rope.restype = C.c_int
+    lib.vqa_qwen25vl_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.vqa_qwen25vl_workspace_bytes.restype = C.c_size_t
+    lib.vqa_qwen25vl_score.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
+                                       vp, vp, vp, C.c_size_t, vp]
+    lib.vqa_qwen25vl_score.restype = C.c_int
     _lib = lib
     return lib
 

@@ -31,9 +31,10 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
+constexpr int AT_THREADS = 320;              // warp0 TMA, warp1 MMA, warps 2..9 softmax
 
 inline size_t attn_tc_smem_bytes(int S) {
-    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
+    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 14 * 8 + 3 * 2 * 128 * 4 + 64;
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -99,7 +100,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // bias table are paid once, and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered),
 // so only the very first tile of a CTA sees the full HBM/L2 latency.
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
@@ -133,6 +134,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     uint64_t* o_done = bars + 11;
     uint64_t* o_free = bars + 12;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+    float* sXch = reinterpret_cast<float*>(bars + 14);   // [2 tile parities + 1 epilogue][2 key halves][128 rows] partial max / sum exchange
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -142,10 +144,10 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);
+        mbar_init(s_empty, 8);
+        mbar_init(p_full, 8);
         mbar_init(o_done, 1);
-        mbar_init(o_free, 4);
+        mbar_init(o_free, 8);
         fence_barrier_init();
         // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
         mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
@@ -245,15 +247,20 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             issue_pv(total_tiles - 1);
         }
     } else {
-        // ===================== softmax / correction / epilogue: one thread per query row =====================
+        // ===================== softmax / correction / epilogue =====================
+        // Eight warps: warps {2..5} and {6..9} both cover the four TMEM lane quadrants; a pair of threads (one per group)
+        // shares a query row and splits the tile's 128 keys (and the 64 output columns) in halves. Row maxima / sums are
+        // exchanged through shared memory under a 64-thread named barrier per quadrant.
         const uint32_t quad = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
         const int row = quad * 32 + lane;
         const uint32_t lane_off = (quad * 32u) << 16;
+        const uint32_t pair_bar = 1u + quad;
         int g = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int q0 = qi * AT_BQ;
             const int qrow = q0 + row;
-            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D + half * 32;
             if (q0 + (int)quad * 32 >= len) {
                 // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
                 for (int j = 0; j < nkt; ++j, ++g) {
@@ -269,23 +276,23 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 if (lane == 0) mbar_arrive(o_free);
                 if (qrow < p.S) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
                 }
                 continue;
             }
-            float m_run = -INFINITY, l_run = 0.f;
-            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow;   // + kcol
+            float m_run = -INFINITY, l_run = 0.f;   // l_run: this thread's half of the row sum
+            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow + (int)half * 64;   // + k0 + i
             for (int j = 0; j < nkt; ++j, ++g) {
-                const int k0 = j * AT_BK;
-                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
+                const int k0 = j * AT_BK + (int)half * 64;       // first key of this thread's half tile
+                const int nch = max(0, min(2, (len - k0 + 31) >> 5));   // 32-key chunks with at least one valid key
                 mbar_wait(s_full, (uint32_t)g & 1u);
                 tcgen05_fence_after();
-                float t[4][32];
+                float t[2][32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     if (c < nch) {
                         uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                        tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
@@ -298,10 +305,10 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     if (c < nch) {
                         if (HAS_BIAS) {
-                            const float* bp = sBias + bias_base + k0 + c * 32;
+                            const float* bp = sBias + bias_base + j * AT_BK + c * 32;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
                         } else {
@@ -320,7 +327,11 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                         }
                     }
                 }
-                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // combine the two halves' row maxima
+                float* xch = sXch + (g & 1) * 256;
+                xch[half * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float tile_max = fmaxf(xch[row], xch[128 + row]);
                 // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
                 float corr = 1.f;
                 bool rescale = false;
@@ -340,20 +351,20 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                     tcgen05_fence_after();
                     if (rescale) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
+                        for (int c = 0; c < 2; ++c) {   // this thread's 32 of the 64 output columns
                             uint32_t ov[16];
-                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
                         }
                     }
                 }
                 // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
                 float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t pk[16];
                     if (c < nch) {
 #pragma unroll
@@ -368,7 +379,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
-                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                    tmem_st_32x32b_x16(tmem_P + lane_off + half * 32 + c * 16, pk);
                 }
                 l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
                 tmem_st_wait();
@@ -376,20 +387,23 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
-            // ---- epilogue of this query tile: O / l
+            // ---- epilogue of this query tile: O / l, this thread's 32 output columns
+            {
+                float* xch = sXch + 2 * 256;   // third buffer: never aliases a tile's max exchange
+                xch[half * 128 + row] = l_run;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                l_run = xch[row] + xch[128 + row];
+            }
             mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
             tcgen05_fence_after();
             const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
                 uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, ov);
                 tmem_ld_wait();
-                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(o_free);
-                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);   // O copied out: the next query tile's first P.V may overwrite it
                 if (qrow < p.S) {
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
@@ -397,7 +411,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(orow + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -430,8 +444,281 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         max_set[which] = smem;
     }
     dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
-    if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
-    else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
+    if (bias_table) attn_tc_d64_kernel<true><<<grid, AT_THREADS, smem, stream>>>(tm, p);
+    else            attn_tc_d64_kernel<false><<<grid, AT_THREADS, smem, stream>>>(tm, p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// head_dim 128 variant (Qwen2.5-VL language model: causal GQA; vision tower: windows / whole frames with the 80-wide heads
+// zero-padded to 128). Variable-length sequences (cu_seqlens) or fixed stride S; one CTA per (query tile, head, sequence).
+struct AttnTc128Params {
+    __nv_bfloat16* o;          // [rows, ldo], column h*128 + d
+    int ldo;
+    const int* cu_seqlens;     // [n_seq + 1] row offsets (varlen) or nullptr
+    const int* seq_lens;       // [n_seq] valid rows (fixed-stride mode) or nullptr
+    int S;                     // fixed-stride mode: rows per sequence
+    int q_col0, k_col0, v_col0;
+    int kv_group;              // query heads per key/value head (GQA); 1 for MHA
+    float scale_log2e;
+};
+
+constexpr int A8_TILE = 128 * 128 * 2;       // 32 KB: 128 rows x 128 bf16 as two 64-column swizzle blocks
+constexpr int A8_BLOCK = 128 * 64 * 2;       // 16 KB
+constexpr int A8_TMEM_COLS = 512;            // S [0,128)  O [128,256)  P [256,320)
+inline size_t attn_tc128_smem_bytes() { return 1024 + 5 * A8_TILE + 128; }
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(192, 1)
+attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc128Params p) {
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int kvh = h / p.kv_group;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    int row_base, len, write_rows;
+    if (p.cu_seqlens) {
+        row_base = p.cu_seqlens[b];
+        len = p.cu_seqlens[b + 1] - row_base;
+        write_rows = len;                       // rows past the sequence belong to the next one
+    } else {
+        row_base = b * p.S;
+        len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
+        write_rows = p.S;                       // padded rows of this sequence get zeros
+    }
+    const int q0 = qt * 128;
+    if (q0 >= write_rows) return;
+    if (q0 >= len) {
+        for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+            const int r = i >> 4, c = i & 15;
+            if (q0 + r < write_rows)
+                *reinterpret_cast<uint4*>(p.o + (size_t)(row_base + q0 + r) * p.ldo + h * 128 + c * 8) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+    extern __shared__ uint8_t a8_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a8_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + A8_TILE;        // [2]
+    uint8_t* sV = smem + 3 * A8_TILE;    // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * A8_TILE);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 3;
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* o_done = bars + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+    int nkt = (len + 127) / 128;
+    if (CAUSAL) nkt = min(nkt, qt + 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        mbar_init(q_full, 1);
+        mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+        mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_ptr_smem, A8_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, A8_TILE);
+            tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col0 + h * 128, row_base + q0);
+            tma_load_2d(sQ + A8_BLOCK, &tmap_qkv, q_full, p.q_col0 + h * 128 + 64, row_base + q0);
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * A8_TILE);
+                const int r = row_base + j * 128;
+                tma_load_2d(sK + st * A8_TILE, &tmap_qkv, &kv_full[st], p.k_col0 + kvh * 128, r);
+                tma_load_2d(sK + st * A8_TILE + A8_BLOCK, &tmap_qkv, &kv_full[st], p.k_col0 + kvh * 128 + 64, r);
+                tma_load_2d(sV + st * A8_TILE, &tmap_qkv, &kv_full[st], p.v_col0 + kvh * 128, r);
+                tma_load_2d(sV + st * A8_TILE + A8_BLOCK, &tmap_qkv, &kv_full[st], p.v_col0 + kvh * 128 + 64, r);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 128) | (1u << 16);   // B (= V) MN-major
+            auto issue_pv = [&](int i) {
+                mbar_wait(p_full, (uint32_t)i & 1u);
+                tcgen05_fence_after();
+                // V tile: two 64-wide head-dim atoms 16 KB apart (LBO), 8-key groups 1 KB apart (SBO)
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (i & 1) * A8_TILE), A8_BLOCK);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * 128), idesc_o, (i > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[i & 1]);
+                umma_commit<1>(o_done);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_full[st], ((uint32_t)j >> 1) & 1u);
+                mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t qd = make_kmajor_sw128_desc(smem_u32(sQ + (k >> 2) * A8_BLOCK)) + 2 * (k & 3);
+                    const uint64_t kd = make_kmajor_sw128_desc(smem_u32(sK + st * A8_TILE + (k >> 2) * A8_BLOCK)) + 2 * (k & 3);
+                    umma_f16<1>(tmem_S, qd, kd, idesc_s, k > 0 ? 1u : 0u);
+                }
+                umma_commit<1>(s_full);
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(nkt - 1);
+        }
+    } else {
+        const uint32_t quad = warp & 3u;
+        const int row = quad * 32 + lane;
+        const int qrow = q0 + row;
+        const uint32_t lane_off = (quad * 32u) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nkt; ++j) {
+            const int k0 = j * 128;
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tcgen05_fence_after();
+            float t[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]) * p.scale_log2e;
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+
+            const bool edge = (k0 + 128 > len) || (CAUSAL && j == qt);
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (edge) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int kcol = k0 + c * 32 + i;
+                        if (kcol >= len || (CAUSAL && kcol > qrow)) t[c][i] = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
+                    mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
+                }
+            }
+            float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            if (tile_max == -INFINITY) tile_max = -1e30f;   // a padded query row may see no key at all in this tile
+            float corr = 1.f;
+            bool rescale = false;
+            if (j == 0) {
+                m_run = tile_max;
+            } else {
+                const bool need = tile_max > m_run + 8.f;
+                rescale = __any_sync(0xffffffffu, need);
+                if (rescale) {
+                    const float m_new = fmaxf(m_run, tile_max);
+                    corr = fast_exp2(m_run - m_new);
+                    m_run = m_new;
+                }
+            }
+            if (j > 0) {
+                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
+                tcgen05_fence_after();
+                if (rescale) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t ov[16];
+                        tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                        tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                    }
+                }
+            }
+            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                    const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
+                    ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+                    pk[i] = pack_bf16x2(e0, e1);
+                    pk[i + 1] = pack_bf16x2(e2, e3);
+                }
+                tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+            }
+            l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
+        tcgen05_fence_after();
+        const float inv = (qrow < len && l_run > 0.f) ? 1.f / l_run : 0.f;
+        __nv_bfloat16* orow = p.o + (size_t)(row_base + qrow) * p.ldo + h * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+            tmem_ld_wait();
+            if (qrow < write_rows) {
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, A8_TMEM_COLS);
+}
+
+// rows: total rows of the packed buffer; max_len: longest sequence (grid sizing)
+inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long rows, int q_col0, int k_col0, int v_col0,
+                                     __nv_bfloat16* o, int ldo, int n_seq, int max_len, int S, int Hq, int kv_group,
+                                     const int* cu_seqlens, const int* seq_lens, float scale, bool causal, cudaStream_t stream) {
+    CUtensorMap tm;
+    if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    AttnTc128Params p;
+    p.o = o; p.ldo = ldo; p.cu_seqlens = cu_seqlens; p.seq_lens = seq_lens; p.S = S;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.kv_group = kv_group;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    const size_t smem = attn_tc128_smem_bytes();
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_d128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_d128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set = true;
+    }
+    dim3 grid((max_len + 127) / 128, Hq, n_seq);
+    if (causal) attn_tc_d128_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
+    else        attn_tc_d128_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ struct GemmParams {
     float* lse_sum;           // [M, num_n_tiles]
     const int* labels;        // [M]
     float* label_logit;       // [M]
+    float lse_scale;          // logits are multiplied by this (1 / temperature) after the bf16 rounding
     // batching: `num_batches` independent GEMMs of the same M,N,K share one launch; batch b reads A at
     // (row + b*a_row_off, k + b*a_k_off), W at (row + b*w_row_off, k + b*w_k_off) and writes C + b*c_batch_stride.
     int num_batches;
@@ -305,7 +306,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = n0 + c * 32 + j;
-                        float val = bf16_round(__uint_as_float(v[j]));   // reference logits are bf16
+                        float val = bf16_round(__uint_as_float(v[j])) * p.lse_scale;   // reference logits are bf16, then / T in fp32
                         x[j] = (n < p.N) ? val : -INFINITY;
                         cmax = fmaxf(cmax, x[j]);
                         if (n == label) p.label_logit[m] = val;

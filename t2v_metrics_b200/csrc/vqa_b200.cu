@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "attention.cuh"
 #include "attention_sm100.cuh"
+#include "qwen_kernels.cuh"
 
 using namespace vqa;
 typedef __nv_bfloat16 bf16;
@@ -38,7 +39,10 @@ struct T5DecLayerW {
     const bf16* ckT;   // Wk^T [d_model, inner] for the absorbed cross-attention (optional)
 };
 
+struct QwenState;
 struct vqa_handle {
+    int kind = 0;               // 0: CLIP-FlanT5, 1: Qwen2.5-VL
+    QwenState* qwen = nullptr;
     vqa_clipt5_config cfg;
     int device = 0;
     int num_sms = 148;
@@ -229,12 +233,13 @@ constexpr int LMHEAD_BN = 128;
 constexpr int LMHEAD_PARTS = GemmConfig<LMHEAD_BN, 1>::LSE_PARTS;   // (max, sum) partials per (row, n tile)
 static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
                               float* lse_max, float* lse_sum, float* label_logit, int num_sms, cudaStream_t st,
-                              int64_t* launch_counter) {
+                              int64_t* launch_counter, float logit_scale = 1.0f) {
     GemmLaunch g;
     g.A = H; g.lda = ldh; g.W = W; g.ldw = ldw; g.w_rows = N;
     memset(&g.p, 0, sizeof(g.p));
     g.p.M = M; g.p.N = N; g.p.K = K;
     g.p.lse_max = lse_max; g.p.lse_sum = lse_sum; g.p.labels = labels; g.p.label_logit = label_logit;
+    g.p.lse_scale = logit_scale;
     if (launch_counter) ++*launch_counter;
     return launch_gemm_t<LMHEAD_BN, 1, EPI_LSE>(g, num_sms, st);
 }
@@ -396,8 +401,14 @@ static const bf16* need(vqa_handle* h, const std::string& name, int64_t d0, int6
     return reinterpret_cast<const bf16*>(b.data);
 }
 
+static int qwen_finalize(vqa_handle* h, QwenState& q);
 extern "C" int vqa_finalize_weights(vqa_handle* h) {
     if (!h) return VQA_ERR_INVALID_ARG;
+    if (h->kind == 1) {
+        int rc = qwen_finalize(h, *h->qwen);
+        h->finalized = (rc == VQA_OK);
+        return rc;
+    }
     const vqa_clipt5_config& c = h->cfg;
     bool ok = true;
     const int P = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
@@ -521,6 +532,8 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     return w;
 }
 
+#include "qwen25vl.cuh"
+
 extern "C" size_t vqa_clipt5_workspace_bytes(vqa_handle* h, int32_t batch, int32_t n_images, int32_t text_len,
                                              int32_t label_len) {
     if (!h || batch <= 0 || n_images <= 0 || text_len <= 0 || label_len <= 0) return 0;
@@ -538,6 +551,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
                                 const int32_t* labels, int32_t B, int32_t L, int32_t T, float* out_scores,
                                 float* out_logprobs, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return VQA_ERR_INVALID_ARG;
+    if (h->kind != 0) return fail(h, VQA_ERR_INVALID_ARG, "not a CLIP-FlanT5 handle");
     if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
     if (!pixels || !input_ids || !text_lens || !labels || !out_scores || !workspace)
         return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
@@ -790,7 +804,82 @@ extern "C" void vqa_destroy(vqa_handle* h) {
     if (h->lut_bidir) cudaFree(h->lut_bidir);
     if (h->lut_unidir) cudaFree(h->lut_unidir);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->qwen) {
+        QwenState* q = h->qwen;
+        if (q->text_axis) cudaFree(q->text_axis);
+        if (q->vis_axis) cudaFree(q->vis_axis);
+        if (q->text_inv_freq) cudaFree(q->text_inv_freq);
+        if (q->vis_inv_freq) cudaFree(q->vis_inv_freq);
+        delete q;
+    }
     delete h;
+}
+
+// ------------------------------------------------------------------------------------------------ Qwen2.5-VL ABI
+extern "C" int vqa_create_qwen25vl(const vqa_qwen25vl_config* cfg, int device, vqa_handle** out) {
+    if (!cfg || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null argument");
+    if (cfg->heads % cfg->kv_heads) return fail(nullptr, VQA_ERR_INVALID_ARG, "heads % kv_heads != 0");
+    if (cfg->vit_head_dim > 128 || cfg->vit_head_dim % 2 || cfg->vit_hidden != cfg->vit_heads * cfg->vit_head_dim)
+        return fail(nullptr, VQA_ERR_UNSUPPORTED, "vision head_dim must be even, <= 128 and hidden = heads * head_dim");
+    if (cfg->hidden % 8 || cfg->mlp % 128 || cfg->vit_hidden % 8 || cfg->patch_dim % 8)
+        return fail(nullptr, VQA_ERR_UNSUPPORTED, "hidden % 8, mlp % 128, vit_hidden % 8, patch_dim % 8 must be 0");
+    if (cfg->vit_depth > 64) return fail(nullptr, VQA_ERR_UNSUPPORTED, "vit_depth > 64");
+    cudaError_t e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess || prop.major != 10) return fail(nullptr, VQA_ERR_UNSUPPORTED, "vqa_b200 requires an sm_100 (B200) device");
+    vqa_handle* h = new vqa_handle();
+    h->kind = 1;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->qwen = new QwenState();
+    h->qwen->cfg = *cfg;
+    *out = h;
+    return VQA_OK;
+}
+
+extern "C" int vqa_qwen25vl_set_rope(vqa_handle* h, const float* text_inv_freq, const int32_t* text_axis, int32_t text_half,
+                                     const float* vis_inv_freq, const int32_t* vis_axis, int32_t vis_half) {
+    if (!h || h->kind != 1 || !text_inv_freq || !text_axis || !vis_inv_freq || !vis_axis)
+        return fail(h, VQA_ERR_INVALID_ARG, "bad rope argument");
+    QwenState& q = *h->qwen;
+    if (text_half != 64 || vis_half != q.cfg.vit_head_dim / 2) return fail(h, VQA_ERR_INVALID_ARG, "rope table sizes do not match the config");
+    auto up = [&](const void* src, size_t bytes, void** dst) -> bool {
+        if (*dst) cudaFree(*dst);
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!up(text_inv_freq, 64 * 4, (void**)&q.text_inv_freq) || !up(text_axis, 64 * 4, (void**)&q.text_axis) ||
+        !up(vis_inv_freq, vis_half * 4, (void**)&q.vis_inv_freq) || !up(vis_axis, vis_half * 4, (void**)&q.vis_axis))
+        return fail(h, VQA_ERR_CUDA, "rope table upload failed");
+    q.rope_set = true;
+    return VQA_OK;
+}
+
+extern "C" size_t vqa_qwen25vl_workspace_bytes(vqa_handle* h, int32_t batch, int32_t seq_len, int32_t n_patches) {
+    if (!h || h->kind != 1 || batch <= 0 || seq_len <= 0 || n_patches <= 0) return 0;
+    return qwen_plan(h->qwen->cfg, batch, seq_len, n_patches).total;
+}
+
+extern "C" int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int32_t pixel_dtype, int32_t n_patches,
+                                  const int32_t* vis_pos_hw, const int32_t* window_index, const int32_t* reverse_index,
+                                  const int32_t* cu_window, int32_t n_windows, int32_t max_window_len, const int32_t* cu_frames,
+                                  int32_t n_frames, int32_t max_frame_len, const int32_t* input_ids, const int32_t* seq_lens,
+                                  const int32_t* feat_index, const int32_t* position_ids, const int32_t* answer_ids, int32_t batch,
+                                  int32_t seq_len, float temperature, float* out_probs, float* out_logprobs, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (!h || h->kind != 1) return fail(h, VQA_ERR_INVALID_ARG, "not a Qwen2.5-VL handle");
+    if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
+    if (!pixel_patches || !vis_pos_hw || !window_index || !reverse_index || !cu_window || !cu_frames || !input_ids || !seq_lens ||
+        !feat_index || !position_ids || !answer_ids || !out_probs || !workspace)
+        return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
+    const int unit = h->qwen->cfg.spatial_merge * h->qwen->cfg.spatial_merge;
+    if (batch <= 0 || seq_len <= 0 || n_patches <= 0 || n_patches % unit || n_windows <= 0 || n_frames <= 0 || !(temperature > 0.f))
+        return fail(h, VQA_ERR_INVALID_ARG, "bad size / temperature");
+    if (pixel_dtype != VQA_DTYPE_F32 && pixel_dtype != VQA_DTYPE_BF16) return fail(h, VQA_ERR_INVALID_ARG, "pixel_dtype must be F32 or BF16");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VQA_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+    return qwen_score(h, *h->qwen, pixel_patches, pixel_dtype, n_patches, vis_pos_hw, window_index, reverse_index, cu_window, n_windows,
+                      max_window_len, cu_frames, n_frames, max_frame_len, input_ids, seq_lens, feat_index, position_ids, answer_ids, batch,
+                      seq_len, temperature, out_probs, out_logprobs, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI
@@ -843,6 +932,16 @@ extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32
     cudaError_t e = run_flash(q, q + H * 64, q + 2 * H * 64, 3 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table,
                               scale, round_scores, (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+extern "C" int vqa_op_attention_d128(const void* qkv, int32_t ld, int64_t rows, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                                     void* out, int32_t ldo, int32_t n_seq, int32_t max_len, int32_t S, int32_t q_heads, int32_t kv_group,
+                                     const int32_t* cu_seqlens, const int32_t* seq_lens, float scale, int32_t causal, void* stream) {
+    if (!qkv || !out || n_seq <= 0 || max_len <= 0 || q_heads <= 0 || kv_group <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
+    cudaError_t e = launch_attn_tc128((const bf16*)qkv, ld, rows, q_col0, k_col0, v_col0, (bf16*)out, ldo, n_seq, max_len, S, q_heads, kv_group,
+                                      cu_seqlens, seq_lens, scale, causal != 0, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention d128 launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }
 

@@ -266,3 +266,165 @@ class ops:
                              _stream_ptr(x.device))
         _check(rc, None, "vqa_op_norm")
         return y
+
+
+# ================================================================================================ Qwen2.5-VL
+def convert_qwen_state_dict(sd: Dict[str, torch.Tensor], cfg, device) -> Dict[str, torch.Tensor]:
+    """HF `Qwen2_5_VLForConditionalGeneration` names -> the engine's fused bf16 layout:
+      * vision qkv: rows regrouped per (q|k|v, head) and every 80-wide head zero-padded to 128 rows, so the packed activation
+        is [L, 3*H*128]; the attention output projection gets matching zero columns;
+      * vision gate|up rows concatenated with the MLP width zero-padded to a multiple of 128; down-projection columns padded;
+      * language-model q|k|v rows concatenated (+ biases), gate|up rows concatenated."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def put(name, t):
+        out[name] = t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+    v = "model.visual."
+    Dv, H, hd = cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim
+    mp = cfg.vit_mlp_padded
+    put("vis.patch_embed", sd[v + "patch_embed.proj.weight"].reshape(Dv, -1))
+    for l in range(cfg.vit_depth):
+        p, q = v + f"blocks.{l}.", f"vis.{l}."
+        put(q + "norm1", sd[p + "norm1.weight"]); put(q + "norm2", sd[p + "norm2.weight"])
+        w = sd[p + "attn.qkv.weight"].float().reshape(3, H, hd, Dv)
+        b = sd[p + "attn.qkv.bias"].float().reshape(3, H, hd)
+        wp = torch.zeros(3, H, 128, Dv); wp[:, :, :hd] = w
+        bp = torch.zeros(3, H, 128); bp[:, :, :hd] = b
+        put(q + "qkv.weight", wp.reshape(3 * H * 128, Dv)); put(q + "qkv.bias", bp.reshape(-1))
+        pw = sd[p + "attn.proj.weight"].float().reshape(Dv, H, hd)
+        pwp = torch.zeros(Dv, H, 128); pwp[:, :, :hd] = pw
+        put(q + "proj.weight", pwp.reshape(Dv, H * 128)); put(q + "proj.bias", sd[p + "attn.proj.bias"])
+        gu = torch.zeros(2 * mp, Dv); gb = torch.zeros(2 * mp)
+        gu[: cfg.vit_mlp] = sd[p + "mlp.gate_proj.weight"].float(); gu[mp: mp + cfg.vit_mlp] = sd[p + "mlp.up_proj.weight"].float()
+        gb[: cfg.vit_mlp] = sd[p + "mlp.gate_proj.bias"].float(); gb[mp: mp + cfg.vit_mlp] = sd[p + "mlp.up_proj.bias"].float()
+        put(q + "gate_up.weight", gu); put(q + "gate_up.bias", gb)
+        dw = torch.zeros(Dv, mp); dw[:, : cfg.vit_mlp] = sd[p + "mlp.down_proj.weight"].float()
+        put(q + "down.weight", dw); put(q + "down.bias", sd[p + "mlp.down_proj.bias"])
+    put("vis.merger.ln_q", sd[v + "merger.ln_q.weight"])
+    put("vis.merger.fc1.weight", sd[v + "merger.mlp.0.weight"]); put("vis.merger.fc1.bias", sd[v + "merger.mlp.0.bias"])
+    put("vis.merger.fc2.weight", sd[v + "merger.mlp.2.weight"]); put("vis.merger.fc2.bias", sd[v + "merger.mlp.2.bias"])
+    t = "model.language_model."
+    put("llm.embed", sd[t + "embed_tokens.weight"])
+    put("llm.norm", sd[t + "norm.weight"])
+    put("llm.lm_head", sd["lm_head.weight"])
+    for l in range(cfg.layers):
+        p, q = t + f"layers.{l}.", f"llm.{l}."
+        put(q + "ln1", sd[p + "input_layernorm.weight"]); put(q + "ln2", sd[p + "post_attention_layernorm.weight"])
+        put(q + "qkv.weight", torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0))
+        put(q + "qkv.bias", torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0))
+        put(q + "o.weight", sd[p + "self_attn.o_proj.weight"])
+        put(q + "gate_up.weight", torch.cat([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], dim=0))
+        put(q + "down.weight", sd[p + "mlp.down_proj.weight"])
+    return out
+
+
+class QwenVLEngine:
+    """Qwen2.5-VL VQAScore engine: P(answer token | image, prompt) for a whole batch of prompts in one prefill."""
+
+    def __init__(self, cfg, device="cuda:0", emulate_bf16_rounding: bool = True):
+        from . import qwen_host
+        if not torch.cuda.is_available():
+            raise RuntimeError("QwenVLEngine needs a CUDA device (sm_100a); there is no CPU path")
+        if cfg.head_dim != 128:
+            raise ValueError("the language-model attention kernel is specialised for head_dim == 128")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        mask = 0
+        for l in cfg.fullatt_block_indexes:
+            mask |= 1 << l
+        c = _lib.VqaQwen25VLConfig(vit_depth=cfg.vit_depth, vit_hidden=cfg.vit_hidden, vit_heads=cfg.vit_heads,
+                                   vit_head_dim=cfg.vit_head_dim, vit_mlp=cfg.vit_mlp, patch_dim=cfg.patch_dim,
+                                   spatial_merge=cfg.spatial_merge_size, out_hidden=cfg.out_hidden, fullatt_mask=mask,
+                                   hidden=cfg.hidden, layers=cfg.layers, heads=cfg.heads, kv_heads=cfg.kv_heads, mlp=cfg.mlp,
+                                   vocab=cfg.vocab, rms_eps=cfg.rms_eps, emulate_bf16_rounding=1 if emulate_bf16_rounding else 0)
+        self._h = C.c_void_p()
+        with torch.cuda.device(idx):
+            _check(self.lib.vqa_create_qwen25vl(C.byref(c), idx, C.byref(self._h)), None, "vqa_create_qwen25vl")
+        t_inv, t_axis, v_inv, v_axis = qwen_host.rope_tables(cfg.head_dim, cfg.rope_theta, cfg.mrope_section, cfg.vit_head_dim)
+        fp = lambda t: t.numpy().ctypes.data_as(C.POINTER(C.c_float))
+        ip = lambda t: t.numpy().ctypes.data_as(C.POINTER(C.c_int32))
+        _check(self.lib.vqa_qwen25vl_set_rope(self._h, fp(t_inv), ip(t_axis), t_inv.numel(), fp(v_inv), ip(v_axis), v_inv.numel()),
+               self._h, "vqa_qwen25vl_set_rope")
+        self._weights: Dict[str, torch.Tensor] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._vision_cache: Dict[tuple, dict] = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.vqa_destroy(h)
+            self._h = C.c_void_p()
+
+    bind_engine_tensors = ClipT5Engine.bind_engine_tensors
+    last_launch_count = ClipT5Engine.last_launch_count
+    set_profile = ClipT5Engine.set_profile
+    read_profile = ClipT5Engine.read_profile
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        self.bind_engine_tensors(convert_qwen_state_dict(sd, self.cfg, self.device))
+
+    def vision_indices(self, grid_thw):
+        """Window order, rotary positions and cumulative lengths for a list of (t, h, w) grids; cached per grid tuple."""
+        from . import qwen_host
+        key = tuple(tuple(int(x) for x in g) for g in grid_thw)
+        hit = self._vision_cache.get(key)
+        if hit is not None:
+            return hit
+        cfg, dev = self.cfg, self.device
+        merge, unit = cfg.spatial_merge_size, cfg.spatial_merge_size ** 2
+        widx, cu_win, cu_frames = qwen_host.vision_window_index(key, merge, cfg.window_size, cfg.patch_size)
+        pos = qwen_host.vision_rot_pos_ids(key, merge)                                   # [L, 2] processor order
+        L = pos.shape[0]
+        pos_win = pos.reshape(L // unit, unit, 2)[widx].reshape(L, 2)                    # window order (:478-484)
+        i32 = lambda t: t.to(torch.int32).contiguous().to(dev)
+        out = dict(window_index=i32(widx), reverse_index=i32(torch.argsort(widx)), vis_pos_hw=i32(pos_win.t()),
+                   cu_window=i32(cu_win), cu_frames=i32(cu_frames), n_windows=cu_win.numel() - 1, n_frames=cu_frames.numel() - 1,
+                   max_window=int((cu_win[1:] - cu_win[:-1]).max()), max_frame=int((cu_frames[1:] - cu_frames[:-1]).max()),
+                   n_patches=L)
+        self._vision_cache[key] = out
+        return out
+
+    def score_tensors(self, pixel_patches: torch.Tensor, grid_thw, input_ids: torch.Tensor, seq_lens: torch.Tensor,
+                      feat_index: torch.Tensor, position_ids: torch.Tensor, answer_ids: torch.Tensor, temperature: float = 1.0,
+                      out: Optional[torch.Tensor] = None, return_logprobs: bool = False):
+        """pixel_patches [sum P, patch_dim] fp32/bf16 cuda; grid_thw list of (t,h,w); the int32 cuda tensors come from
+        qwen_host.build_batch_indices. Returns probabilities [B] fp32 on the device."""
+        dev = self.device
+        vi = self.vision_indices(grid_thw)
+        assert pixel_patches.is_cuda and pixel_patches.is_contiguous() and pixel_patches.shape == (vi["n_patches"], self.cfg.patch_dim)
+        assert pixel_patches.dtype in (torch.float32, torch.bfloat16)
+        for t in (input_ids, seq_lens, feat_index, position_ids, answer_ids):
+            assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()
+        B, S = input_ids.shape
+        need = int(self.lib.vqa_qwen25vl_workspace_bytes(self._h, B, S, vi["n_patches"]))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, device=dev)
+        logp = torch.empty(B, dtype=torch.float32, device=dev) if return_logprobs else None
+        pdt = _lib.VQA_DTYPE_F32 if pixel_patches.dtype == torch.float32 else _lib.VQA_DTYPE_BF16
+        rc = self.lib.vqa_qwen25vl_score(self._h, _ptr(pixel_patches), pdt, vi["n_patches"], _ptr(vi["vis_pos_hw"]),
+                                         _ptr(vi["window_index"]), _ptr(vi["reverse_index"]), _ptr(vi["cu_window"]), vi["n_windows"],
+                                         vi["max_window"], _ptr(vi["cu_frames"]), vi["n_frames"], vi["max_frame"], _ptr(input_ids),
+                                         _ptr(seq_lens), _ptr(feat_index), _ptr(position_ids), _ptr(answer_ids), B, S,
+                                         float(temperature), _ptr(out), _ptr(logp), _ptr(self._workspace), self._workspace.numel(),
+                                         _stream_ptr(dev))
+        _check(rc, self._h, "vqa_qwen25vl_score")
+        return (out, logp) if return_logprobs else out
+
+    def score_prompts(self, pixel_patches, grid_thw, prompts, answer_ids, image_of_sample=None, temperature: float = 1.0):
+        """Convenience: prompts = list of 1-D id lists (each with one image-token run). Host index logic + one engine call."""
+        from . import qwen_host
+        cfg, dev = self.cfg, self.device
+        B = len(prompts)
+        img = list(image_of_sample) if image_of_sample is not None else list(range(B))
+        idx = qwen_host.build_batch_indices([list(map(int, p)) for p in prompts], [tuple(map(int, g)) for g in grid_thw], img,
+                                            cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second)
+        d = {k: v.to(dev) for k, v in idx.items()}
+        ans = torch.as_tensor(list(map(int, answer_ids)), dtype=torch.int32).to(dev)
+        return self.score_tensors(pixel_patches.to(dev), grid_thw, d["input_ids"], d["seq_lens"], d["feat_index"], d["position_ids"],
+                                  ans, temperature)

@@ -1,0 +1,122 @@
+"""Qwen2.5-VL path on a real B200: head-dim-128 tcgen05 attention vs torch, and the engine vs the oracle."""
+import dataclasses
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import qwen25vl_oracle as qo
+
+TINY = dict(hidden=256, heads=2, kv_heads=1, mrope_section=(16, 24, 24))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def attn_d128(qkv, out_cols, n_seq, max_len, S, Hq, group, cu, lens, scale, causal, q0, k0, v0):
+    import ctypes as C
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    out = torch.zeros(qkv.shape[0], out_cols, dtype=torch.bfloat16, device=qkv.device)
+    rc = lib.vqa_op_attention_d128(_ptr(qkv), qkv.shape[1], qkv.shape[0], q0, k0, v0, _ptr(out), out_cols, n_seq, max_len, S, Hq, group,
+                                   _ptr(cu), _ptr(lens), float(scale), 1 if causal else 0, _stream_ptr(qkv.device))
+    _check(rc, None, "vqa_op_attention_d128")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv", [(3, 320, 4, 2), (2, 130, 2, 1), (1, 64, 28, 4)])
+def test_causal_gqa_attention_d128(dev, B, S, Hq, Hkv):
+    torch.manual_seed(0)
+    cols = (Hq + 2 * Hkv) * 128
+    qkv = (torch.randn(B * S, cols, device=dev) * 0.5).bfloat16()
+    lens = torch.randint(max(1, S // 2), S + 1, (B,), device=dev, dtype=torch.int32)
+    out = attn_d128(qkv, Hq * 128, B, S, S, Hq, Hq // Hkv, None, lens, 128 ** -0.5, True, 0, Hq * 128, (Hq + Hkv) * 128)
+    x = qkv.float().view(B, S, Hq + 2 * Hkv, 128)
+    q, k, v = x[:, :, :Hq], x[:, :, Hq:Hq + Hkv], x[:, :, Hq + Hkv:]
+    k = k.repeat_interleave(Hq // Hkv, dim=2)
+    v = v.repeat_interleave(Hq // Hkv, dim=2)
+    sc = torch.einsum("bqhd,bkhd->bhqk", q, k) * 128 ** -0.5
+    mask = torch.tril(torch.ones(S, S, dtype=torch.bool, device=dev))[None, None] & (torch.arange(S, device=dev)[None, None, None, :] < lens[:, None, None, None])
+    sc = sc.masked_fill(~mask, float("-inf"))
+    ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(sc, -1), v).reshape(B * S, Hq * 128)
+    valid = (torch.arange(S, device=dev)[None, :] < lens[:, None]).reshape(-1)
+    assert float((out[valid].float() - ref[valid]).abs().max()) < 0.02
+    assert float(out[~valid].float().abs().max()) == 0.0 if (~valid).any() else True
+
+
+def test_varlen_window_attention_d128_padded_heads(dev):
+    """Vision-tower layout: 80-wide heads zero-padded to 128 columns, variable-length windows via cu_seqlens."""
+    torch.manual_seed(1)
+    H, hd = 4, 80
+    lens = [64, 64, 16, 48, 130, 2]
+    L = sum(lens)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    x = torch.zeros(L, 3, H, 128, device=dev)
+    x[..., :hd] = torch.randn(L, 3, H, hd, device=dev) * 0.5
+    qkv = x.reshape(L, 3 * H * 128).bfloat16()
+    out = attn_d128(qkv, H * 128, len(lens), max(lens), 0, H, 1, cu, None, hd ** -0.5, False, 0, H * 128, 2 * H * 128)
+    xf = qkv.float().view(L, 3, H, 128)
+    ref = torch.zeros(L, H, 128, device=dev)
+    s = 0
+    for n in lens:
+        q, k, v = (xf[s:s + n, i].transpose(0, 1) for i in range(3))
+        p = torch.softmax(torch.matmul(q, k.transpose(1, 2)) * hd ** -0.5, -1)
+        ref[s:s + n] = torch.matmul(p, v).transpose(0, 1)
+        s += n
+    assert float((out.float() - ref.reshape(L, H * 128)).abs().max()) < 0.02
+
+
+def make_engine(cfg, sd, dev):
+    from t2v_metrics_b200.config import Qwen25VLConfig
+    from t2v_metrics_b200.engine import QwenVLEngine
+    fields = {f.name for f in dataclasses.fields(Qwen25VLConfig)}
+    eng = QwenVLEngine(Qwen25VLConfig(**{k: v for k, v in dataclasses.asdict(cfg).items() if k in fields}), dev)
+    eng.load_state_dict(sd)
+    return eng
+
+
+@pytest.mark.parametrize("hw,n_images", [((84, 56), None), ((112, 112), None), ((56, 84), 2)])
+def test_qwen_engine_matches_oracle(dev, hw, n_images):
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=0)
+    inp = qo.make_synthetic_inputs(cfg, 4, hw, 12, ragged=True, n_images=n_images)
+    o32 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
+                            mode="fp32", return_all=True)
+    o16 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
+                            mode="bf16", return_all=True)
+    eng = make_engine(cfg, sd, dev)
+    probs = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], [x.tolist() for x in inp["input_ids"]], inp["answer_ids"],
+                              inp["image_of_sample"])
+    torch.cuda.synchronize()
+    p = probs.cpu()
+    lp, l32, l16 = torch.log(p), torch.log(o32["scores"]), torch.log(o16["scores"])
+    gap = float((l16 - l32).abs().max())
+    print(f"\n[qwen {hw}] engine {p.tolist()}\n   oracle fp32 {o32['scores'].tolist()}\n   |dlogp| vs fp32 {float((lp - l32).abs().max()):.3e} vs bf16 "
+          f"{float((lp - l16).abs().max()):.3e} | oracle bf16-vs-fp32 {gap:.3e} | launches {eng.last_launch_count()}")
+    assert float((lp - l32).abs().max()) <= 2.0 * gap + 2e-2
+    assert float((p - o32["scores"]).abs().max()) <= 1e-3 + 2.0 * float((o16["scores"] - o32["scores"]).abs().max())
+    # temperature is applied to the fp32 logits before the softmax (qwen2vl_model.py:166)
+    pT = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], [x.tolist() for x in inp["input_ids"]], inp["answer_ids"],
+                           inp["image_of_sample"], temperature=2.0).cpu()
+    refT = torch.stack([qo.answer_probability(o32["logits"][b], inp["answer_ids"][b], 2.0) for b in range(len(pT))])
+    assert float((torch.log(pT) - torch.log(refT)).abs().max()) <= 2.0 * gap + 2e-2
+
+
+def test_qwen_batch_invariance(dev):
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=3)
+    inp = qo.make_synthetic_inputs(cfg, 3, (84, 84), 10, ragged=True)
+    eng = make_engine(cfg, sd, dev)
+    prompts = [x.tolist() for x in inp["input_ids"]]
+    full = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"]).cpu()
+    P = inp["grid_thw"][0][1] * inp["grid_thw"][0][2]
+    for b in range(3):
+        one = eng.score_prompts(inp["pixel_patches"][b * P:(b + 1) * P], [inp["grid_thw"][b]], [prompts[b]], [inp["answer_ids"][b]]).cpu()
+        assert abs(float(torch.log(one[0]) - torch.log(full[b]))) < 2e-2

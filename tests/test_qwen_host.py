@@ -1,0 +1,111 @@
+"""Qwen2.5-VL: host index logic and oracle pinned to the real transformers implementation (CPU only)."""
+import pytest
+import torch
+
+from oracle import qwen25vl_oracle as qo
+from t2v_metrics_b200 import qwen_host
+
+
+def hf_model(cfg):
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    c = Qwen2_5_VLConfig(
+        text_config=dict(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers,
+                         num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads, rms_norm_eps=cfg.rms_eps,
+                         rope_parameters=dict(rope_type="default", rope_theta=cfg.rope_theta, mrope_section=list(cfg.mrope_section)),
+                         tie_word_embeddings=False, max_position_embeddings=4096, use_sliding_window=False),
+        vision_config=dict(depth=cfg.vit_depth, hidden_size=cfg.vit_hidden, intermediate_size=cfg.vit_mlp, num_heads=cfg.vit_heads,
+                           patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
+                           spatial_merge_size=cfg.spatial_merge_size, window_size=cfg.window_size,
+                           fullatt_block_indexes=list(cfg.fullatt_block_indexes), out_hidden_size=cfg.out_hidden,
+                           tokens_per_second=cfg.tokens_per_second, hidden_act="silu"),
+        image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id, tie_word_embeddings=False)
+    c._attn_implementation = "eager"
+    return Qwen2_5_VLForConditionalGeneration(c).eval()
+
+
+TINY = dict(hidden=256, heads=2, kv_heads=1, mrope_section=(16, 24, 24))   # head_dim 128 like the 7B model
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    return cfg, hf_model(cfg)
+
+
+@pytest.mark.parametrize("grids", [[(1, 8, 6)], [(1, 4, 4), (1, 6, 10)], [(1, 16, 12)], [(2, 4, 6)]])
+def test_vision_index_logic_matches_transformers(tiny, grids):
+    cfg, m = tiny
+    vis = m.model.visual
+    g = torch.tensor(grids)
+    widx_hf, cu_hf = vis.get_window_index(g)
+    cu_hf = torch.unique_consecutive(torch.tensor(cu_hf, dtype=torch.int32))
+    widx, cu_win, cu_frames = qwen_host.vision_window_index(grids, cfg.spatial_merge_size, cfg.window_size, cfg.patch_size)
+    assert torch.equal(widx, widx_hf) and torch.equal(cu_win, cu_hf)
+    cu_full = torch.nn.functional.pad(torch.repeat_interleave(g[:, 1] * g[:, 2], g[:, 0]).cumsum(0, dtype=torch.int32), (1, 0))
+    assert torch.equal(cu_frames, cu_full)
+    # rotary angles: table built from (pos ids, inv_freq, axis) == transformers' rot_pos_emb
+    rot_hf = vis.rot_pos_emb(g)                                                    # [L, head_dim/2]
+    pos = qwen_host.vision_rot_pos_ids(grids, cfg.spatial_merge_size)
+    _, _, v_inv, v_axis = qwen_host.rope_tables(cfg.head_dim, cfg.rope_theta, cfg.mrope_section, cfg.vit_hidden // cfg.vit_heads)
+    mine = pos[:, v_axis.long()].float() * v_inv[None]
+    assert torch.equal(mine, rot_hf)
+
+
+def test_mrope_positions_and_tables_match_transformers(tiny):
+    cfg, m = tiny
+    inp = qo.make_synthetic_inputs(cfg, 3, (84, 56), 11, ragged=True)
+    for b, ids in enumerate(inp["input_ids"]):
+        grid = [inp["grid_thw"][b]]
+        hf_pos, _ = m.model.get_rope_index(ids[None], (ids == cfg.image_token_id).long()[None], image_grid_thw=torch.tensor(grid),
+                                           attention_mask=torch.ones(1, len(ids), dtype=torch.long))
+        mine = qwen_host.mrope_position_ids(ids.tolist(), grid, cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second)
+        assert torch.equal(mine, hf_pos[:, 0])
+        assert torch.equal(mine, qo.mrope_position_ids(ids, grid, cfg))
+    t_inv, t_axis, _, _ = qwen_host.rope_tables(cfg.head_dim, cfg.rope_theta, cfg.mrope_section, cfg.vit_hidden // cfg.vit_heads)
+    assert torch.equal(t_inv, m.model.language_model.rotary_emb.inv_freq.float())
+    assert t_axis.tolist() == [0] * 16 + [1] * 24 + [2] * 24
+
+
+def test_build_batch_indices_round_trip(tiny):
+    cfg, _ = tiny
+    inp = qo.make_synthetic_inputs(cfg, 4, (56, 56), 9, ragged=True, n_images=2)
+    idx = qwen_host.build_batch_indices([x.tolist() for x in inp["input_ids"]], inp["grid_thw"], inp["image_of_sample"],
+                                        cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second)
+    B, S = idx["input_ids"].shape
+    n_tok = 4 * 4 // 4
+    for b in range(B):
+        n = int(idx["seq_lens"][b])
+        assert idx["input_ids"][b, :n].tolist() == inp["input_ids"][b].tolist()
+        f = idx["feat_index"][b]
+        assert (f[:n] >= 0).sum() == n_tok and (f[n:] == -1).all()
+        img = inp["image_of_sample"][b]
+        assert f[f >= 0].tolist() == list(range(img * n_tok, (img + 1) * n_tok))
+    assert idx["position_ids"].shape == (3, B * S)
+
+
+@pytest.mark.parametrize("hw", [(84, 56), (56, 112)])
+def test_qwen_oracle_matches_transformers(tiny, hw):
+    cfg, m = tiny
+    sd = qo.make_synthetic_state_dict(cfg, seed=0)
+    m.load_state_dict({k: v.float() for k, v in sd.items()})
+    inp = qo.make_synthetic_inputs(cfg, 2, hw, 10, ragged=True)
+    o = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], return_all=True)
+    P = inp["grid_thw"][0][1] * inp["grid_thw"][0][2]
+    for b, ids in enumerate(inp["input_ids"]):
+        with torch.no_grad():
+            out = m(input_ids=ids[None], pixel_values=inp["pixel_patches"][b * P:(b + 1) * P],
+                    image_grid_thw=torch.tensor([list(inp["grid_thw"][b])]), mm_token_type_ids=(ids == cfg.image_token_id).long()[None],
+                    attention_mask=torch.ones(1, len(ids), dtype=torch.long))
+        lg = out.logits[0, -1].float()
+        assert float((lg - o["logits"][b]).abs().max()) < 5e-5
+        assert abs(float(torch.softmax(lg, -1)[inp["answer_ids"][b]]) - float(o["scores"][b])) < 1e-6
+
+
+def test_repetition_penalty_semantics():
+    """the logits processor rescales ids present in the prompt before the softmax."""
+    from transformers.generation.logits_process import RepetitionPenaltyLogitsProcessor
+    torch.manual_seed(0)
+    logits = torch.randn(50)
+    prompt = torch.tensor([3, 7, 7, 11])
+    ref = torch.softmax(RepetitionPenaltyLogitsProcessor(1.05)(prompt[None], logits[None].clone())[0], -1)[7]
+    assert abs(float(qo.answer_probability(logits, 7, 1.0, prompt, 1.05)) - float(ref)) < 1e-7

@@ -237,6 +237,13 @@ def t_pipeline(kind="tiny", batch=3):
          oracle_secs=round(t_or, 2))
 
 
+def t_pytest(*args):
+    """Run a pytest selection inside this (timeout-guarded) process."""
+    import pytest as _pt
+    rc = _pt.main(["-q", "-s", "-x", "-m", "gpu", *args])
+    emit(test="pytest", args=list(args), ok=bool(rc == 0), rc=int(rc))
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     fn = globals()["t_" + name]
