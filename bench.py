@@ -20,7 +20,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_PAIR = {"clip-flant5-xxl": 7.896e12, "clip-flant5-xl": 2.294e12}   # SURVEY 8(d), reference algorithm
+FLOPS_PER_PAIR = {"clip-flant5-xxl": 7.896e12, "clip-flant5-xl": 2.294e12,    # SURVEY 8(d), reference algorithm
+                  "qwen2.5-vl-7b": 5.545e12}
 
 
 def parse():
@@ -254,6 +255,110 @@ def run_engine(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_engine_qwen(args, rank, local_rank, world):
+    """BASELINE config 3: qwen2.5-vl-7b VQAScore, batch 32 per GPU, synthetic 448x448 images (1024 patches -> 256 vision tokens) +
+    64 text ids (S = 320). Secondary bench line (`--model qwen2.5-vl-7b`); the default/headline line is clip-flant5-xxl."""
+    import torch
+    import torch.distributed as dist
+    from t2v_metrics_b200 import qwen_host
+    from t2v_metrics_b200.config import QWEN25VL_MODELS
+    from t2v_metrics_b200.engine import QwenVLEngine
+    from t2v_metrics_b200.synthetic import synthetic_qwen_engine_weights, synthetic_qwen_batch
+    from t2v_metrics_b200.parallel import gather_scores
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = QWEN25VL_MODELS[args.model]["config"]()
+    eng = QwenVLEngine(cfg, dev)
+    eng.bind_engine_tensors(synthetic_qwen_engine_weights(cfg, dev, seed=0))
+    B = args.batch if args.batch != 64 else 32
+    host = synthetic_qwen_batch(cfg, B, (448, 448), 64, seed=1 + rank)
+    idx = qwen_host.build_batch_indices(host["prompts"], host["grid_thw"], list(range(B)), cfg.image_token_id, cfg.spatial_merge_size,
+                                        cfg.tokens_per_second)
+    idx = {k: v.pin_memory() for k, v in idx.items()}
+    ans_h = torch.tensor(host["answer_ids"], dtype=torch.int32).pin_memory()
+    d_idx = {k: v.to(dev) for k, v in idx.items()}
+    d_pix, d_ans = host["pixel_patches"].to(dev), ans_h.to(dev)
+    total = B * world
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step_device():
+        s = eng.score_tensors(d_pix, host["grid_thw"], d_idx["input_ids"], d_idx["seq_lens"], d_idx["feat_index"], d_idx["position_ids"], d_ans)
+        return gather_scores(s, total) if world > 1 else s
+
+    def step_host():
+        t = {k: v.to(dev, non_blocking=True) for k, v in idx.items()}
+        s = eng.score_tensors(host["pixel_patches"].to(dev, non_blocking=True), host["grid_thw"], t["input_ids"], t["seq_lens"],
+                              t["feat_index"], t["position_ids"], ans_h.to(dev, non_blocking=True))
+        if world > 1:
+            s = gather_scores(s, total)
+        return s.cpu()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_device()
+    sync_all()
+    eng.set_profile(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    sync_all()
+    prof = eng.read_profile()
+    launches = eng.last_launch_count()
+    eng.set_profile(False)
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([(time.perf_counter() - t0) * 1000.0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / args.steps
+    h2d = host["pixel_patches"].numel() * 4 + sum(v.numel() * 4 for v in idx.values()) + B * 4
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_ms, gemm_flops, gemm_n = prof["gemm"]
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        value = total / (ms_step * 1e-3)
+        line = dict(metric="VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px", value=value, unit="pairs/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic",
+                    config=dict(workload=f"{args.model} VQAScore: batch {B}/GPU, synthetic 448x448 images (1024 patches, 256 vision tokens) + 64 "
+                                         "text ids (S=320), one answer token", model=args.model, global_batch=total, seq_len=320,
+                                parallelism=f"dp{world}", l2_policy="inputs larger than L2: 16.6 GB of weights stream per step"),
+                    roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
+                                  frac=(achieved / peaks["tflops"]) if achieved else None, traffic=None,
+                                  kernel="gemm_bf16_sm100_kernel (all tcgen05 GEMM launches of the step)", launches=gemm_n, device_ms=gemm_ms,
+                                  flops_per_launch=gemm_flops / max(gemm_n, 1), peak_source=peaks["source"],
+                                  whole_step_tflops=(value / world) * FLOPS_PER_PAIR[args.model] / 1e12),
+                    breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
+                    e2e=dict(value=total / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=B * 4, ms_per_step=e2e_ms),
+                    gpu_launches=int(launches) * args.steps, clocks=clocks, sample_scores=[float(x) for x in out[:4].float().cpu()])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -261,6 +366,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.model.startswith("qwen"):
+        run_engine_qwen(args, rank, local_rank, world)
     else:
         run_engine(args, rank, local_rank, world)
 

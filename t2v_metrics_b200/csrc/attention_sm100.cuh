@@ -31,10 +31,9 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
-constexpr int AT_THREADS = 320;              // warp0 TMA, warp1 MMA, warps 2..9 softmax
 
 inline size_t attn_tc_smem_bytes(int S) {
-    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 14 * 8 + 3 * 2 * 128 * 4 + 64;
+    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -100,7 +99,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // bias table are paid once, and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered),
 // so only the very first tile of a CTA sees the full HBM/L2 latency.
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(192, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
@@ -134,7 +133,6 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     uint64_t* o_done = bars + 11;
     uint64_t* o_free = bars + 12;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
-    float* sXch = reinterpret_cast<float*>(bars + 14);   // [2 tile parities + 1 epilogue][2 key halves][128 rows] partial max / sum exchange
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -144,10 +142,10 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_empty, 8);
-        mbar_init(p_full, 8);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
         mbar_init(o_done, 1);
-        mbar_init(o_free, 8);
+        mbar_init(o_free, 4);
         fence_barrier_init();
         // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
         mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
@@ -247,20 +245,15 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             issue_pv(total_tiles - 1);
         }
     } else {
-        // ===================== softmax / correction / epilogue =====================
-        // Eight warps: warps {2..5} and {6..9} both cover the four TMEM lane quadrants; a pair of threads (one per group)
-        // shares a query row and splits the tile's 128 keys (and the 64 output columns) in halves. Row maxima / sums are
-        // exchanged through shared memory under a 64-thread named barrier per quadrant.
+        // ===================== softmax / correction / epilogue: one thread per query row =====================
         const uint32_t quad = warp & 3u;
-        const uint32_t half = (warp - 2u) >> 2;
         const int row = quad * 32 + lane;
         const uint32_t lane_off = (quad * 32u) << 16;
-        const uint32_t pair_bar = 1u + quad;
         int g = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int q0 = qi * AT_BQ;
             const int qrow = q0 + row;
-            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D + half * 32;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
             if (q0 + (int)quad * 32 >= len) {
                 // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
                 for (int j = 0; j < nkt; ++j, ++g) {
@@ -276,23 +269,23 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 if (lane == 0) mbar_arrive(o_free);
                 if (qrow < p.S) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
                 }
                 continue;
             }
-            float m_run = -INFINITY, l_run = 0.f;   // l_run: this thread's half of the row sum
-            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow + (int)half * 64;   // + k0 + i
+            float m_run = -INFINITY, l_run = 0.f;
+            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow;   // + kcol
             for (int j = 0; j < nkt; ++j, ++g) {
-                const int k0 = j * AT_BK + (int)half * 64;       // first key of this thread's half tile
-                const int nch = max(0, min(2, (len - k0 + 31) >> 5));   // 32-key chunks with at least one valid key
+                const int k0 = j * AT_BK;
+                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
                 mbar_wait(s_full, (uint32_t)g & 1u);
                 tcgen05_fence_after();
-                float t[2][32];
+                float t[4][32];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     if (c < nch) {
                         uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c * 32, v);
+                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
@@ -305,10 +298,10 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     if (c < nch) {
                         if (HAS_BIAS) {
-                            const float* bp = sBias + bias_base + j * AT_BK + c * 32;
+                            const float* bp = sBias + bias_base + k0 + c * 32;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
                         } else {
@@ -327,11 +320,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                         }
                     }
                 }
-                // combine the two halves' row maxima
-                float* xch = sXch + (g & 1) * 256;
-                xch[half * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                const float tile_max = fmaxf(xch[row], xch[128 + row]);
+                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
                 float corr = 1.f;
                 bool rescale = false;
@@ -351,20 +340,20 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                     tcgen05_fence_after();
                     if (rescale) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {   // this thread's 32 of the 64 output columns
+                        for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
                             uint32_t ov[16];
-                            tmem_ld_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                            tmem_st_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                         }
                     }
                 }
                 // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
                 float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
                     if (c < nch) {
 #pragma unroll
@@ -379,7 +368,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
-                    tmem_st_32x32b_x16(tmem_P + lane_off + half * 32 + c * 16, pk);
+                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
                 }
                 l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
                 tmem_st_wait();
@@ -387,23 +376,20 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
-            // ---- epilogue of this query tile: O / l, this thread's 32 output columns
-            {
-                float* xch = sXch + 2 * 256;   // third buffer: never aliases a tile's max exchange
-                xch[half * 128 + row] = l_run;
-                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                l_run = xch[row] + xch[128 + row];
-            }
+            // ---- epilogue of this query tile: O / l
             mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
             tcgen05_fence_after();
             const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-            {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, ov);
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
                 tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(o_free);   // O copied out: the next query tile's first P.V may overwrite it
+                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_free);
+                }
                 if (qrow < p.S) {
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
@@ -411,7 +397,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
-                        *reinterpret_cast<uint4*>(orow + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -444,8 +430,8 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         max_set[which] = smem;
     }
     dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
-    if (bias_table) attn_tc_d64_kernel<true><<<grid, AT_THREADS, smem, stream>>>(tm, p);
-    else            attn_tc_d64_kernel<false><<<grid, AT_THREADS, smem, stream>>>(tm, p);
+    if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
+    else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
     return cudaGetLastError();
 }
 

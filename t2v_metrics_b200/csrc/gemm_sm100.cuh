@@ -13,6 +13,7 @@
 #pragma once
 #include "ptx.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace vqa {
 
@@ -472,7 +473,11 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
     const int rows_per_tile = Cfg::BLOCK_M * CG;
     p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    p.group_m = max(1, 2048 / rows_per_tile);
+    // Tile order: groups of `group_rows` A rows sweep all N tiles before the next group starts, so the group's A panel
+    // (group_rows x K) stays in L2 while W streams. 16 MB of A per group by default; VQA_GEMM_GROUP_ROWS overrides (tuning).
+    static const int env_rows = [] { const char* v = getenv("VQA_GEMM_GROUP_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
+    int group_rows = env_rows > 0 ? env_rows : 2048;
+    p.group_m = max(1, group_rows / rows_per_tile);
     const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_batches;
     int workers = num_sms / CG;
     if (workers > num_tiles) workers = num_tiles;

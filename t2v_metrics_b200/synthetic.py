@@ -101,3 +101,64 @@ def synthetic_batch(cfg: ClipT5Config, batch: int, text_len: int = 97, seed: int
     if torch.cuda.is_available():
         out = {k: v.pin_memory() for k, v in out.items()}
     return out
+
+
+def synthetic_qwen_engine_weights(cfg, device, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Qwen2.5-VL weights in the engine's fused/padded layout (see engine.convert_qwen_state_dict), generated on the GPU."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+
+    def nrm(*shape, std=0.02):
+        return torch.randn(*shape, generator=g, device=device, dtype=torch.bfloat16) * std
+
+    def gain(n):
+        return (1.0 + 0.1 * torch.randn(n, generator=g, device=device)).to(torch.bfloat16)
+
+    Dv, H, hd, mp, mlp_v = cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim, cfg.vit_mlp_padded, cfg.vit_mlp
+    out["vis.patch_embed"] = nrm(Dv, cfg.patch_dim, std=cfg.patch_dim ** -0.5)
+    for l in range(cfg.vit_depth):
+        q = f"vis.{l}."
+        out[q + "norm1"] = gain(Dv); out[q + "norm2"] = gain(Dv)
+        w = torch.zeros(3, H, 128, Dv, device=device, dtype=torch.bfloat16); w[:, :, :hd] = nrm(3, H, hd, Dv, std=Dv ** -0.5)
+        b = torch.zeros(3, H, 128, device=device, dtype=torch.bfloat16); b[:, :, :hd] = nrm(3, H, hd)
+        out[q + "qkv.weight"] = w.reshape(3 * H * 128, Dv).contiguous(); out[q + "qkv.bias"] = b.reshape(-1).contiguous()
+        pw = torch.zeros(Dv, H, 128, device=device, dtype=torch.bfloat16); pw[:, :, :hd] = nrm(Dv, H, hd, std=Dv ** -0.5)
+        out[q + "proj.weight"] = pw.reshape(Dv, H * 128).contiguous(); out[q + "proj.bias"] = nrm(Dv)
+        gu = torch.zeros(2 * mp, Dv, device=device, dtype=torch.bfloat16)
+        gu[:mlp_v] = nrm(mlp_v, Dv, std=Dv ** -0.5); gu[mp:mp + mlp_v] = nrm(mlp_v, Dv, std=Dv ** -0.5)
+        gb = torch.zeros(2 * mp, device=device, dtype=torch.bfloat16); gb[:mlp_v] = nrm(mlp_v); gb[mp:mp + mlp_v] = nrm(mlp_v)
+        out[q + "gate_up.weight"] = gu; out[q + "gate_up.bias"] = gb
+        dw = torch.zeros(Dv, mp, device=device, dtype=torch.bfloat16); dw[:, :mlp_v] = nrm(Dv, mlp_v, std=mlp_v ** -0.5)
+        out[q + "down.weight"] = dw; out[q + "down.bias"] = nrm(Dv)
+    M = Dv * cfg.spatial_merge_size ** 2
+    out["vis.merger.ln_q"] = gain(Dv)
+    out["vis.merger.fc1.weight"] = nrm(M, M, std=M ** -0.5); out["vis.merger.fc1.bias"] = nrm(M)
+    out["vis.merger.fc2.weight"] = nrm(cfg.out_hidden, M, std=M ** -0.5); out["vis.merger.fc2.bias"] = nrm(cfg.out_hidden)
+    D, kvd = cfg.hidden, cfg.kv_heads * cfg.head_dim
+    out["llm.embed"] = nrm(cfg.vocab, D, std=1.0)
+    out["llm.norm"] = gain(D)
+    out["llm.lm_head"] = nrm(cfg.vocab, D, std=D ** -0.5)
+    for l in range(cfg.layers):
+        q = f"llm.{l}."
+        out[q + "ln1"] = gain(D); out[q + "ln2"] = gain(D)
+        out[q + "qkv.weight"] = nrm(D + 2 * kvd, D, std=D ** -0.5); out[q + "qkv.bias"] = nrm(D + 2 * kvd, std=0.1)
+        out[q + "o.weight"] = nrm(D, D, std=D ** -0.5)
+        out[q + "gate_up.weight"] = nrm(2 * cfg.mlp, D, std=D ** -0.5)
+        out[q + "down.weight"] = nrm(D, cfg.mlp, std=cfg.mlp ** -0.5)
+    return out
+
+
+def synthetic_qwen_batch(cfg, batch: int, image_hw=(448, 448), text_len: int = 64, seed: int = 1, answer_id: int = 9454):
+    """BASELINE config 3: `batch` still images of image_hw (already multiples of 28) as processor-layout patches
+    [batch * h/14 * w/14, 1176] fp32 (normalised noise), prompts of `text_len` text ids around one image-token run."""
+    g = torch.Generator().manual_seed(seed)
+    gh, gw = image_hw[0] // cfg.patch_size, image_hw[1] // cfg.patch_size
+    n_tok = gh * gw // cfg.spatial_merge_size ** 2
+    patches = torch.randn(batch * gh * gw, cfg.patch_dim, generator=g)
+    prompts = []
+    for b in range(batch):
+        txt = torch.randint(0, min(cfg.image_token_id, cfg.vocab - 8), (text_len,), generator=g)
+        pre = 14                                     # chat-template prefix length before <|vision_start|>
+        prompts.append(torch.cat([txt[:pre], torch.full((n_tok,), cfg.image_token_id), txt[pre:]]).tolist())
+    return dict(pixel_patches=patches.pin_memory() if torch.cuda.is_available() else patches, grid_thw=[(1, gh, gw)] * batch,
+                prompts=prompts, answer_ids=[answer_id % cfg.vocab] * batch)

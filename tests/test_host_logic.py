@@ -64,7 +64,7 @@ def test_clip_preprocess_matches_hf_processor():
 
 
 def test_registry_surface_matches_reference():
-    assert t2v.list_all_models() == ["clip-flant5-xxl", "clip-flant5-xl"]
+    assert t2v.list_all_models() == ["clip-flant5-xxl", "clip-flant5-xl", "qwen2.5-vl-7b"]
     assert CLIPT5Model.video_mode == "concat" and CLIPT5Model.allows_image
     assert set(CLIP_T5_MODELS["clip-flant5-xxl"]) >= {"tokenizer", "model"}
     with pytest.raises(NotImplementedError):
@@ -90,3 +90,20 @@ def test_shard_bounds_cover_all_pairs_once(n, world):
         assert 0 <= s <= e <= n and e - s <= per
         seen.extend(range(s, e))
     assert seen == list(range(n))
+
+
+def test_qwen_patch_layout_matches_hf_processor():
+    """a19: smart_resize + patch flattening vs transformers' Qwen2VLImageProcessor (do_resize=False on a pre-sized image, as the
+    reference calls it after qwen_vl_utils resized the image: qwen2vl_model.py:208-216)."""
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor, smart_resize as hf_smart_resize
+    from t2v_metrics_b200.models.vqascore_models.qwen_utils import smart_resize, qwen_image_to_patches
+    for hw in [(448, 448), (500, 333), (30, 4000), (2000, 3000), (57, 57)]:
+        assert smart_resize(*hw) == hf_smart_resize(*hw)
+    rng = np.random.RandomState(0)
+    proc = Qwen2VLImageProcessor()
+    for (h, w) in [(448, 448), (84, 140)]:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        ref = proc(images=[img], do_resize=False, return_tensors="pt")
+        got, grid = qwen_image_to_patches(img)
+        assert list(grid) == ref["image_grid_thw"][0].tolist()
+        assert float((got - ref["pixel_values"]).abs().max()) < 1e-5

@@ -102,6 +102,21 @@ def t_gemm_perf(variant, M, N, K, epilogue="store"):
          cublas_ms=ms_ref, cublas_tflops=2.0 * M * N * K / ms_ref / 1e9)
 
 
+def t_gemm_once(variant, M, N, K, epilogue="store", reps=3):
+    """A few launches of one GEMM shape (run under ncu --metrics dram__bytes... to read its DRAM traffic)."""
+    from t2v_metrics_b200.engine import ops
+    variant, M, N, K, reps = int(variant), int(M), int(N), int(K), int(reps)
+    dev = "cuda:0"
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * (K ** -0.5)).bfloat16()
+    n_out = N // 2 if epilogue == "gated_gelu" else N
+    out = torch.empty(M, n_out, dtype=torch.bfloat16, device=dev)
+    for _ in range(reps):
+        ops.gemm(a, w, epilogue=epilogue, variant=variant, out=out, gate_up_offset=N // 2)
+    torch.cuda.synchronize()
+    emit(test="gemm_once", M=M, N=N, K=K, epilogue=epilogue, group_rows=os.environ.get("VQA_GEMM_GROUP_ROWS", "default"))
+
+
 def t_norm():
     from t2v_metrics_b200.engine import ops
     dev = "cuda:0"
