@@ -474,9 +474,19 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
     p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     // Tile order: groups of `group_rows` A rows sweep all N tiles before the next group starts, so the group's A panel
-    // (group_rows x K) stays in L2 while W streams. 16 MB of A per group by default; VQA_GEMM_GROUP_ROWS overrides (tuning).
+    // (group_rows x K) stays in L2 while W streams. Measured on B200 (profiles/r01_summary.md, DRAM bytes per launch): a
+    // ~32 MB A panel minimises re-reads when W is larger than L2 (FFN wi: 9.6 / 4.3 / 3.1 / 6.7 GB at 1024 / 2048 / 4096 /
+    // 8192 rows); when W itself fits in L2 a small group is best. VQA_GEMM_GROUP_ROWS overrides (tuning).
     static const int env_rows = [] { const char* v = getenv("VQA_GEMM_GROUP_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
-    int group_rows = env_rows > 0 ? env_rows : 2048;
+    int group_rows;
+    if (env_rows > 0) {
+        group_rows = env_rows;
+    } else if ((long long)g.w_rows * p.K * 2 <= (48ll << 20)) {
+        group_rows = 1024;
+    } else {
+        group_rows = (int)((32ll << 20) / ((long long)p.K * 2));
+        group_rows = max(512, min(8192, group_rows / 256 * 256));
+    }
     p.group_m = max(1, group_rows / rows_per_tile);
     const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_batches;
     int workers = num_sms / CG;
