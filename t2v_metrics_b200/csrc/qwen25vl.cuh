@@ -170,8 +170,9 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         {
             ProfScope ps(h, CAT_OTHER, 0, st);
             ++*lc;
-            rope_inplace_kernel<<<(unsigned)(((long long)L * 2 * Hv + 7) / 8), 256, 0, st>>>(P_(w.vqkv), 3 * Hv * 128, 0, 2 * Hv, 128, hdv,
-                                                                                          F_(w.vcos), F_(w.vsin), L, 0);
+            const long long nthr = (long long)L * 2 * Hv * (hdv / 16);
+            rope_inplace_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(P_(w.vqkv), 3 * Hv * 128, 0, 2 * Hv, 128, hdv, F_(w.vcos),
+                                                                            F_(w.vsin), L, 0);
             TRY(cuda_ok(cudaSuccess, "vision rope"));
         }
         {
@@ -211,8 +212,9 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
             ProfScope ps(h, CAT_OTHER, 0, st);
             ++*lc;
             // q heads and k heads are contiguous in the packed buffer -> one launch rotates Hq + Hkv heads
-            rope_inplace_kernel<<<(unsigned)(((long long)M * (Hq + Hkv) + 7) / 8), 256, 0, st>>>(P_(w.qkv), qkv_cols, 0, Hq + Hkv, 128, 128, F_(w.cos),
-                                                                                               F_(w.sin), M, c.emulate_bf16_rounding);
+            const long long nthr = (long long)M * (Hq + Hkv) * 8;
+            rope_inplace_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(P_(w.qkv), qkv_cols, 0, Hq + Hkv, 128, 128, F_(w.cos), F_(w.sin), M,
+                                                                            c.emulate_bf16_rounding);
             TRY(cuda_ok(cudaSuccess, "llm rope"));
         }
         {

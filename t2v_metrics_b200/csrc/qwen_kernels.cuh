@@ -26,35 +26,55 @@ __global__ void rope_table_kernel(const int* __restrict__ pos, int rows, const i
 }
 
 // In-place rotary embedding on `n_heads` consecutive heads of a packed row-major buffer (head h at column col0 + h*head_stride,
-// `head_dim` <= head_stride real dims): x' = x*cos + rotate_half(x)*sin  (modeling_qwen2_5_vl.py:156-167, :650-669).
-// bf16_products: the text path multiplies in bf16 (each product and the sum are rounded); the vision path works in fp32.
-// One warp per (row, head); lane handles dims lane, lane+32, ... of the first half.
+// `head_dim` <= head_stride real dims, head_dim % 16 == 0): x' = x*cos + rotate_half(x)*sin  (modeling_qwen2_5_vl.py:156-167,
+// :650-669). bf16_products: the text path multiplies in bf16 (each product and the sum are rounded); the vision path works in
+// fp32. One thread per (row, head, 8-dim chunk of the first half): 16-byte loads/stores of both halves.
 __global__ void rope_inplace_kernel(__nv_bfloat16* __restrict__ x, int ld, int col0, int n_heads, int head_stride,
                                     int head_dim, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                     long long rows, int bf16_products) {
-    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= rows * n_heads) return;
-    const int lane = threadIdx.x & 31;
-    const long long row = w / n_heads;
-    const int h = (int)(w % n_heads);
-    __nv_bfloat16* px = x + (size_t)row * ld + col0 + h * head_stride;
-    const float* pc = cos_t + (size_t)row * head_dim;
-    const float* ps = sin_t + (size_t)row * head_dim;
     const int half = head_dim >> 1;
-    for (int i = lane; i < half; i += 32) {
-        const float x1 = __bfloat162float(px[i]), x2 = __bfloat162float(px[i + half]);
-        const float c1 = pc[i], s1 = ps[i], c2 = pc[i + half], s2 = ps[i + half];
-        float o1, o2;
-        if (bf16_products) {
-            o1 = bf16_round(x1 * c1) + bf16_round(-x2 * s1);
-            o2 = bf16_round(x2 * c2) + bf16_round(x1 * s2);
-        } else {
-            o1 = x1 * c1 - x2 * s1;
-            o2 = x2 * c2 + x1 * s2;
-        }
-        px[i] = __float2bfloat16_rn(o1);
-        px[i + half] = __float2bfloat16_rn(o2);
+    const int chunks = half >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * n_heads * chunks) return;
+    const int c = (int)(idx % chunks);
+    const int h = (int)((idx / chunks) % n_heads);
+    const long long row = idx / ((long long)chunks * n_heads);
+    __nv_bfloat16* px = x + (size_t)row * ld + col0 + h * head_stride + c * 8;
+    const float* pc = cos_t + (size_t)row * head_dim + c * 8;
+    const float* ps = sin_t + (size_t)row * head_dim + c * 8;
+    const uint4 v1 = *reinterpret_cast<const uint4*>(px);
+    const uint4 v2 = *reinterpret_cast<const uint4*>(px + half);
+    const uint32_t* u1 = reinterpret_cast<const uint32_t*>(&v1);
+    const uint32_t* u2 = reinterpret_cast<const uint32_t*>(&v2);
+    float c1[8], s1[8], c2[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<float4*>(&c1[4 * i]) = *reinterpret_cast<const float4*>(pc + 4 * i);
+        *reinterpret_cast<float4*>(&s1[4 * i]) = *reinterpret_cast<const float4*>(ps + 4 * i);
+        *reinterpret_cast<float4*>(&c2[4 * i]) = *reinterpret_cast<const float4*>(pc + half + 4 * i);
+        *reinterpret_cast<float4*>(&s2[4 * i]) = *reinterpret_cast<const float4*>(ps + half + 4 * i);
     }
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack_bf16x2(u1[e]), b2 = unpack_bf16x2(u2[e]);
+        float r1x, r1y, r2x, r2y;
+        if (bf16_products) {
+            r1x = bf16_round(a.x * c1[2 * e]) + bf16_round(-b2.x * s1[2 * e]);
+            r1y = bf16_round(a.y * c1[2 * e + 1]) + bf16_round(-b2.y * s1[2 * e + 1]);
+            r2x = bf16_round(b2.x * c2[2 * e]) + bf16_round(a.x * s2[2 * e]);
+            r2y = bf16_round(b2.y * c2[2 * e + 1]) + bf16_round(a.y * s2[2 * e + 1]);
+        } else {
+            r1x = a.x * c1[2 * e] - b2.x * s1[2 * e];
+            r1y = a.y * c1[2 * e + 1] - b2.y * s1[2 * e + 1];
+            r2x = b2.x * c2[2 * e] + a.x * s2[2 * e];
+            r2y = b2.y * c2[2 * e + 1] + a.y * s2[2 * e + 1];
+        }
+        o1[e] = pack_bf16x2(r1x, r1y);
+        o2[e] = pack_bf16x2(r2x, r2y);
+    }
+    *reinterpret_cast<uint4*>(px) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(px + half) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
 }
 
 // dst row r = src row index[r / group] * group + r % group (window re-ordering of 2x2 patch groups, and its inverse on the

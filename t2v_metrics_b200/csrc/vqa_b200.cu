@@ -819,8 +819,8 @@ extern "C" void vqa_destroy(vqa_handle* h) {
 extern "C" int vqa_create_qwen25vl(const vqa_qwen25vl_config* cfg, int device, vqa_handle** out) {
     if (!cfg || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null argument");
     if (cfg->heads % cfg->kv_heads) return fail(nullptr, VQA_ERR_INVALID_ARG, "heads % kv_heads != 0");
-    if (cfg->vit_head_dim > 128 || cfg->vit_head_dim % 2 || cfg->vit_hidden != cfg->vit_heads * cfg->vit_head_dim)
-        return fail(nullptr, VQA_ERR_UNSUPPORTED, "vision head_dim must be even, <= 128 and hidden = heads * head_dim");
+    if (cfg->vit_head_dim > 128 || cfg->vit_head_dim % 16 || cfg->vit_hidden != cfg->vit_heads * cfg->vit_head_dim)
+        return fail(nullptr, VQA_ERR_UNSUPPORTED, "vision head_dim must be a multiple of 16, <= 128, and hidden = heads * head_dim");
     if (cfg->hidden % 8 || cfg->mlp % 128 || cfg->vit_hidden % 8 || cfg->patch_dim % 8)
         return fail(nullptr, VQA_ERR_UNSUPPORTED, "hidden % 8, mlp % 128, vit_hidden % 8, patch_dim % 8 must be 0");
     if (cfg->vit_depth > 64) return fail(nullptr, VQA_ERR_UNSUPPORTED, "vit_depth > 64");
