@@ -48,6 +48,16 @@ def measured_peaks():
         return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def measured_traffic(model):
+    """DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/r01_gemm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(model)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -223,9 +233,10 @@ def run_engine(args, rank, local_rank, world):
 
     if rank == 0:
         peaks = measured_peaks()
-        gemm_ms, gemm_flops, gemm_n = prof["gemm"]
+        gemm_ms, gemm_flops, gemm_n, gemm_bytes = prof["gemm"]
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         value = total_pairs / (ms_step * 1e-3)
+        traffic = measured_traffic(args.model)
         fpp = FLOPS_PER_PAIR.get(args.model)
         line = dict(
             metric="VQAScore (image,text) pairs/sec @ clip-flant5-xxl, 512px", value=value, unit="pairs/s", n_gpus=world,
@@ -236,7 +247,9 @@ def run_engine(args, rank, local_rank, world):
                         model=args.model, global_batch=total_pairs, seq_len=L - 1 + cfg.num_patches, parallelism=f"dp{world}",
                         l2_policy="inputs larger than L2: 22.6 GB of weights + 4.5 GB of activations stream per step"),
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                          frac=(achieved / peaks["tflops"]) if achieved else None, traffic=None,
+                          frac=(achieved / peaks["tflops"]) if achieved else None,
+                          traffic=traffic.get("dram_bytes_per_launch") if traffic else None, traffic_source=traffic.get("source") if traffic else None,
+                          algorithmic_bytes_per_launch=gemm_bytes / max(gemm_n, 1),
                           kernel="gemm_bf16_sm100_kernel (all tcgen05 GEMM launches of the step)",
                           flops_per_launch=gemm_flops / max(gemm_n, 1), launches=gemm_n, device_ms=gemm_ms, peak_source=peaks["source"],
                           whole_step_tflops=(value / world) * fpp / 1e12 if fpp else None),
@@ -337,7 +350,7 @@ def run_engine_qwen(args, rank, local_rank, world):
     h2d = host["pixel_patches"].numel() * 4 + sum(v.numel() * 4 for v in idx.values()) + B * 4
     if rank == 0:
         peaks = measured_peaks()
-        gemm_ms, gemm_flops, gemm_n = prof["gemm"]
+        gemm_ms, gemm_flops, gemm_n, gemm_bytes = prof["gemm"]
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         value = total / (ms_step * 1e-3)
         line = dict(metric="VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px", value=value, unit="pairs/s", n_gpus=world, steps=args.steps,

@@ -174,10 +174,11 @@ int64_t vqa_last_launch_count(vqa_handle* h);
 
 /* Optional device-side timing of the forward: with profiling on, every launch of vqa_clipt5_score is bracketed by CUDA
  * events on the caller's stream. After the caller synchronised the stream, vqa_profile_read returns, per category
- * {0 gemm, 1 attention, 2 norm, 3 other} (arrays of 4): device ms, algorithmic FLOPs (2MNK / 4*S*S*d) and scope counts
- * of the LAST call. Used by bench.py for the roofline object. */
+ * {0 gemm, 1 attention, 2 norm, 3 other} (arrays of 4): device ms, algorithmic FLOPs (2MNK / 4*S*S*d), algorithmic bytes
+ * (GEMM: A and W read once, C written once, residual read once) and scope counts of the LAST call. Used by bench.py for the
+ * roofline object. */
 int vqa_set_profile(vqa_handle* h, int32_t enable);
-int vqa_profile_read(vqa_handle* h, float* ms, double* flops, int64_t* scopes);
+int vqa_profile_read(vqa_handle* h, float* ms, double* flops, double* bytes, int64_t* scopes);
 
 const char* vqa_last_error(vqa_handle* h);
 void vqa_destroy(vqa_handle* h);

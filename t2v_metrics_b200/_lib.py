@@ -79,7 +79,7 @@ def load() -> C.CDLL:
     lib.vqa_clipt5_score.restype = C.c_int
     lib.vqa_set_profile.argtypes = [vp, i32]
     lib.vqa_set_profile.restype = C.c_int
-    lib.vqa_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.vqa_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.vqa_profile_read.restype = C.c_int
     lib.vqa_last_launch_count.argtypes = [vp]
     lib.vqa_last_launch_count.restype = i64

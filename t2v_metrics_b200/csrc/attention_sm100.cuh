@@ -280,64 +280,67 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
                 mbar_wait(s_full, (uint32_t)g & 1u);
                 tcgen05_fence_after();
+                float t[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
+                    }
+                }
+                // S is in registers: hand the TMEM columns back so the next QK^T can start
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
 
-                // Streaming softmax over the tile's 32-key chunks with the TMEM read of chunk c+1 in flight while chunk c is
-                // being exponentiated (tcgen05.wait::ld covers every load issued so far, so the next load is issued right
-                // AFTER the wait for the current one). TMEM read bandwidth (~64 B/clk/SM) and the MUFU pipe (ex2) are the two
-                // co-bottlenecks of this kernel; keeping both busy at the same time is the point of this schedule.
-                // Reference maximum: for j > 0 the running maximum m_run (lazy rescale rule: any row growing by more than
-                // 2^8 forces an exact redo of the tile); for j == 0 the maximum of the first chunk, same rule.
-                auto finish_chunk = [&](int c, const uint32_t (&v)[32], float (&t)[32]) {   // raw S -> log2-domain scores
-                    if (HAS_BIAS) {
-                        const float* bp = sBias + bias_base + k0 + c * 32;
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) t[i] = fmaf(__uint_as_float(v[i]), p.scale_log2e, bp[i]);
-                    } else {
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        if (HAS_BIAS) {
+                            const float* bp = sBias + bias_base + k0 + c * 32;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(v[i]) * p.scale_log2e;
+                            for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
+                        }
+                        if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (k0 + c * 32 + i >= len) t[c][i] = -INFINITY;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
+                            mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
+                        }
                     }
-                    if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (k0 + c * 32 + i >= len) t[i] = -INFINITY;
+                }
+                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
+                float corr = 1.f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_run = tile_max;
+                } else {
+                    const bool need = tile_max > m_run + 8.f;
+                    rescale = __any_sync(0xffffffffu, need);
+                    if (rescale) {
+                        const float m_new = fmaxf(m_run, tile_max);
+                        corr = fast_exp2(m_run - m_new);
+                        m_run = m_new;
                     }
-                };
-                auto chunk_max = [&](const float (&t)[32]) {
-                    float a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3];
+                }
+                if (j > 0) {
+                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                    tcgen05_fence_after();
+                    if (rescale) {
 #pragma unroll
-                    for (int i = 4; i < 32; i += 4) {
-                        a0 = fmaxf(a0, t[i]); a1 = fmaxf(a1, t[i + 1]); a2 = fmaxf(a2, t[i + 2]); a3 = fmaxf(a3, t[i + 3]);
-                    }
-                    return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-                };
-
-                bool exact = false;
-                bool o_synced = (j == 0);
-                float m_ref = m_run, corr = 1.f, psum = 0.f;
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    if (exact) {   // rare path: exact row maximum of the whole tile first (S is still in TMEM)
-                        float tm = -INFINITY;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c < nch) {
-                                uint32_t v[32];
-                                float t[32];
-                                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                                tmem_ld_wait();
-                                finish_chunk(c, v, t);
-                                tm = fmaxf(tm, chunk_max(t));
-                            }
-                        m_ref = (j == 0) ? tm : fmaxf(m_run, tm);
-                        corr = (j == 0) ? 1.f : fast_exp2(m_run - m_ref);
-                    }
-                    if (!o_synced) {
-                        mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
-                        tcgen05_fence_after();
-                        o_synced = true;
-                    }
-                    if (exact && j > 0 && __any_sync(0xffffffffu, m_ref > m_run)) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
                             uint32_t ov[16];
                             tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                             tmem_ld_wait();
@@ -346,52 +349,32 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                             tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
                         }
                     }
-                    float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f, tmax = -INFINITY;
-                    uint32_t va[32], vb[32];
-                    tmem_ld_32x32b_x32(tmem_S + lane_off, va);          // chunk 0 (nch >= 1 always)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[16];
-                        if (c < nch) {
-                            tmem_ld_wait();                              // chunk c has landed
-                            uint32_t (&cur)[32] = (c & 1) ? vb : va;
-                            uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-                            if (c + 1 < nch) tmem_ld_32x32b_x32(tmem_S + lane_off + (c + 1) * 32, nxt);   // prefetch chunk c+1
-                            float t[32];
-                            finish_chunk(c, cur, t);
-                            const float cm = chunk_max(t);
-                            if (!exact && j == 0 && c == 0) m_ref = cm;   // first chunk of a query tile seeds the reference
-                            tmax = fmaxf(tmax, cm);
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                const float e0 = fast_exp2(t[2 * i] - m_ref),     e1 = fast_exp2(t[2 * i + 1] - m_ref);
-                                const float e2 = fast_exp2(t[2 * i + 2] - m_ref), e3 = fast_exp2(t[2 * i + 3] - m_ref);
-                                ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-                                pk[i] = pack_bf16x2(e0, e1);
-                                pk[i + 1] = pack_bf16x2(e2, e3);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-                        }
-                        tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-                    }
-                    psum = (ps0 + ps1) + (ps2 + ps3);
-                    if (!exact && __any_sync(0xffffffffu, !(tmax <= m_ref + 8.f))) {
-                        exact = true;    // a row outgrew the reference by more than 2^8 (or has no finite reference): redo exactly
-                        continue;
-                    }
-                    break;
                 }
-                l_run = l_run * corr + psum;
-                m_run = m_ref;
+                // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
+                float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+                    if (c < nch) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                            const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
+                            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+                            pk[i] = pack_bf16x2(e0, e1);
+                            pk[i + 1] = pack_bf16x2(e2, e3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    }
+                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                }
+                l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(s_empty);   // S fully consumed: the next QK^T may overwrite it
-                    mbar_arrive(p_full);
-                }
+                if (lane == 0) mbar_arrive(p_full);
             }
             // ---- epilogue of this query tile: O / l
             mbar_wait(o_done, (uint32_t)(g - 1) & 1u);

@@ -128,7 +128,9 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     };
     auto gemm = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M_, int N_, int K_,
                     const bf16* bias, const bf16* res, int ldr, int epi, int gate_off) -> int {
-        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st);
+        const double n_out = epi_is_gated(epi) ? N_ / 2 : N_;
+        const double bytes = 2.0 * ((double)M_ * K_ + (double)N_ * K_ + (double)M_ * n_out * (res ? 2 : 1));
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st, bytes);
         return cuda_ok(run_gemm(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, bias, res, ldr, epi, gate_off, 0, nsm, st, lc), "gemm");
     };
     auto rms = [&](const bf16* x, const bf16* wgt, bf16* y, int rows, int D_) -> int {
@@ -238,7 +240,7 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     TRY(rms(P_(w.last), q.final_norm, P_(w.lastn), B, D));
     const int ntiles = LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
     {
-        ProfScope ps(h, CAT_GEMM, 2.0 * B * (double)c.vocab * D, st);
+        ProfScope ps(h, CAT_GEMM, 2.0 * B * (double)c.vocab * D, st, 2.0 * ((double)B * D + (double)c.vocab * D));
         TRY(cuda_ok(run_lmhead(P_(w.lastn), D, q.lm_head, D, B, c.vocab, D, answer_ids, F_(w.lse_max), F_(w.lse_sum), F_(w.label_logit), nsm, st,
                                lc, 1.0f / temperature), "lm_head"));
     }

@@ -65,7 +65,7 @@ struct vqa_handle {
     // optional per-category device timing (vqa_set_profile): CUDA events around every launch of the forward
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
-    struct ProfRec { int cat; double flops; int ev0, ev1; };
+    struct ProfRec { int cat; double flops; double bytes; int ev0, ev1; };
     std::vector<ProfRec> prof;
     size_t ev_used = 0;
 };
@@ -75,14 +75,14 @@ enum ProfCat { CAT_GEMM = 0, CAT_ATTENTION = 1, CAT_NORM = 2, CAT_OTHER = 3, CAT
 // Records an event pair around the launches issued in its lifetime (only in profile mode).
 struct ProfScope {
     vqa_handle* h; cudaStream_t st; int idx = -1;
-    ProfScope(vqa_handle* h_, int cat, double flops, cudaStream_t st_) : h(h_), st(st_) {
+    ProfScope(vqa_handle* h_, int cat, double flops, cudaStream_t st_, double bytes = 0.0) : h(h_), st(st_) {
         if (!h->profile) return;
         while (h->ev_pool.size() < h->ev_used + 2) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) return;
             h->ev_pool.push_back(e);
         }
-        vqa_handle::ProfRec r{cat, flops, (int)h->ev_used, (int)h->ev_used + 1};
+        vqa_handle::ProfRec r{cat, flops, bytes, (int)h->ev_used, (int)h->ev_used + 1};
         h->ev_used += 2;
         cudaEventRecord(h->ev_pool[r.ev0], st);
         idx = (int)h->prof.size();
@@ -589,7 +589,10 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     };
     auto gemm = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M_, int N_, int K_,
                     const bf16* bias, const bf16* res, int ldr, int epi, int gate_off) -> int {
-        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st);
+        // algorithmic bytes: A and W read once, C written once (+ residual read once)
+        const double n_out = epi_is_gated(epi) ? N_ / 2 : N_;
+        const double bytes = 2.0 * ((double)M_ * K_ + (double)N_ * K_ + (double)M_ * n_out * (res ? 2 : 1));
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st, bytes);
         return cuda_ok(run_gemm(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, bias, res, ldr, epi, gate_off, 0, nsm, st, lc), "gemm");
     };
     auto rms = [&](const bf16* x, const bf16* wgt, bf16* y, int rows) -> int {
@@ -722,7 +725,8 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
             const int TH = T * H;
             auto bgemm = [&](const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M_, int N_, int K_,
                              const BatchSpec& bs, int variant) -> int {
-                ProfScope ps(h, CAT_GEMM, 2.0 * bs.nb * (double)M_ * N_ * K_, st);
+                ProfScope ps(h, CAT_GEMM, 2.0 * bs.nb * (double)M_ * N_ * K_, st,
+                             2.0 * bs.nb * ((double)M_ * K_ + (double)N_ * K_ + (double)M_ * N_));
                 return cuda_ok(run_gemm_batched(A, lda, W, ldw, C, ldc, M_, N_, K_, bs, variant, nsm, st, lc), "batched gemm");
             };
             // (1) q~[b,t,h,:] = Wk[h]^T q[b,t,h,:]   -- per head: [B*T, 64] x ckT[:, h*64:(h+1)*64]^T -> rows (b*T+t)*H + h
@@ -760,7 +764,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     float* label_logit = reinterpret_cast<float*>(ws + w.label_logit);
     const int ntiles = LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
     {
-        ProfScope ps(h, CAT_GEMM, 2.0 * Md * (double)c.vocab * Dm, st);
+        ProfScope ps(h, CAT_GEMM, 2.0 * Md * (double)c.vocab * Dm, st, 2.0 * ((double)Md * Dm + (double)c.vocab * Dm));
         TRY(cuda_ok(run_lmhead(P_(w.yn), Dm, h->lm_head, Dm, Md, c.vocab, Dm, labels, lse_max, lse_sum, label_logit, nsm, st, lc),
                     "lm_head"));
     }
@@ -783,15 +787,16 @@ extern "C" int vqa_set_profile(vqa_handle* h, int32_t enable) {
 
 // After the stream has been synchronised by the caller: device milliseconds, algorithmic FLOPs and launch-scope counts of
 // the last vqa_clipt5_score call per category {0 gemm, 1 attention, 2 norm, 3 other}.
-extern "C" int vqa_profile_read(vqa_handle* h, float* ms, double* flops, int64_t* scopes) {
-    if (!h || !ms || !flops || !scopes) return VQA_ERR_INVALID_ARG;
-    for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.f; flops[i] = 0.0; scopes[i] = 0; }
+extern "C" int vqa_profile_read(vqa_handle* h, float* ms, double* flops, double* bytes, int64_t* scopes) {
+    if (!h || !ms || !flops || !bytes || !scopes) return VQA_ERR_INVALID_ARG;
+    for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.f; flops[i] = 0.0; bytes[i] = 0.0; scopes[i] = 0; }
     for (const auto& r : h->prof) {
         float t = 0.f;
         cudaError_t e = cudaEventElapsedTime(&t, h->ev_pool[r.ev0], h->ev_pool[r.ev1]);
         if (e != cudaSuccess) return fail(h, VQA_ERR_CUDA, std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e));
         ms[r.cat] += t;
         flops[r.cat] += r.flops;
+        bytes[r.cat] += r.bytes;
         scopes[r.cat] += 1;
     }
     return VQA_OK;

@@ -204,13 +204,14 @@ class ClipT5Engine:
         _check(self.lib.vqa_set_profile(self._h, 1 if enable else 0), self._h, "vqa_set_profile")
 
     def read_profile(self):
-        """After torch.cuda.synchronize(): {category: (device_ms, algorithmic_flops, scopes)} of the last call."""
+        """After torch.cuda.synchronize(): {category: (device_ms, algorithmic_flops, scopes, algorithmic_bytes)} of the last call."""
         ms = (C.c_float * 4)()
         fl = (C.c_double * 4)()
+        by = (C.c_double * 4)()
         sc = (C.c_int64 * 4)()
-        _check(self.lib.vqa_profile_read(self._h, ms, fl, sc), self._h, "vqa_profile_read")
+        _check(self.lib.vqa_profile_read(self._h, ms, fl, by, sc), self._h, "vqa_profile_read")
         names = ("gemm", "attention", "norm", "other")
-        return {n: (float(ms[i]), float(fl[i]), int(sc[i])) for i, n in enumerate(names)}
+        return {n: (float(ms[i]), float(fl[i]), int(sc[i]), float(by[i])) for i, n in enumerate(names)}
 
 
 # ------------------------------------------------------------------------------------------------ single-kernel ops
