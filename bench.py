@@ -33,6 +33,10 @@ def parse():
     ap.add_argument("--model", default="clip-flant5-xxl")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--text-len", type=int, default=97)
+    ap.add_argument("--ragged", action="store_true", help="clip-flant5: text lens ~U[64, text_len] instead of all = text_len (SURVEY 8d)")
+    ap.add_argument("--video", action="store_true", help="qwen: SURVEY 8(d) config 5 shape (grid 8x16x16, S=576, batch 8)")
+    ap.add_argument("--pairs", type=int, default=0, help="clip-flant5: SURVEY 8(d) config 4 -- a JOB of this many pairs sharded "
+                    "contiguously over the ranks in batches of --batch (+ tail), one all-gather; a step = the whole job; strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profiling pass: 2 device steps only, no JSON (run under ncu)")
     return ap.parse_args()
@@ -145,6 +149,72 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ engine arm
+def run_job(args, rank, world, dev, cfg, eng):
+    """N pairs, contiguous shard per rank (parallel.shard_bounds), full batches of --batch plus one
+    tail batch, ONE all-gather of the N fp32 scores at the end. A step is the whole job (strong scaling: the total is fixed)."""
+    import torch
+    import torch.distributed as dist
+    from t2v_metrics_b200.synthetic import synthetic_batch
+    from t2v_metrics_b200.parallel import gather_scores, shard_bounds
+    B, L, N = args.batch, args.text_len, args.pairs
+    start, end, per = shard_bounds(N, world, rank)
+    n_local = end - start
+    full = {k: v.to(dev) for k, v in synthetic_batch(cfg, B, L, seed=1 + rank, ragged=args.ragged).items()}
+    tail_n = n_local % B
+    tail = {k: v[:tail_n].contiguous() for k, v in full.items()} if tail_n else None
+    local = torch.empty(n_local, dtype=torch.float32, device=dev)
+
+    def job():
+        o = 0
+        for _ in range(n_local // B):
+            eng.score_tensors(full["pixels"], full["input_ids"], full["text_lens"], full["labels"], out=local[o:o + B])
+            o += B
+        if tail is not None:
+            eng.score_tensors(tail["pixels"], tail["input_ids"], tail["text_lens"], tail["labels"], out=local[o:o + tail_n])
+        return gather_scores(local, N) if world > 1 else local
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(3):        # warm-up: three full batches (+ the tail shape once)
+        eng.score_tensors(full["pixels"], full["input_ids"], full["text_lens"], full["labels"])
+    if tail is not None:
+        eng.score_tensors(tail["pixels"], tail["input_ids"], tail["text_lens"], tail["labels"])
+    sync_all()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 2))
+    sync_all()
+    ev0.record()
+    for _ in range(steps):
+        out = job()
+    ev1.record()
+    sync_all()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_job = float(t) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        assert out.numel() == N and bool(torch.isfinite(out).all()) and float(out.min()) >= 0 and float(out.max()) <= 1
+        print(json.dumps(dict(
+            metric="VQAScore (image,text) pairs/sec @ clip-flant5-xxl, 512px", value=N / (ms_job * 1e-3), unit="pairs/s", n_gpus=world,
+            steps=steps, warmup=3, ms_per_step=ms_job, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload=f"{args.model} VQAScore JOB: {N} pairs sharded contiguously over {world} GPU(s) = {per} per rank in batches of "
+                                 f"{B} + tail {per % B}, one all-gather of {N} fp32 scores; S_enc={L - 1 + cfg.num_patches}, T=2",
+                        model=args.model, global_batch=B * world, seq_len=L - 1 + cfg.num_patches, parallelism=f"dp{world}",
+                        l2_policy="inputs larger than L2"),
+            gpu_launches=int(eng.last_launch_count()) * (-(-n_local // B)) * steps, clocks=clocks)), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_engine(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -161,7 +231,9 @@ def run_engine(args, rank, local_rank, world):
     eng = ClipT5Engine(cfg, dev)
     eng.bind_engine_tensors(synthetic_engine_weights(cfg, dev, seed=0))
     B, L = args.batch, args.text_len
-    host = synthetic_batch(cfg, B, L, seed=1 + rank)
+    if args.pairs:
+        return run_job(args, rank, world, dev, cfg, eng)
+    host = synthetic_batch(cfg, B, L, seed=1 + rank, ragged=args.ragged)
     d = {k: v.to(dev) for k, v in host.items()}
     total_pairs = B * world
 
@@ -243,7 +315,7 @@ def run_engine(args, rank, local_rank, world):
             steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload=f"{args.model} VQAScore: batch {B}/GPU, synthetic 512x512 uint8 images -> 336px CLIP input, "
-                                 f"{L} ids incl. image slot (S_enc={L - 1 + cfg.num_patches}), labels [Yes,</s>] (T=2)",
+                                 f"{'64..' if args.ragged else ''}{L} ids incl. image slot (S_enc={L - 1 + cfg.num_patches}), labels [Yes,</s>] (T=2)",
                         model=args.model, global_batch=total_pairs, seq_len=L - 1 + cfg.num_patches, parallelism=f"dp{world}",
                         l2_policy="inputs larger than L2: 22.6 GB of weights + 4.5 GB of activations stream per step"),
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
@@ -286,10 +358,16 @@ def run_engine_qwen(args, rank, local_rank, world):
     cfg = QWEN25VL_MODELS[args.model]["config"]()
     eng = QwenVLEngine(cfg, dev)
     eng.bind_engine_tensors(synthetic_qwen_engine_weights(cfg, dev, seed=0))
-    B = args.batch if args.batch != 64 else 32
-    host = synthetic_qwen_batch(cfg, B, (448, 448), 64, seed=1 + rank)
+    # --video = SURVEY 8(d) config 5: 16 frames of 224x224 -> grid (8, 16, 16) = 2048 patches / 512 video tokens, S = 576, B = 8
+    video = bool(args.video)
+    B = args.batch if args.batch != 64 else (8 if video else 32)
+    hw, frames = ((224, 224), 8) if video else ((448, 448), 1)
+    host = synthetic_qwen_batch(cfg, B, hw, 64, seed=1 + rank, frames=frames)
+    seq_len = 64 + frames * (hw[0] // 28) * (hw[1] // 28)
+    flops_pair = 10.25e12 if video else FLOPS_PER_PAIR[args.model]
     idx = qwen_host.build_batch_indices(host["prompts"], host["grid_thw"], list(range(B)), cfg.image_token_id, cfg.spatial_merge_size,
-                                        cfg.tokens_per_second)
+                                        cfg.tokens_per_second, video_token_id=cfg.video_token_id,
+                                        second_per_grid_ts=[1.0] * B if video else None)
     idx = {k: v.pin_memory() for k, v in idx.items()}
     ans_h = torch.tensor(host["answer_ids"], dtype=torch.int32).pin_memory()
     d_idx = {k: v.to(dev) for k, v in idx.items()}
@@ -353,17 +431,20 @@ def run_engine_qwen(args, rank, local_rank, world):
         gemm_ms, gemm_flops, gemm_n, gemm_bytes = prof["gemm"]
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         value = total / (ms_step * 1e-3)
-        line = dict(metric="VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px", value=value, unit="pairs/s", n_gpus=world, steps=args.steps,
+        shape = ("synthetic 16-frame 224x224 videos (grid 8x16x16: 2048 patches, 512 video tokens) + 64 text ids (S=576)" if video else
+                 "synthetic 448x448 images (1024 patches, 256 vision tokens) + 64 text ids (S=320)")
+        line = dict(metric="VQAScore (video,text) pairs/sec @ qwen2.5-vl-7b, 16x224px" if video else
+                    "VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px", value=value, unit="pairs/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",
-                    config=dict(workload=f"{args.model} VQAScore: batch {B}/GPU, synthetic 448x448 images (1024 patches, 256 vision tokens) + 64 "
-                                         "text ids (S=320), one answer token", model=args.model, global_batch=total, seq_len=320,
+                    config=dict(workload=f"{args.model} VQAScore: batch {B}/GPU, {shape}, one answer token", model=args.model,
+                                global_batch=total, seq_len=seq_len,
                                 parallelism=f"dp{world}", l2_policy="inputs larger than L2: 16.6 GB of weights stream per step"),
                     roofline=dict(bound="tensor", achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
                                   frac=(achieved / peaks["tflops"]) if achieved else None, traffic=None,
                                   kernel="gemm_bf16_sm100_kernel (all tcgen05 GEMM launches of the step)", launches=gemm_n, device_ms=gemm_ms,
                                   flops_per_launch=gemm_flops / max(gemm_n, 1), peak_source=peaks["source"],
-                                  whole_step_tflops=(value / world) * FLOPS_PER_PAIR[args.model] / 1e12),
+                                  whole_step_tflops=(value / world) * flops_pair / 1e12),
                     breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
                     e2e=dict(value=total / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=B * 4, ms_per_step=e2e_ms),
                     gpu_launches=int(launches) * args.steps, clocks=clocks, sample_scores=[float(x) for x in out[:4].float().cpu()])

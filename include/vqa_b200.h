@@ -159,15 +159,18 @@ size_t vqa_qwen25vl_workspace_bytes(vqa_handle* h, int32_t batch, int32_t seq_le
  *   feat_index     [batch, seq_len] row of the merged vision features for image-token positions, -1 elsewhere
  *   position_ids   [3, batch*seq_len] (t, h, w) mRoPE positions
  *   answer_ids     [batch] the answer's first token id
- *   out_probs      [batch] softmax(last-position logits / temperature)[answer_id]; out_logprobs optional
+ *   repetition_penalty  1.0 = off; otherwise HF's RepetitionPenaltyLogitsProcessor over each sample's prompt ids is applied to the
+ *                  fp32 logits before the temperature (generation/utils.py:2762-2770; the checkpoint's generation_config.json
+ *                  decides it in the reference)
+ *   out_probs      [batch] softmax(processed last-position logits / temperature)[answer_id]; out_logprobs optional
  */
 int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int32_t pixel_dtype, int32_t n_patches,
                        const int32_t* vis_pos_hw, const int32_t* window_index, const int32_t* reverse_index,
                        const int32_t* cu_window, int32_t n_windows, int32_t max_window_len, const int32_t* cu_frames,
                        int32_t n_frames, int32_t max_frame_len, const int32_t* input_ids, const int32_t* seq_lens,
                        const int32_t* feat_index, const int32_t* position_ids, const int32_t* answer_ids, int32_t batch,
-                       int32_t seq_len, float temperature, float* out_probs, float* out_logprobs, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       int32_t seq_len, float temperature, float repetition_penalty, float* out_probs, float* out_logprobs,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels the last vqa_clipt5_score call launched (for bench.py's gpu_launches). */
 int64_t vqa_last_launch_count(vqa_handle* h);
@@ -182,6 +185,21 @@ int vqa_profile_read(vqa_handle* h, float* ms, double* flops, double* bytes, int
 
 const char* vqa_last_error(vqa_handle* h);
 void vqa_destroy(vqa_handle* h);
+
+/* ---- image pre-processing on the device ----
+ * Replaces expand2square (t2v_metrics/models/vqascore_models/mm_utils.py:128-139) + the CLIP image processor of the v3.0 wrapper
+ * (PIL BICUBIC resize of the shortest edge to out_size, centre crop, /255, (x - mean) / std): bit-identical to Pillow's integer
+ * resampling (Resample.c) and to the fp32 normalisation of oracle/clipt5_oracle.py:clip_preprocess.
+ *   src        DEVICE, the decoded images as packed HWC uint8 RGB, image i at byte offsets[i], heights[i] x widths[i] x 3
+ *   offsets / heights / widths   HOST arrays [n_images]
+ *   pad_to_square  1 = image_aspect_ratio 'pad' (centre on a max(h, w) square of `background`), 0 = plain resize + centre crop
+ *   out        DEVICE [n_images, 3, out_size, out_size], out_dtype VQA_DTYPE_F32 or VQA_DTYPE_BF16
+ *   workspace  DEVICE, >= vqa_clip_preprocess_workspace_bytes(...) (0 = bad arguments, see vqa_last_error(NULL)) */
+size_t vqa_clip_preprocess_workspace_bytes(const int32_t* heights, const int32_t* widths, int32_t n_images, int32_t out_size,
+                                           int32_t pad_to_square);
+int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
+                        int32_t out_size, int32_t pad_to_square, const uint8_t* background, const float* mean, const float* stdv,
+                        void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- kernel-level entry points (used by tests/ and bench.py to exercise single kernels through the same ABI) ---- */
 

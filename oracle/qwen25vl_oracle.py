@@ -106,18 +106,22 @@ def vision_window_index(grid_thw: Sequence[Sequence[int]], cfg: Qwen25VLConfig):
     return torch.cat(window_index), cu_win_t, cu_full
 
 
-def mrope_position_ids(input_ids: torch.Tensor, grid_thw: Sequence[Sequence[int]], cfg: Qwen25VLConfig) -> torch.Tensor:
-    """get_rope_index for ONE unpadded sequence with image tokens (modeling_qwen2_5_vl.py:1024-1133): text runs advance all
-    three axes together, an image run takes (t, h, w) grid indices offset by the running position and advances it by
-    max(h, w) / merge. Returns [3, L] int64."""
+def mrope_position_ids(input_ids: torch.Tensor, grid_thw: Sequence[Sequence[int]], cfg: Qwen25VLConfig,
+                       second_per_grid_ts: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """get_rope_index for ONE unpadded sequence with image / video tokens (modeling_qwen2_5_vl.py:1024-1133): text runs advance
+    all three axes together, a vision run (image_token_id or video_token_id; `grid_thw` lists the grids in order of appearance)
+    takes (t, h, w) grid indices offset by the running position and advances it by max(h, w) / merge. `second_per_grid_ts`: one
+    entry per vision run in order (the reference's iterator is advanced by image runs too, :1113), default 1. Returns [3, L]."""
     ids = input_ids.tolist()
     merge = cfg.spatial_merge_size
+    spg = iter(second_per_grid_ts) if second_per_grid_ts is not None else None
+    kind = lambda tok: 1 if tok == cfg.image_token_id else (2 if tok == cfg.video_token_id else 0)   # mm_token_type_ids
     pos: List[torch.Tensor] = []
     cur, i, g = 0, 0, 0
     while i < len(ids):
-        is_img = ids[i] == cfg.image_token_id
+        is_img = kind(ids[i])
         j = i
-        while j < len(ids) and (ids[j] == cfg.image_token_id) == is_img:
+        while j < len(ids) and kind(ids[j]) == is_img:
             j += 1
         if not is_img:
             n = j - i
@@ -132,7 +136,8 @@ def mrope_position_ids(input_ids: torch.Tensor, grid_thw: Sequence[Sequence[int]
             ph = torch.arange(cur, cur + gh).repeat_interleave(gw * gt)
             # transformers 5.5.0 get_vision_position_ids (:1018-1019): the temporal index is start_position * time_interval
             # with time_interval = tokens_per_second * second_per_grid (1 for images) -- also for still images (SURVEY 8c iii)
-            pt = torch.full((gt * gh * gw,), cur * cfg.tokens_per_second, dtype=torch.long)
+            interval = cfg.tokens_per_second * (int(next(spg)) if spg is not None else 1)
+            pt = torch.full((gt * gh * gw,), cur * interval, dtype=torch.long)
             pos.append(torch.stack([pt, ph, pw], dim=0))
             cur += max(h, w) // merge
         i = j
@@ -257,9 +262,12 @@ def answer_probability(logits: torch.Tensor, answer_id: int, temperature: float 
 @torch.no_grad()
 def qwen25vl_score(sd: Dict[str, torch.Tensor], cfg: Qwen25VLConfig, pixel_patches: torch.Tensor, grid_thw: Sequence[Sequence[int]],
                    input_ids: List[torch.Tensor], answer_ids: Sequence[int], image_of_sample: Optional[Sequence[int]] = None,
-                   mode: str = "fp32", temperature: float = 1.0, repetition_penalty: float = 1.0, return_all: bool = False):
-    """pixel_patches: all images' patches concatenated [sum P, patch_dim]; grid_thw one (t,h,w) per image; input_ids: one 1-D
-    id tensor per sample containing a run of image_token_id for its image; answer_ids[b]: the single answer token id.
+                   mode: str = "fp32", temperature: float = 1.0, repetition_penalty: float = 1.0, return_all: bool = False,
+                   second_per_grid_ts: Optional[Sequence[float]] = None):
+    """pixel_patches: all images' (or videos') patches concatenated [sum P, patch_dim]; grid_thw one (t,h,w) per image / video;
+    input_ids: one 1-D id tensor per sample containing a run of image_token_id (or video_token_id) for its visual input -- the
+    model treats both the same way: same tower, masked_scatter at the run (:1298-1322); answer_ids[b]: the single answer token
+    id; second_per_grid_ts: one per image / video (temporal patch duration in seconds, videos only; default 1).
     Returns probabilities [B] (fp32)."""
     num = _Num(mode)
     feats = vision_tower(sd, pixel_patches, grid_thw, cfg, mode)
@@ -272,9 +280,9 @@ def qwen25vl_score(sd: Dict[str, torch.Tensor], cfg: Qwen25VLConfig, pixel_patch
     for b, ids in enumerate(input_ids):
         img = image_of_sample[b] if image_of_sample is not None else b
         e = embed_w[ids].clone()
-        mask = ids == cfg.image_token_id
+        mask = (ids == cfg.image_token_id) | (ids == cfg.video_token_id)
         e[mask] = num.r(feats[offs[img]:offs[img + 1]])                                           # masked_scatter (:1301-1307)
-        pos = mrope_position_ids(ids, [grid_thw[img]], cfg)
+        pos = mrope_position_ids(ids, [grid_thw[img]], cfg, None if second_per_grid_ts is None else [second_per_grid_ts[img]])
         logits = text_last_logits(sd, e, pos, cfg, mode)
         all_logits.append(logits)
         probs.append(answer_probability(logits, int(answer_ids[b]), temperature, ids, repetition_penalty))
@@ -328,22 +336,25 @@ def make_synthetic_state_dict(cfg: Qwen25VLConfig, seed: int = 0, dtype=torch.bf
 
 
 def make_synthetic_inputs(cfg: Qwen25VLConfig, batch: int, image_hw: Tuple[int, int] = (56, 56), text_len: int = 12, seed: int = 1,
-                          ragged: bool = False, n_images: Optional[int] = None, answer_id: int = 9):
+                          ragged: bool = False, n_images: Optional[int] = None, answer_id: int = 9, frames: int = 1):
     """Patches as the Qwen2-VL image processor lays them out (image_processing_qwen2_vl.py:191-220): one still image ->
     grid (1, H/14, W/14), each row = one 2x14x14x3 patch (the frame duplicated along the temporal axis), in merge-block
     order. Ids: `text_len` text ids with one run of image_token_id of length h*w/4 somewhere inside."""
     g = torch.Generator().manual_seed(seed)
     ni = n_images or batch
     gh, gw = image_hw[0] // cfg.patch_size, image_hw[1] // cfg.patch_size
-    grid = [(1, gh, gw)] * ni
-    n_tok = gh * gw // cfg.spatial_merge_size ** 2
-    patches = torch.randn(ni * gh * gw, cfg.patch_dim, generator=g)
+    # frames > 1: a video of `frames` temporal patches (grid (frames, gh, gw), video_token_id run; image_processing / video
+    # processing lay patches out frame-major in the same merge-block order)
+    grid = [(frames, gh, gw)] * ni
+    n_tok = frames * gh * gw // cfg.spatial_merge_size ** 2
+    vis_id = cfg.image_token_id if frames == 1 else cfg.video_token_id
+    patches = torch.randn(ni * frames * gh * gw, cfg.patch_dim, generator=g)
     ids, img_of = [], []
     for b in range(batch):
         n = text_len if not ragged else int(torch.randint(max(4, text_len // 2), text_len + 1, (1,), generator=g))
         pre = int(torch.randint(1, n - 1, (1,), generator=g))
-        txt = torch.randint(0, min(cfg.image_token_id, cfg.vocab - 8), (n,), generator=g)
-        ids.append(torch.cat([txt[:pre], torch.full((n_tok,), cfg.image_token_id), txt[pre:]]))
+        txt = torch.randint(0, min(cfg.image_token_id, cfg.video_token_id, cfg.vocab - 8), (n,), generator=g)
+        ids.append(torch.cat([txt[:pre], torch.full((n_tok,), vis_id), txt[pre:]]))
         img_of.append(b % ni)
     return dict(pixel_patches=patches, grid_thw=grid, input_ids=ids, answer_ids=[answer_id] * batch,
                 image_of_sample=None if ni == batch else img_of)

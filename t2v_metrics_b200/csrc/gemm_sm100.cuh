@@ -42,6 +42,11 @@ struct GemmParams {
     const int* labels;        // [M]
     float* label_logit;       // [M]
     float lse_scale;          // logits are multiplied by this (1 / temperature) after the bf16 rounding
+    // optional repetition penalty (HF RepetitionPenaltyLogitsProcessor, generation/logits_process.py): bit n of row m's bitmap
+    // set -> logit = logit < 0 ? logit * penalty : logit / penalty, applied to the bf16-rounded fp32 logit BEFORE the 1/T scale
+    const uint32_t* penalty_bitmap;   // [M, penalty_words] or nullptr
+    int penalty_words;
+    float penalty;
     // batching: `num_batches` independent GEMMs of the same M,N,K share one launch; batch b reads A at
     // (row + b*a_row_off, k + b*a_k_off), W at (row + b*w_row_off, k + b*w_k_off) and writes C + b*c_batch_stride.
     int num_batches;
@@ -304,10 +309,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     tmem_ld_wait();
                     float x[32];
                     float cmax = -INFINITY;
+                    const uint32_t pen_bits = (p.penalty_bitmap && row_ok && n0 + c * 32 < p.N)
+                                                  ? p.penalty_bitmap[(size_t)m * p.penalty_words + ((n0 + c * 32) >> 5)] : 0u;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = n0 + c * 32 + j;
-                        float val = bf16_round(__uint_as_float(v[j])) * p.lse_scale;   // reference logits are bf16, then / T in fp32
+                        float raw = bf16_round(__uint_as_float(v[j]));                  // reference logits are bf16, then fp32
+                        if (pen_bits && ((pen_bits >> j) & 1u)) raw = raw < 0.f ? raw * p.penalty : __fdiv_rn(raw, p.penalty);
+                        float val = raw * p.lse_scale;                                   // ... / T in fp32
                         x[j] = (n < p.N) ? val : -INFINITY;
                         cmax = fmaxf(cmax, x[j]);
                         if (n == label) p.label_logit[m] = val;

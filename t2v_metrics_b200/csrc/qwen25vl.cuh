@@ -25,7 +25,7 @@ static inline int qwen_mlp_pad(int mlp) { return (mlp + 127) / 128 * 128; }
 
 struct QwenWorkspace {
     size_t patches, vx, vxn, vqkv, vattn, vff, vmerge_in, vfc1, vfeat, vfeat_orig, vcos, vsin;
-    size_t x, xn, qkv, attn, ff, cos, sin, last, lastn, lse_max, lse_sum, label_logit, logprob;
+    size_t x, xn, qkv, attn, ff, cos, sin, last, lastn, lse_max, lse_sum, label_logit, logprob, pen_bitmap;
     size_t total;
 };
 static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n_patches) {
@@ -62,6 +62,7 @@ static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n
     w.lse_sum = pl.take((size_t)B * ntiles * 4);
     w.label_logit = pl.take((size_t)B * 4);
     w.logprob = pl.take((size_t)B * 4);
+    w.pen_bitmap = pl.take((size_t)B * ((c.vocab + 31) / 32) * 4);
     w.total = pl.off;
     return w;
 }
@@ -107,7 +108,8 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
                       const int* vis_pos_hw, const int* window_index, const int* reverse_index, const int* cu_window,
                       int n_windows, int max_window_len, const int* cu_frames, int n_frames, int max_frame_len,
                       const int* input_ids, const int* seq_lens, const int* feat_index, const int* position_ids,
-                      const int* answer_ids, int B, int S, float temperature, float* out_probs, float* out_logprobs,
+                      const int* answer_ids, int B, int S, float temperature, float repetition_penalty, float* out_probs,
+                      float* out_logprobs,
                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const vqa_qwen25vl_config& c = q.cfg;
     const QwenWorkspace w = qwen_plan(c, B, S, n_patches);
@@ -115,6 +117,7 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     auto P_ = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
     auto F_ = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    auto P8_ = [&](size_t off) { return ws + off; };
     h->launches = 0;
     h->prof.clear();
     h->ev_used = 0;
@@ -239,10 +242,23 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     }
     TRY(rms(P_(w.last), q.final_norm, P_(w.lastn), B, D));
     const int ntiles = LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
+    const int pen_words = (c.vocab + 31) / 32;
+    const bool penalise = repetition_penalty != 1.0f;
+    if (penalise) {
+        // HF applies RepetitionPenaltyLogitsProcessor over the prompt ids before the scores are returned (generation/utils.py:2762-2770,
+        // logits_process.py): one bit per (sample, vocabulary id) that occurs in the sample's prompt.
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        *lc += 2;
+        TRY(cuda_ok(cudaMemsetAsync(P8_(w.pen_bitmap), 0, (size_t)B * pen_words * 4, st), "penalty bitmap clear"));
+        token_bitmap_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(input_ids, seq_lens, B, S, c.vocab,
+                                                                 reinterpret_cast<uint32_t*>(P8_(w.pen_bitmap)), pen_words);
+        TRY(cuda_ok(cudaSuccess, "penalty bitmap"));
+    }
     {
         ProfScope ps(h, CAT_GEMM, 2.0 * B * (double)c.vocab * D, st, 2.0 * ((double)B * D + (double)c.vocab * D));
         TRY(cuda_ok(run_lmhead(P_(w.lastn), D, q.lm_head, D, B, c.vocab, D, answer_ids, F_(w.lse_max), F_(w.lse_sum), F_(w.label_logit), nsm, st,
-                               lc, 1.0f / temperature), "lm_head"));
+                               lc, 1.0f / temperature, penalise ? reinterpret_cast<const uint32_t*>(P8_(w.pen_bitmap)) : nullptr, pen_words,
+                               repetition_penalty), "lm_head"));
     }
     {
         ProfScope ps(h, CAT_OTHER, 0, st);

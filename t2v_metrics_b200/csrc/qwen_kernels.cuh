@@ -125,6 +125,18 @@ __global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, con
     for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
 }
 
+// bitmap[b, id / 32] |= 1 << (id % 32) for every prompt id of sample b (the set RepetitionPenaltyLogitsProcessor gathers over).
+__global__ void token_bitmap_kernel(const int* __restrict__ ids, const int* __restrict__ seq_lens, int B, int S, int vocab,
+                                    uint32_t* __restrict__ bitmap, int words) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * S) return;
+    const int b = idx / S, s = idx % S;
+    if (s >= seq_lens[b]) return;
+    const int id = ids[idx];
+    if (id < 0 || id >= vocab) return;
+    atomicOr(&bitmap[(size_t)b * words + (id >> 5)], 1u << (id & 31));
+}
+
 // prob[b] = exp(logprob[b])
 __global__ void exp_kernel(const float* __restrict__ lp, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

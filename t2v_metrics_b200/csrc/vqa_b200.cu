@@ -16,6 +16,7 @@
 #include "attention.cuh"
 #include "attention_sm100.cuh"
 #include "qwen_kernels.cuh"
+#include "preprocess.cuh"
 
 using namespace vqa;
 typedef __nv_bfloat16 bf16;
@@ -233,13 +234,15 @@ constexpr int LMHEAD_BN = 128;
 constexpr int LMHEAD_PARTS = GemmConfig<LMHEAD_BN, 1>::LSE_PARTS;   // (max, sum) partials per (row, n tile)
 static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
                               float* lse_max, float* lse_sum, float* label_logit, int num_sms, cudaStream_t st,
-                              int64_t* launch_counter, float logit_scale = 1.0f) {
+                              int64_t* launch_counter, float logit_scale = 1.0f, const uint32_t* penalty_bitmap = nullptr,
+                              int penalty_words = 0, float penalty = 1.0f) {
     GemmLaunch g;
     g.A = H; g.lda = ldh; g.W = W; g.ldw = ldw; g.w_rows = N;
     memset(&g.p, 0, sizeof(g.p));
     g.p.M = M; g.p.N = N; g.p.K = K;
     g.p.lse_max = lse_max; g.p.lse_sum = lse_sum; g.p.labels = labels; g.p.label_logit = label_logit;
     g.p.lse_scale = logit_scale;
+    g.p.penalty_bitmap = penalty_bitmap; g.p.penalty_words = penalty_words; g.p.penalty = penalty;
     if (launch_counter) ++*launch_counter;
     return launch_gemm_t<LMHEAD_BN, 1, EPI_LSE>(g, num_sms, st);
 }
@@ -870,7 +873,8 @@ extern "C" int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int3
                                   const int32_t* cu_window, int32_t n_windows, int32_t max_window_len, const int32_t* cu_frames,
                                   int32_t n_frames, int32_t max_frame_len, const int32_t* input_ids, const int32_t* seq_lens,
                                   const int32_t* feat_index, const int32_t* position_ids, const int32_t* answer_ids, int32_t batch,
-                                  int32_t seq_len, float temperature, float* out_probs, float* out_logprobs, void* workspace,
+                                  int32_t seq_len, float temperature, float repetition_penalty, float* out_probs, float* out_logprobs,
+                                  void* workspace,
                                   size_t workspace_bytes, void* stream) {
     if (!h || h->kind != 1) return fail(h, VQA_ERR_INVALID_ARG, "not a Qwen2.5-VL handle");
     if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
@@ -878,13 +882,15 @@ extern "C" int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int3
         !feat_index || !position_ids || !answer_ids || !out_probs || !workspace)
         return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
     const int unit = h->qwen->cfg.spatial_merge * h->qwen->cfg.spatial_merge;
-    if (batch <= 0 || seq_len <= 0 || n_patches <= 0 || n_patches % unit || n_windows <= 0 || n_frames <= 0 || !(temperature > 0.f))
-        return fail(h, VQA_ERR_INVALID_ARG, "bad size / temperature");
+    if (batch <= 0 || seq_len <= 0 || n_patches <= 0 || n_patches % unit || n_windows <= 0 || n_frames <= 0 || !(temperature > 0.f) ||
+        !(repetition_penalty > 0.f))
+        return fail(h, VQA_ERR_INVALID_ARG, "bad size / temperature / repetition penalty");
     if (pixel_dtype != VQA_DTYPE_F32 && pixel_dtype != VQA_DTYPE_BF16) return fail(h, VQA_ERR_INVALID_ARG, "pixel_dtype must be F32 or BF16");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VQA_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
     return qwen_score(h, *h->qwen, pixel_patches, pixel_dtype, n_patches, vis_pos_hw, window_index, reverse_index, cu_window, n_windows,
                       max_window_len, cu_frames, n_frames, max_frame_len, input_ids, seq_lens, feat_index, position_ids, answer_ids, batch,
-                      seq_len, temperature, out_probs, out_logprobs, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+                      seq_len, temperature, repetition_penalty, out_probs, out_logprobs, workspace, workspace_bytes,
+                      reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI
@@ -958,5 +964,57 @@ extern "C" int vqa_op_norm(const void* x, const void* gamma, const void* beta, v
                          : run_rmsnorm((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, D, eps, (cudaStream_t)stream,
                                        nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("norm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- image pre-processing
+extern "C" size_t vqa_clip_preprocess_workspace_bytes(const int32_t* heights, const int32_t* widths, int32_t n_images,
+                                                      int32_t out_size, int32_t pad_to_square) {
+    if (!heights || !widths || n_images <= 0 || out_size <= 0) return 0;
+    PrePlan plan;
+    std::vector<int64_t> off(n_images, 0);
+    if (!pre_plan(heights, widths, off.data(), n_images, out_size, pad_to_square != 0, plan)) {
+        fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+        return 0;
+    }
+    return plan.bytes();
+}
+
+extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                                   int32_t n_images, int32_t out_size, int32_t pad_to_square, const uint8_t* background,
+                                   const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    if (!src || !offsets || !heights || !widths || !background || !mean || !stdv || !out || !workspace)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    if (n_images <= 0 || out_size <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad size");
+    if (out_dtype != VQA_DTYPE_F32 && out_dtype != VQA_DTYPE_BF16) return fail(nullptr, VQA_ERR_INVALID_ARG, "out_dtype must be f32 or bf16");
+    PrePlan plan;
+    if (!pre_plan(heights, widths, offsets, n_images, out_size, pad_to_square != 0, plan)) return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+    if (workspace_bytes < plan.bytes()) return fail(nullptr, VQA_ERR_WORKSPACE, "pre-processing workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    // pageable host -> device: the runtime stages the bytes before returning, so the vectors may die with this frame
+    cudaError_t e = cudaMemcpyAsync(ws, plan.images.data(), plan.images.size() * sizeof(PreImage), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ws + plan.images_bytes(), plan.tables.data(), plan.tables.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("pre-processing table upload: ") + cudaGetErrorString(e));
+    const PreImage* d_images = reinterpret_cast<const PreImage*>(ws);
+    const int* d_tables = reinterpret_cast<const int*>(ws + plan.images_bytes());
+    const uchar3 bg = make_uchar3(background[0], background[1], background[2]);
+    const float3 mu = make_float3(mean[0], mean[1], mean[2]), sd = make_float3(stdv[0], stdv[1], stdv[2]);
+    dim3 grid(plan.max_tiles, n_images);
+    if (out_dtype == VQA_DTYPE_F32) {
+        e = cudaFuncSetAttribute(clip_preprocess_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
+        if (e == cudaSuccess)
+            clip_preprocess_kernel<float><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, out_size, bg,
+                                                                              mu, sd, static_cast<float*>(out));
+    } else {
+        e = cudaFuncSetAttribute(clip_preprocess_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
+        if (e == cudaSuccess)
+            clip_preprocess_kernel<bf16><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, out_size, bg,
+                                                                             mu, sd, static_cast<bf16*>(out));
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("pre-processing launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

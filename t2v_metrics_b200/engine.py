@@ -8,7 +8,7 @@ current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -269,6 +269,52 @@ class ops:
         return y
 
 
+# ------------------------------------------------------------------------------------------------ image pre-processing
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess_u8(images: Sequence[torch.Tensor], out_size: int, device, pad: bool = True, mean=CLIP_MEAN, std=CLIP_STD,
+                       background=None, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decoded images (uint8 HWC RGB tensors, each [h, w, 3], on the host or on `device`) -> CLIP input [n, 3, S, S] on the device,
+    by ONE kernel launch of libvqa_b200.so: expand2square (reference mm_utils.py:128-139, background = int(mean * 255)) + PIL-exact
+    bicubic resize + centre crop + /255 + normalise. Host images are packed into one pinned buffer and copied once (a 512x512 image
+    is 0.79 MB as uint8 against 1.35 MB as the fp32 336x336 tensor the CPU path ships). Enqueued on the current stream."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    n = len(images)
+    assert n > 0
+    hs, ws, offs, total = [], [], [], 0
+    for im in images:
+        assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3, "images must be uint8 [h, w, 3]"
+        hs.append(int(im.shape[0])); ws.append(int(im.shape[1])); offs.append(total)
+        total += int(im.numel())
+    if all(im.is_cuda for im in images):
+        src = images[0].contiguous().view(-1) if n == 1 else torch.cat([im.contiguous().view(-1) for im in images])
+    else:
+        stage = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        for im, o in zip(images, offs):
+            stage[o:o + im.numel()] = im.contiguous().view(-1)
+        src = stage.to(dev, non_blocking=True)
+    H = (C.c_int32 * n)(*hs)
+    W = (C.c_int32 * n)(*ws)
+    O = (C.c_int64 * n)(*offs)
+    need = int(lib.vqa_clip_preprocess_workspace_bytes(H, W, n, out_size, 1 if pad else 0))
+    if need == 0:
+        raise RuntimeError(f"vqa_clip_preprocess_workspace_bytes: {_lib.last_error(None)}")
+    wsb = torch.empty(need, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty(n, 3, out_size, out_size, dtype=out_dtype, device=dev)
+    assert out.is_cuda and out.is_contiguous() and out.shape == (n, 3, out_size, out_size) and out.dtype in (torch.float32, torch.bfloat16)
+    bg = background if background is not None else tuple(int(x * 255) for x in mean)
+    rc = lib.vqa_clip_preprocess(_ptr(src), O, H, W, n, out_size, 1 if pad else 0, (C.c_uint8 * 3)(*bg), (C.c_float * 3)(*mean),
+                                 (C.c_float * 3)(*std), _ptr(out), _lib.VQA_DTYPE_F32 if out.dtype == torch.float32 else _lib.VQA_DTYPE_BF16,
+                                 _ptr(wsb), need, _stream_ptr(dev))
+    _check(rc, None, "vqa_clip_preprocess")
+    # src / wsb stay referenced by the caching allocator's stream ordering: both were allocated on the current stream
+    return out
+
+
 # ================================================================================================ Qwen2.5-VL
 def convert_qwen_state_dict(sd: Dict[str, torch.Tensor], cfg, device) -> Dict[str, torch.Tensor]:
     """HF `Qwen2_5_VLForConditionalGeneration` names -> the engine's fused bf16 layout:
@@ -390,9 +436,11 @@ class QwenVLEngine:
 
     def score_tensors(self, pixel_patches: torch.Tensor, grid_thw, input_ids: torch.Tensor, seq_lens: torch.Tensor,
                       feat_index: torch.Tensor, position_ids: torch.Tensor, answer_ids: torch.Tensor, temperature: float = 1.0,
-                      out: Optional[torch.Tensor] = None, return_logprobs: bool = False):
+                      out: Optional[torch.Tensor] = None, return_logprobs: bool = False, repetition_penalty: float = 1.0):
         """pixel_patches [sum P, patch_dim] fp32/bf16 cuda; grid_thw list of (t,h,w); the int32 cuda tensors come from
-        qwen_host.build_batch_indices. Returns probabilities [B] fp32 on the device."""
+        qwen_host.build_batch_indices. repetition_penalty != 1 applies HF's RepetitionPenaltyLogitsProcessor over each sample's
+        prompt ids before the softmax (what `generate(..., output_scores=True)` returns when the checkpoint's
+        generation_config.json carries one). Returns probabilities [B] fp32 on the device."""
         dev = self.device
         vi = self.vision_indices(grid_thw)
         assert pixel_patches.is_cuda and pixel_patches.is_contiguous() and pixel_patches.shape == (vi["n_patches"], self.cfg.patch_dim)
@@ -412,20 +460,23 @@ class QwenVLEngine:
                                          _ptr(vi["window_index"]), _ptr(vi["reverse_index"]), _ptr(vi["cu_window"]), vi["n_windows"],
                                          vi["max_window"], _ptr(vi["cu_frames"]), vi["n_frames"], vi["max_frame"], _ptr(input_ids),
                                          _ptr(seq_lens), _ptr(feat_index), _ptr(position_ids), _ptr(answer_ids), B, S,
-                                         float(temperature), _ptr(out), _ptr(logp), _ptr(self._workspace), self._workspace.numel(),
+                                         float(temperature), float(repetition_penalty), _ptr(out), _ptr(logp), _ptr(self._workspace), self._workspace.numel(),
                                          _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_score")
         return (out, logp) if return_logprobs else out
 
-    def score_prompts(self, pixel_patches, grid_thw, prompts, answer_ids, image_of_sample=None, temperature: float = 1.0):
-        """Convenience: prompts = list of 1-D id lists (each with one image-token run). Host index logic + one engine call."""
+    def score_prompts(self, pixel_patches, grid_thw, prompts, answer_ids, image_of_sample=None, temperature: float = 1.0,
+                      repetition_penalty: float = 1.0, second_per_grid_ts=None):
+        """Convenience: prompts = list of 1-D id lists (each with one image- or video-token run). Host index logic + one engine
+        call. Videos are grids with t > 1 whose prompt run uses cfg.video_token_id (second_per_grid_ts = temporal_patch / fps)."""
         from . import qwen_host
         cfg, dev = self.cfg, self.device
         B = len(prompts)
         img = list(image_of_sample) if image_of_sample is not None else list(range(B))
         idx = qwen_host.build_batch_indices([list(map(int, p)) for p in prompts], [tuple(map(int, g)) for g in grid_thw], img,
-                                            cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second)
+                                            cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second,
+                                            video_token_id=cfg.video_token_id, second_per_grid_ts=second_per_grid_ts)
         d = {k: v.to(dev) for k, v in idx.items()}
         ans = torch.as_tensor(list(map(int, answer_ids)), dtype=torch.int32).to(dev)
         return self.score_tensors(pixel_patches.to(dev), grid_thw, d["input_ids"], d["seq_lens"], d["feat_index"], d["position_ids"],
-                                  ans, temperature)
+                                  ans, temperature, repetition_penalty=repetition_penalty)

@@ -20,6 +20,18 @@ from .vqa_model import VQAScoreModel
 QWEN2_VL_MODELS: Dict[str, dict] = {name: dict(model=dict(path=spec["weights"]), config=spec["config"]) for name, spec in _TABLE.items()}
 
 
+def _generation_config_penalty(checkpoint_path: str) -> float:
+    """repetition_penalty of the generation_config.json stored beside the checkpoint (what `from_pretrained` would attach to
+    `model.generation_config` in the reference, qwen2vl_model.py:116-130); 1.0 when there is none."""
+    import json, os
+    d = checkpoint_path if os.path.isdir(checkpoint_path) else os.path.dirname(checkpoint_path)
+    f = os.path.join(d, "generation_config.json")
+    if d and os.path.isfile(f):
+        with open(f) as fh:
+            return float(json.load(fh).get("repetition_penalty", 1.0) or 1.0)
+    return 1.0
+
+
 class Qwen2VLModel(VQAScoreModel):
     video_mode = "direct"
     allows_image = True
@@ -27,8 +39,12 @@ class Qwen2VLModel(VQAScoreModel):
 
     def __init__(self, model_name="qwen2.5-vl-7b", device="cuda", cache_dir=HF_CACHE_DIR, tokenizer=None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, config: Optional[Qwen25VLConfig] = None,
-                 checkpoint: Optional[str] = None, **kwargs):
+                 checkpoint: Optional[str] = None, repetition_penalty: Optional[float] = None, **kwargs):
         assert model_name in QWEN2_VL_MODELS
+        # The reference's scores come out of `generate(..., output_scores=True)`, i.e. AFTER the logits processors the checkpoint's
+        # generation_config.json configures (Qwen2.5-VL-Instruct ships repetition_penalty 1.05). None = read it from the
+        # generation_config.json next to `checkpoint` when there is one, else 1.0 (off).
+        self.repetition_penalty = repetition_penalty
         self._tokenizer_override, self._state_dict, self._config_override, self._checkpoint = tokenizer, state_dict, config, checkpoint
         super().__init__(model_name=model_name, device=device, cache_dir=cache_dir)
 
@@ -52,6 +68,8 @@ class Qwen2VLModel(VQAScoreModel):
                 sd = load_file(path)
             else:
                 sd = torch.load(path, map_location="cpu")
+        if self.repetition_penalty is None:
+            self.repetition_penalty = _generation_config_penalty(self._checkpoint or spec["model"]["path"])
         dev = torch.device(self.device if self.device != "cuda" else "cuda:0")
         self.engine = QwenVLEngine(self.cfg, dev)
         self.engine.load_state_dict(sd)
@@ -70,7 +88,7 @@ class Qwen2VLModel(VQAScoreModel):
     @torch.no_grad()
     def forward(self, images: List[str], texts: List[str], fps=None, question_template: str = default_question_template,
                 answer_template: str = default_answer_template, max_new_tokens: int = 1, temperature: float = 1.0,
-                debug: bool = False) -> torch.Tensor:
+                debug: bool = False, repetition_penalty: Optional[float] = None) -> torch.Tensor:
         assert len(images) == len(texts), "Number of images/videos and texts must match"
         questions = [question_template.format(t) for t in texts]
         answers = [answer_template.format(t) for t in texts]
@@ -86,5 +104,6 @@ class Qwen2VLModel(VQAScoreModel):
             if not ids:
                 raise ValueError("empty answer")
             answer_ids.append(ids[0])      # max_new_tokens=1: only the first answer token is ever scored (qwen2vl_model.py:259-263)
-        probs = self.engine.score_prompts(patches, grids, prompts, answer_ids, image_of_sample=index, temperature=temperature)
+        probs = self.engine.score_prompts(patches, grids, prompts, answer_ids, image_of_sample=index, temperature=temperature,
+                                          repetition_penalty=self.repetition_penalty if repetition_penalty is None else repetition_penalty)
         return probs.float().cpu()

@@ -9,7 +9,7 @@ tests/test_qwen_host.py checks every function against the transformers implement
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -48,17 +48,24 @@ def vision_window_index(grid_thw: Sequence[Sequence[int]], merge: int, window_si
 
 
 def mrope_position_ids(input_ids: Sequence[int], grids: Sequence[Sequence[int]], image_token_id: int, merge: int,
-                       tokens_per_second: int) -> torch.Tensor:
-    """(t, h, w) positions of ONE unpadded prompt whose image-token runs correspond, in order, to `grids`. [3, L] int64.
-    transformers 5.5.0 multiplies the temporal start position by time_interval = tokens_per_second * 1 for still images too
-    (:1018-1019); the parity target is the installed transformers, so this does the same."""
+                       tokens_per_second: int, video_token_id: Optional[int] = None,
+                       second_per_grid_ts: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """(t, h, w) positions of ONE unpadded prompt whose image / video token runs correspond, in order, to `grids`. [3, L] int64.
+    transformers 5.5.0 multiplies the temporal START position by time_interval = tokens_per_second * int(second_per_grid)
+    -- constant over the whole grid, and applied to still images too with second_per_grid = 1 (:1018-1019, :1113); the parity
+    target is the installed transformers, so this does the same. `second_per_grid_ts`: one entry per vision run, default 1."""
     ids = list(input_ids)
+    spg = iter(second_per_grid_ts) if second_per_grid_ts is not None else None
+
+    def kind(tok):          # mm_token_type_ids: text 0, image 1, video 2 -- adjacent runs of different kinds are separate groups
+        return 1 if tok == image_token_id else (2 if video_token_id is not None and tok == video_token_id else 0)
+
     pos: List[torch.Tensor] = []
     cur, i, g = 0, 0, 0
     while i < len(ids):
-        is_img = ids[i] == image_token_id
+        is_img = kind(ids[i])
         j = i
-        while j < len(ids) and (ids[j] == image_token_id) == is_img:
+        while j < len(ids) and kind(ids[j]) == is_img:
             j += 1
         if not is_img:
             n = j - i
@@ -72,7 +79,8 @@ def mrope_position_ids(input_ids: Sequence[int], grids: Sequence[Sequence[int]],
                 raise ValueError(f"image token run of {j - i} does not match grid {(t, h, w)}")
             pw = torch.arange(cur, cur + gw).repeat(gh * gt)
             ph = torch.arange(cur, cur + gh).repeat_interleave(gw * gt)
-            pt = torch.full((gt * gh * gw,), cur * tokens_per_second, dtype=torch.long)
+            interval = tokens_per_second * (int(next(spg)) if spg is not None else 1)
+            pt = torch.full((gt * gh * gw,), cur * interval, dtype=torch.long)
             pos.append(torch.stack([pt, ph, pw], dim=0))
             cur += max(h, w) // merge
         i = j
@@ -92,8 +100,10 @@ def rope_tables(head_dim_text: int, rope_theta: float, mrope_section: Sequence[i
 
 
 def build_batch_indices(input_ids: List[Sequence[int]], grids: Sequence[Sequence[int]], image_of_sample: Sequence[int],
-                        image_token_id: int, merge: int, tokens_per_second: int, pad_id: int = 0):
-    """Right-pad a batch of prompts and build the per-token arrays the engine consumes.
+                        image_token_id: int, merge: int, tokens_per_second: int, pad_id: int = 0,
+                        video_token_id: Optional[int] = None, second_per_grid_ts: Optional[Sequence[float]] = None):
+    """Right-pad a batch of prompts and build the per-token arrays the engine consumes. Each prompt holds ONE vision run (image
+    or video tokens) fed by grid `image_of_sample[b]`; second_per_grid_ts is per grid (videos: temporal_patch_size / fps).
     Returns dict(input_ids [B,S], seq_lens [B], feat_index [B,S], position_ids [3, B*S]) as int32 CPU tensors."""
     unit = merge * merge
     feat_off = [0]
@@ -112,6 +122,10 @@ def build_batch_indices(input_ids: List[Sequence[int]], grids: Sequence[Sequence
         lens[b] = n
         img = image_of_sample[b]
         m = seq_t == image_token_id
+        if video_token_id is not None:
+            m = m | (seq_t == video_token_id)
         feat[b, :n][m] = torch.arange(feat_off[img], feat_off[img + 1], dtype=torch.int32)
-        pos[:, b, :n] = mrope_position_ids(seq_t.tolist(), [grids[img]], image_token_id, merge, tokens_per_second).to(torch.int32)
+        spg = None if second_per_grid_ts is None else [second_per_grid_ts[img]]
+        pos[:, b, :n] = mrope_position_ids(seq_t.tolist(), [grids[img]], image_token_id, merge, tokens_per_second, video_token_id,
+                                           spg).to(torch.int32)
     return dict(input_ids=ids, seq_lens=lens, feat_index=feat, position_ids=pos.reshape(3, B * S).contiguous())

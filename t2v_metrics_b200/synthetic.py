@@ -148,17 +148,20 @@ def synthetic_qwen_engine_weights(cfg, device, seed: int = 0) -> Dict[str, torch
     return out
 
 
-def synthetic_qwen_batch(cfg, batch: int, image_hw=(448, 448), text_len: int = 64, seed: int = 1, answer_id: int = 9454):
+def synthetic_qwen_batch(cfg, batch: int, image_hw=(448, 448), text_len: int = 64, seed: int = 1, answer_id: int = 9454,
+                         frames: int = 1):
     """BASELINE config 3: `batch` still images of image_hw (already multiples of 28) as processor-layout patches
-    [batch * h/14 * w/14, 1176] fp32 (normalised noise), prompts of `text_len` text ids around one image-token run."""
+    [batch * h/14 * w/14, 1176] fp32 (normalised noise), prompts of `text_len` text ids around one image-token run.
+    frames > 1 (config 5): videos of `frames` temporal patches, grid (frames, h/14, w/14), video-token run."""
     g = torch.Generator().manual_seed(seed)
     gh, gw = image_hw[0] // cfg.patch_size, image_hw[1] // cfg.patch_size
-    n_tok = gh * gw // cfg.spatial_merge_size ** 2
-    patches = torch.randn(batch * gh * gw, cfg.patch_dim, generator=g)
+    n_tok = frames * gh * gw // cfg.spatial_merge_size ** 2
+    vis_id = cfg.image_token_id if frames == 1 else cfg.video_token_id
+    patches = torch.randn(batch * frames * gh * gw, cfg.patch_dim, generator=g)
     prompts = []
     for b in range(batch):
-        txt = torch.randint(0, min(cfg.image_token_id, cfg.vocab - 8), (text_len,), generator=g)
+        txt = torch.randint(0, min(cfg.image_token_id, cfg.video_token_id, cfg.vocab - 8), (text_len,), generator=g)
         pre = 14                                     # chat-template prefix length before <|vision_start|>
-        prompts.append(torch.cat([txt[:pre], torch.full((n_tok,), cfg.image_token_id), txt[pre:]]).tolist())
-    return dict(pixel_patches=patches.pin_memory() if torch.cuda.is_available() else patches, grid_thw=[(1, gh, gw)] * batch,
+        prompts.append(torch.cat([txt[:pre], torch.full((n_tok,), vis_id), txt[pre:]]).tolist())
+    return dict(pixel_patches=patches.pin_memory() if torch.cuda.is_available() else patches, grid_thw=[(frames, gh, gw)] * batch,
                 prompts=prompts, answer_ids=[answer_id % cfg.vocab] * batch)

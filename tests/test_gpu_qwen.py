@@ -109,6 +109,59 @@ def test_qwen_engine_matches_oracle(dev, hw, n_images):
     assert float((torch.log(pT) - torch.log(refT)).abs().max()) <= 2.0 * gap + 2e-2
 
 
+@pytest.mark.parametrize("frames,hw", [(2, (56, 84)), (4, (84, 56))])
+def test_qwen_engine_video_grid(dev, frames, hw):
+    """a video is a grid with t > 1 temporal patches -- same tower (windows and full attention are per
+    temporal patch), video-token run in the prompt, constant temporal rope index scaled by second_per_grid."""
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=2)
+    inp = qo.make_synthetic_inputs(cfg, 3, hw, 10, ragged=True, frames=frames)
+    spg = [2.0] * 3
+    o32 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], mode="fp32",
+                            return_all=True, second_per_grid_ts=spg)
+    o16 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], mode="bf16",
+                            return_all=True, second_per_grid_ts=spg)
+    eng = make_engine(cfg, sd, dev)
+    p = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], [x.tolist() for x in inp["input_ids"]], inp["answer_ids"],
+                          second_per_grid_ts=spg).cpu()
+    lp, l32, l16 = torch.log(p), torch.log(o32["scores"]), torch.log(o16["scores"])
+    gap = float((l16 - l32).abs().max())
+    print(f"\n[qwen video t={frames} {hw}] engine {p.tolist()} oracle {o32['scores'].tolist()} |dlogp| {float((lp - l32).abs().max()):.3e} "
+          f"(oracle bf16-vs-fp32 {gap:.3e})")
+    assert float((lp - l32).abs().max()) <= 2.0 * gap + 2e-2
+
+
+def test_qwen_repetition_penalty(dev):
+    """the reference's scores are post-logits-processor. With a repetition penalty the engine applies HF's
+    RepetitionPenaltyLogitsProcessor over each sample's own prompt ids inside the lm_head epilogue (bitmap), then 1/T, then the
+    full-vocabulary softmax. Sample 0's answer id is taken from its own prompt so the label logit itself is penalised too."""
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=5)
+    inp = qo.make_synthetic_inputs(cfg, 4, (84, 56), 12, ragged=True)
+    prompts = [x.tolist() for x in inp["input_ids"]]
+    answers = list(map(int, inp["answer_ids"]))
+    answers[0] = prompts[0][-1]
+    o32 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], answers, inp["image_of_sample"],
+                            mode="fp32", return_all=True)
+    o16 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], answers, inp["image_of_sample"],
+                            mode="bf16", return_all=True)
+    gap = float((torch.log(o16["scores"]) - torch.log(o32["scores"])).abs().max())
+    eng = make_engine(cfg, sd, dev)
+    base = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, answers, inp["image_of_sample"]).cpu()
+    for pen, T in ((1.05, 1.0), (1.5, 1.0), (1.3, 0.5), (0.8, 1.0)):
+        got = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, answers, inp["image_of_sample"], temperature=T,
+                                repetition_penalty=pen).cpu()
+        ref = torch.stack([qo.answer_probability(o32["logits"][b], answers[b], T, inp["input_ids"][b], pen) for b in range(4)])
+        err = float((torch.log(got) - torch.log(ref)).abs().max())
+        print(f"\n[qwen penalty {pen} T {T}] engine {got.tolist()} oracle {ref.tolist()} |dlogp| {err:.3e}")
+        assert err <= 2.0 * gap / min(T, 1.0) + 2e-2
+    # the penalty must actually move the penalised answer (sample 0) and be a no-op at 1.0
+    strong = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, answers, inp["image_of_sample"], repetition_penalty=1.5).cpu()
+    assert abs(float(torch.log(strong[0]) - torch.log(base[0]))) > 1e-3
+    same = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, answers, inp["image_of_sample"], repetition_penalty=1.0).cpu()
+    assert torch.equal(same, base)
+
+
 def test_qwen_batch_invariance(dev):
     cfg = qo.Qwen25VLConfig.tiny(**TINY)
     sd = qo.make_synthetic_state_dict(cfg, seed=3)

@@ -66,6 +66,47 @@ def test_mrope_positions_and_tables_match_transformers(tiny):
     assert t_axis.tolist() == [0] * 16 + [1] * 24 + [2] * 24
 
 
+@pytest.mark.parametrize("spg", [None, [2.0], [0.5]])
+def test_mrope_positions_video_match_transformers(tiny, spg):
+    """SURVEY 8(d) config 5 / 8(c) iii: video runs (mm_token_type 2, video_grid_thw, second_per_grid_ts) in the installed
+    transformers: temporal index = start * tokens_per_second * int(second_per_grid), constant over the grid."""
+    cfg, m = tiny
+    inp = qo.make_synthetic_inputs(cfg, 2, (56, 84), 9, ragged=True, frames=3)
+    for b, ids in enumerate(inp["input_ids"]):
+        grid = [inp["grid_thw"][b]]
+        tt = torch.where(ids == cfg.video_token_id, 2, 0)[None]
+        hf_pos, _ = m.model.get_rope_index(ids[None], tt, video_grid_thw=torch.tensor(grid),
+                                           second_per_grid_ts=None if spg is None else torch.tensor(spg),
+                                           attention_mask=torch.ones(1, len(ids), dtype=torch.long))
+        mine = qwen_host.mrope_position_ids(ids.tolist(), grid, cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second,
+                                            cfg.video_token_id, spg)
+        assert torch.equal(mine, hf_pos[:, 0])
+        assert torch.equal(mine, qo.mrope_position_ids(ids, grid, cfg, spg))
+
+
+def test_qwen_oracle_matches_transformers_video(tiny):
+    """The oracle on a video input (grid t = 2 temporal patches, video token run) against Qwen2_5_VLForConditionalGeneration fed
+    pixel_values_videos / video_grid_thw."""
+    cfg, m = tiny
+    sd = qo.make_synthetic_state_dict(cfg, seed=0)
+    m.load_state_dict({k: v.float() for k, v in sd.items()})
+    inp = qo.make_synthetic_inputs(cfg, 2, (56, 84), 10, ragged=True, frames=2)
+    spg = [2.0, 2.0]
+    o = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], return_all=True,
+                          second_per_grid_ts=spg)
+    t, gh, gw = inp["grid_thw"][0]
+    P = t * gh * gw
+    for b, ids in enumerate(inp["input_ids"]):
+        with torch.no_grad():
+            out = m(input_ids=ids[None], pixel_values_videos=inp["pixel_patches"][b * P:(b + 1) * P],
+                    video_grid_thw=torch.tensor([list(inp["grid_thw"][b])]), second_per_grid_ts=torch.tensor([spg[b]]),
+                    mm_token_type_ids=torch.where(ids == cfg.video_token_id, 2, 0)[None],
+                    attention_mask=torch.ones(1, len(ids), dtype=torch.long))
+        lg = out.logits[0, -1].float()
+        assert float((lg - o["logits"][b]).abs().max()) < 5e-5
+        assert abs(float(torch.softmax(lg, -1)[inp["answer_ids"][b]]) - float(o["scores"][b])) < 1e-6
+
+
 def test_build_batch_indices_round_trip(tiny):
     cfg, _ = tiny
     inp = qo.make_synthetic_inputs(cfg, 4, (56, 56), 9, ragged=True, n_images=2)
