@@ -233,7 +233,8 @@ def run_engine(args, rank, local_rank, world):
     B, L = args.batch, args.text_len
     if args.pairs:
         return run_job(args, rank, world, dev, cfg, eng)
-    host = synthetic_batch(cfg, B, L, seed=1 + rank, ragged=args.ragged)
+    host = synthetic_batch(cfg, B, L, seed=1 + rank, ragged=args.ragged, raw_u8=True)
+    raw_u8 = host.pop("raw_u8")                      # [B, 512, 512, 3] uint8 pinned: the decoded images of config 2
     d = {k: v.to(dev) for k, v in host.items()}
     total_pairs = B * world
 
@@ -248,7 +249,9 @@ def run_engine(args, rank, local_rank, world):
         return gather_scores(s, total_pairs) if world > 1 else s
 
     def step_host():
-        s = eng.score_host(host["pixels"], host["input_ids"], host["text_lens"], host["labels"])
+        # the call a user makes: decoded uint8 images + token ids on the HOST -> H2D -> device pre-processing (expand2square, PIL-exact
+        # bicubic 512 -> 336, normalise) -> forward -> scores back on the host
+        s = eng.score_images_u8(raw_u8, host["input_ids"], host["text_lens"], host["labels"])
         if world > 1:
             s = gather_scores(s.to(dev), total_pairs).cpu()
         return s
@@ -300,7 +303,7 @@ def run_engine(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_step = float(t) / args.steps
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = raw_u8.numel() + sum(v.numel() * v.element_size() for k, v in host.items() if k != "pixels")
     d2h = B * 4
 
     if rank == 0:
@@ -327,7 +330,9 @@ def run_engine(args, rank, local_rank, world):
                           whole_step_tflops=(value / world) * fpp / 1e12 if fpp else None),
             breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
             e2e=dict(value=total_pairs / (e2e_ms_step * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                     ms_per_step=e2e_ms_step),
+                     ms_per_step=e2e_ms_step,
+                     path="ClipT5Engine.score_images_u8: pinned uint8 512x512 images + ids -> H2D -> vqa_clip_preprocess -> "
+                          "vqa_clipt5_score -> D2H scores"),
             gpu_launches=int(launches) * args.steps, clocks=clocks,
             sample_scores=[round(float(x), 6) for x in out[:4].float().cpu()])
         if world == 1 and not args.no_cpu_baseline:

@@ -201,6 +201,22 @@ int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* 
                         int32_t out_size, int32_t pad_to_square, const uint8_t* background, const float* mean, const float* stdv,
                         void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Qwen2.5-VL still-image pre-processing on the device: smart_resize (qwen_vl_utils / image_processing_qwen2_vl.py:62-87) + PIL-exact
+ * bicubic resize + /255 + normalise + frame duplication + 14x14 patch rows in 2x2 merge-block order
+ * (image_processing_qwen2_vl.py:191-220). vqa_qwen_preprocess_plan is host-only: grid_hw [n][2] = (h, w) patch grid of each image,
+ * total_patches = rows of `out`, workspace_bytes = device scratch needed. out: DEVICE [total_patches, 3*temporal_patch*patch^2]. */
+int vqa_qwen_preprocess_plan(const int32_t* heights, const int32_t* widths, int32_t n_images, int32_t patch, int32_t merge,
+                             int64_t min_pixels, int64_t max_pixels, int32_t* grid_hw, int64_t* total_patches, size_t* workspace_bytes);
+int vqa_qwen_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
+                        int32_t patch, int32_t temporal_patch, int32_t merge, int64_t min_pixels, int64_t max_pixels, const float* mean,
+                        const float* stdv, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-only helper (no GPU needed): the 22-bit fixed-point bicubic tap table of one resize axis (in_size -> out_size, output
+ * pixels [first, first + count)), exactly as vqa_clip_preprocess builds it after Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc. bounds [count][2] = (first source index, taps used); kk [count][ksize]; returns ksize (0 = bad
+ * arguments). Either output pointer may be NULL. */
+int32_t vqa_resample_table(int32_t in_size, int32_t out_size, int32_t first, int32_t count, int32_t* bounds, int32_t* kk);
+
 /* ---- kernel-level entry points (used by tests/ and bench.py to exercise single kernels through the same ABI) ---- */
 
 /* C[M,N] = epilogue(A[M,K] . W[N,K]^T); all DEVICE bf16 row-major. epilogue: 0 store, 1 quick_gelu, 2 gelu(erf),

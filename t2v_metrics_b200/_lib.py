@@ -17,7 +17,8 @@ ABI_SYMBOLS = [
     "vqa_clipt5_score", "vqa_set_profile", "vqa_profile_read", "vqa_last_launch_count", "vqa_last_error", "vqa_destroy", "vqa_op_gemm_bf16",
     "vqa_op_lmhead_logprob", "vqa_op_attention_d64", "vqa_op_norm", "vqa_op_attention_d128",
     "vqa_create_qwen25vl", "vqa_qwen25vl_set_rope", "vqa_qwen25vl_workspace_bytes", "vqa_qwen25vl_score",
-    "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess",
+    "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess", "vqa_resample_table", "vqa_qwen_preprocess_plan",
+    "vqa_qwen_preprocess",
 ]
 
 VQA_DTYPE_BF16, VQA_DTYPE_F32, VQA_DTYPE_I32 = 0, 1, 2
@@ -112,6 +113,14 @@ def load() -> C.CDLL:
     lib.vqa_clip_preprocess.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), i32, i32, i32, C.POINTER(C.c_uint8),
                                         C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, vp, C.c_size_t, vp]
     lib.vqa_clip_preprocess.restype = C.c_int
+    lib.vqa_qwen_preprocess_plan.argtypes = [C.POINTER(i32), C.POINTER(i32), i32, i32, i32, i64, i64, C.POINTER(i32), C.POINTER(i64),
+                                             C.POINTER(C.c_size_t)]
+    lib.vqa_qwen_preprocess_plan.restype = C.c_int
+    lib.vqa_qwen_preprocess.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), i32, i32, i32, i32, i64, i64,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_float), vp, i32, vp, C.c_size_t, vp]
+    lib.vqa_qwen_preprocess.restype = C.c_int
+    lib.vqa_resample_table.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.vqa_resample_table.restype = i32
     _lib = lib
     return lib
 

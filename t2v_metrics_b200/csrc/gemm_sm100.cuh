@@ -54,6 +54,8 @@ struct GemmParams {
     long long c_batch_stride;
     // scheduling
     int num_m_tiles, num_n_tiles, group_m;
+    // L2 eviction priority of the two operand streams (ptx.cuh L2_EVICT_*), chosen per launch by launch_gemm_t
+    unsigned long long a_policy, w_policy;
 };
 
 template <int BLOCK_N, int CG>
@@ -179,20 +181,20 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     const int k0w = kb * BLOCK_K + batch * p.w_k_off;
                     if constexpr (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m_row);
+                        tma_load_2d_hint(sa, &tmap_a, &full_bar[stage], k0, m_row, p.a_policy);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             int n_row = epi_is_gated(EPI) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                                 : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
-                            tma_load_2d(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0w,
-                                        n_row + w_row_base);
+                            tma_load_2d_hint(sb + h * Cfg::B_HALF_ROWS * BLOCK_K * 2, &tmap_b, &full_bar[stage], k0w,
+                                             n_row + w_row_base, p.w_policy);
                         }
                     } else {
                         const int h = (int)cta_rank;
                         int n_row = epi_is_gated(EPI) ? h * p.gate_up_offset + n_blk * Cfg::B_HALF_ROWS
                                                             : n_blk * BLOCK_N + h * Cfg::B_HALF_ROWS;
-                        tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m_row);
-                        tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0w, n_row + w_row_base);
+                        tma_load_2d_2sm_hint(sa, &tmap_a, &full_bar[stage], k0, m_row, p.a_policy);
+                        tma_load_2d_2sm_hint(sb, &tmap_b, &full_bar[stage], k0w, n_row + w_row_base, p.w_policy);
                         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         else           mbar_arrive_cluster(&full_bar[stage], 0);
                     }
@@ -490,13 +492,29 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
     int group_rows;
     if (env_rows > 0) {
         group_rows = env_rows;
-    } else if ((long long)g.w_rows * p.K * 2 <= (48ll << 20)) {
+    } else if ((long long)g.w_rows * p.K * 2 <= (96ll << 20)) {
         group_rows = 1024;
     } else {
         group_rows = (int)((32ll << 20) / ((long long)p.K * 2));
         group_rows = max(512, min(8192, group_rows / 256 * 256));
     }
     p.group_m = max(1, group_rows / rows_per_tile);
+    // L2 residency: when W fits (<= 96 MB of the 126 MB L2) it is the operand every tile re-reads -> keep it (evict_last) and let
+    // the A rows stream (evict_first); otherwise the A panel of the current row group is what the sweep over N re-reads -> keep
+    // that and stream W. VQA_GEMM_L2_POLICY=<a><w> with digits 0 normal / 1 first / 2 last overrides (tuning).
+    static const int env_pol = [] { const char* v = getenv("VQA_GEMM_L2_POLICY"); return (v && v[0] && v[1]) ? (v[0] - '0') * 10 + (v[1] - '0') : -1; }();
+    const unsigned long long pol[3] = {L2_EVICT_NORMAL, L2_EVICT_FIRST, L2_EVICT_LAST};
+    const long long w_bytes = (long long)g.w_rows * p.K * 2;
+    const bool small_problem = (long long)p.M * p.K * 2 + w_bytes <= (64ll << 20);
+    if (env_pol >= 0 && env_pol / 10 < 3 && env_pol % 10 < 3) {
+        p.a_policy = pol[env_pol / 10]; p.w_policy = pol[env_pol % 10];
+    } else if (small_problem) {
+        p.a_policy = p.w_policy = L2_EVICT_NORMAL;
+    } else if (w_bytes <= (96ll << 20)) {
+        p.a_policy = L2_EVICT_FIRST; p.w_policy = L2_EVICT_LAST;
+    } else {
+        p.a_policy = L2_EVICT_LAST; p.w_policy = L2_EVICT_FIRST;
+    }
     const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_batches;
     int workers = num_sms / CG;
     if (workers > num_tiles) workers = num_tiles;

@@ -8,9 +8,11 @@
 // coefficient tables are built on the host in double exactly as Pillow builds them (so the integers are identical), the two integer
 // passes run here, and the result is bit-identical to PIL for every pixel.
 //
-// One CTA = one image x one band of `tile_rows` output rows: the horizontally resampled source rows the band needs live in shared
-// memory (uint8), the vertical pass reads them from there, the normalised fp32 / bf16 CHW pixels are written once. The source is
-// read once from HBM (plus the band overlap, absorbed by L2), the output written once.
+// One CTA = one image x one band of `tile_rows` output rows. The canvas rows the band needs are staged `chunk_rows` at a time into
+// shared memory as packed RGBX words (coalesced byte reads, padding colour filled in, so the passes need no bounds checks), the
+// horizontal pass turns them into RGBX words of the band buffer (one coefficient load serves up to 4 rows x 3 channels), the vertical
+// pass reads the band (one word = 3 channels) and a 768-entry lookup table does the /255, -mean, /std in exact fp32. The source is read
+// once from HBM (plus the band overlap, absorbed by L2), the output written once.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -33,7 +35,14 @@ struct PreImage {            // one per image, lives in the workspace (device) a
     int hks, vks;            // taps per output pixel
     int tile_rows;           // output rows per CTA
     int band_rows;           // max source rows any band of this image needs (shared memory rows)
+    int out_h, out_w;        // output window (after the crop) of this image
+    long long out_off;       // element offset of this image's output inside `out`
+    int x_lo, span;          // canvas columns [x_lo, x_lo + span) the horizontal windows of this image touch
+    int chunk_rows;          // canvas rows staged per pass (1..8)
 };
+
+enum PreLayout { PRE_CHW = 0, PRE_QWEN_PATCHES = 1 };
+struct PrePatchGeom { int patch, merge, temporal; };     // PRE_QWEN_PATCHES only
 
 // ---------------------------------------------------------------------------------------------- host: Pillow's coefficient tables
 inline double pre_bicubic(double x) {                 // Resample.c bicubic_filter, a = -0.5
@@ -91,66 +100,132 @@ __device__ __forceinline__ int pre_clip8(int v) {     // Resample.c clip8: table
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-template <typename OUT>
+// LAYOUT PRE_CHW: out[c][y][x] per image ([3, out_h, out_w]). PRE_QWEN_PATCHES: the Qwen2-VL processor's patch rows
+// (image_processing_qwen2_vl.py:191-220): row ((by * gw/m + bx) * m + iy) * m + ix for the 14x14 patch at grid (by*m+iy, bx*m+ix),
+// column (c * temporal + t) * ps*ps + py * ps + px, the still frame written to every temporal slot t.
+constexpr int PRE_XL = 128;                 // x lanes; PRE_THREADS / PRE_XL row groups
+constexpr int PRE_RG = PRE_THREADS / PRE_XL;
+constexpr int PRE_MAX_CHUNK = 4 * PRE_RG;   // rows per staging pass: each thread keeps up to 4 rows x 3 channels of accumulators
+
+template <typename OUT, int LAYOUT>
 __global__ void __launch_bounds__(PRE_THREADS)
-clip_preprocess_kernel(const uint8_t* __restrict__ src, const PreImage* __restrict__ images, const int* __restrict__ tables,
-                       int out_size, uchar3 background, float3 mean, float3 stdv, OUT* __restrict__ out) {
-    extern __shared__ uint8_t band[];                 // [band_rows][out_size][3] horizontally resampled rows
+image_preprocess_kernel(const uint8_t* __restrict__ src, const PreImage* __restrict__ images, const int* __restrict__ tables,
+                        uchar3 background, float3 mean, float3 stdv, PrePatchGeom geom, OUT* __restrict__ out) {
+    extern __shared__ uint32_t pre_smem[];
     const PreImage im = images[blockIdx.y];
     const int y0 = blockIdx.x * im.tile_rows;
-    if (y0 >= out_size) return;
-    const int ny = min(im.tile_rows, out_size - y0);
+    if (y0 >= im.out_h) return;
+    const int out_w = im.out_w;
+    const int ny = min(im.tile_rows, im.out_h - y0);
+    float* lut = reinterpret_cast<float*>(pre_smem);                 // [3][256] normalised value of every grey level
+    uint32_t* band = pre_smem + 768;                                  // [band_rows][out_w] RGBX, horizontally resampled canvas rows
+    uint32_t* stage = band + (size_t)im.band_rows * out_w;            // [chunk_rows][span] RGBX canvas rows
     const int* hb = tables + im.htab;
-    const int* hk = hb + 2 * out_size;
+    const int* hk = hb + 2 * out_w;
     const int* vb = tables + im.vtab;
-    const int* vk = vb + 2 * out_size;
-    // source rows this band needs: windows are monotonic in y
+    const int* vk = vb + 2 * im.out_h;
+    // canvas rows this band needs: the windows are monotonic in y
     const int r0 = vb[2 * y0];
     const int r1 = vb[2 * (y0 + ny - 1)] + vb[2 * (y0 + ny - 1) + 1];
     const int nrows = r1 - r0;
-    const int row_elems = out_size * 3;
     const uint8_t* img = src + im.src_off;
-    const int bg[3] = {background.x, background.y, background.z};
+    const uint32_t bgw = (uint32_t)background.x | ((uint32_t)background.y << 8) | ((uint32_t)background.z << 16);
+    const int lane_x = threadIdx.x % PRE_XL, grp = threadIdx.x / PRE_XL;
 
-    // ---- horizontal pass: canvas rows r0 .. r1 -> band (uint8, rounded exactly like ImagingResampleHorizontal_8bpc)
-    for (int idx = threadIdx.x; idx < nrows * row_elems; idx += PRE_THREADS) {
-        const int r = idx / row_elems, rem = idx - r * row_elems;
-        const int xx = rem / 3, c = rem - xx * 3;
-        const int xmin = hb[2 * xx], n = hb[2 * xx + 1];
-        const int* k = hk + (size_t)xx * im.hks;
-        const int sy = r0 + r - im.paste_y;           // row inside the stored image
-        int ss = 1 << (PRE_PRECISION_BITS - 1);
-        if (sy < 0 || sy >= im.h) {
-            for (int x = 0; x < n; ++x) ss += bg[c] * k[x];
-        } else {
-            const uint8_t* row = img + (size_t)sy * im.w * 3 + c;
-            for (int x = 0; x < n; ++x) {
-                const int sx = xmin + x - im.paste_x;
-                const int v = (sx < 0 || sx >= im.w) ? bg[c] : (int)row[(size_t)sx * 3];
-                ss += v * k[x];
+    // out = ((u8 / 255) - mean[c]) / std[c] in fp32 with IEEE division and no fma, as numpy / torch compute it on the host
+    for (int i = threadIdx.x; i < 768; i += PRE_THREADS) {
+        const int c = i >> 8;
+        const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z), sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+        lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mu), sd);
+    }
+
+    for (int rc = 0; rc < nrows; rc += im.chunk_rows) {
+        const int nr = min(im.chunk_rows, nrows - rc);
+        // ---- stage canvas rows r0+rc .. as RGBX words; outside the pasted image the canvas is the padding colour
+        for (int rr = 0; rr < nr; ++rr) {
+            const int sy = r0 + rc + rr - im.paste_y;
+            const bool row_in = sy >= 0 && sy < im.h;
+            const uint8_t* row = img + (size_t)(row_in ? sy : 0) * im.w * 3;
+            for (int cx = threadIdx.x; cx < im.span; cx += PRE_THREADS) {
+                const int sx = cx + im.x_lo - im.paste_x;
+                uint32_t px = bgw;
+                if (row_in && sx >= 0 && sx < im.w) {
+                    const uint8_t* p = row + (size_t)sx * 3;
+                    px = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                }
+                stage[rr * im.span + cx] = px;
             }
         }
-        band[idx] = (uint8_t)pre_clip8(ss);
+        __syncthreads();
+        // ---- horizontal pass (ImagingResampleHorizontal_8bpc): thread = one output column, rows grp, grp + PRE_RG, ...
+        for (int xx = lane_x; xx < out_w; xx += PRE_XL) {
+            const int xmin = hb[2 * xx] - im.x_lo, n = hb[2 * xx + 1];
+            const int* k = hk + (size_t)xx * im.hks;
+            int acc[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 1 << (PRE_PRECISION_BITS - 1);
+            for (int x = 0; x < n; ++x) {
+                const int kv = __ldg(k + x);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = grp + PRE_RG * q;
+                    if (rr < nr) {
+                        const uint32_t px = stage[rr * im.span + xmin + x];
+                        acc[q][0] += (int)(px & 0xffu) * kv;
+                        acc[q][1] += (int)((px >> 8) & 0xffu) * kv;
+                        acc[q][2] += (int)((px >> 16) & 0xffu) * kv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rr = grp + PRE_RG * q;
+                if (rr < nr)
+                    band[(size_t)(rc + rr) * out_w + xx] = (uint32_t)pre_clip8(acc[q][0]) | ((uint32_t)pre_clip8(acc[q][1]) << 8) |
+                                                           ((uint32_t)pre_clip8(acc[q][2]) << 16);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- vertical pass + rescale + normalise: out[c][y][x] = ((u8 / 255) - mean[c]) / std[c] in fp32 (IEEE division, no fma)
-    const float mu[3] = {mean.x, mean.y, mean.z}, sd[3] = {stdv.x, stdv.y, stdv.z};
-    OUT* dst = out + (size_t)blockIdx.y * 3 * out_size * out_size;
-    for (int idx = threadIdx.x; idx < ny * row_elems; idx += PRE_THREADS) {
-        const int xx = idx % out_size;
-        const int c = (idx / out_size) % 3;
-        const int y = y0 + idx / row_elems;
-        const int ymin = vb[2 * y], n = vb[2 * y + 1];
+    // ---- vertical pass (ImagingResampleVertical_8bpc) + normalisation
+    OUT* dst = out + im.out_off;
+    const int ps = geom.patch, mg = geom.merge, pp = geom.patch * geom.patch;
+    const int gwm = LAYOUT == PRE_QWEN_PATCHES ? out_w / (ps * mg) : 0;
+    for (int yy = grp; yy < ny; yy += PRE_RG) {
+        const int y = y0 + yy;
+        const int ymin = vb[2 * y] - r0, n = vb[2 * y + 1];
         const int* k = vk + (size_t)y * im.vks;
-        const uint8_t* col = band + (size_t)(ymin - r0) * row_elems + xx * 3 + c;
-        int ss = 1 << (PRE_PRECISION_BITS - 1);
-        for (int j = 0; j < n; ++j) ss += (int)col[(size_t)j * row_elems] * k[j];
-        const float u = (float)pre_clip8(ss);
-        const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mu[c]), sd[c]);
-        const size_t o = ((size_t)c * out_size + y) * out_size + xx;
-        if constexpr (sizeof(OUT) == 4) dst[o] = v;
-        else dst[o] = __float2bfloat16_rn(v);
+        for (int xx = lane_x; xx < out_w; xx += PRE_XL) {
+            int a0 = 1 << (PRE_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+            const uint32_t* col = band + (size_t)ymin * out_w + xx;
+            for (int j = 0; j < n; ++j) {
+                const int kv = __ldg(k + j);
+                const uint32_t px = col[(size_t)j * out_w];
+                a0 += (int)(px & 0xffu) * kv;
+                a1 += (int)((px >> 8) & 0xffu) * kv;
+                a2 += (int)((px >> 16) & 0xffu) * kv;
+            }
+            const float v[3] = {lut[pre_clip8(a0)], lut[256 + pre_clip8(a1)], lut[512 + pre_clip8(a2)]};
+            if constexpr (LAYOUT == PRE_CHW) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const size_t o = ((size_t)c * im.out_h + y) * out_w + xx;
+                    if constexpr (sizeof(OUT) == 4) dst[o] = v[c];
+                    else dst[o] = __float2bfloat16_rn(v[c]);
+                }
+            } else {
+                const int gy = y / ps, py = y - gy * ps, gx = xx / ps, px_ = xx - gx * ps;
+                const size_t row = (((size_t)(gy / mg) * gwm + gx / mg) * mg + gy % mg) * mg + gx % mg;
+                OUT* q = dst + row * (size_t)(3 * geom.temporal * pp) + py * ps + px_;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    for (int t = 0; t < geom.temporal; ++t) {
+                        if constexpr (sizeof(OUT) == 4) q[(size_t)(c * geom.temporal + t) * pp] = v[c];
+                        else q[(size_t)(c * geom.temporal + t) * pp] = __float2bfloat16_rn(v[c]);
+                    }
+            }
+        }
     }
 }
 
@@ -165,11 +240,59 @@ struct PrePlan {
     size_t bytes() const { return images_bytes() + tables.size() * sizeof(int); }
 };
 
+struct PreTableKey { int ch, cw, nh, nw, top, left, oh, ow, htab, vtab, hks, vks, tile, band, x_lo, span, chunk; };
+inline size_t pre_smem_bytes(int band_rows, int out_w, int chunk_rows, int span) {
+    return 768 * sizeof(float) + ((size_t)band_rows * out_w + (size_t)chunk_rows * span) * sizeof(uint32_t);
+}
+
+// Tables + band geometry for "resize the ch x cw canvas to nh x nw, keep the oh x ow window at (top, left)"; shared between images
+// with the same geometry. Returns nullptr (plan.error set) when the vertical window cannot fit the shared-memory budget.
+inline const PreTableKey* pre_tables(PrePlan& plan, std::vector<PreTableKey>& cache, int ch, int cw, int nh, int nw, int top, int left,
+                                     int oh, int ow) {
+    for (const PreTableKey& k : cache)
+        if (k.ch == ch && k.cw == cw && k.nh == nh && k.nw == nw && k.top == top && k.left == left && k.oh == oh && k.ow == ow) return &k;
+    PreTableKey k{ch, cw, nh, nw, top, left, oh, ow, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    k.htab = (int)plan.tables.size();
+    k.hks = pre_build_table(cw, nw, left, ow, plan.tables);
+    k.vtab = (int)plan.tables.size();
+    k.vks = pre_build_table(ch, nh, top, oh, plan.tables);
+    const int* hb = plan.tables.data() + k.htab;
+    const int* vb = plan.tables.data() + k.vtab;
+    k.x_lo = hb[0];                                // horizontal windows are monotonic: first start .. last end
+    k.span = hb[2 * (ow - 1)] + hb[2 * (ow - 1) + 1] - k.x_lo;
+    // output rows per CTA (<= 16) and canvas rows staged per pass (<= PRE_MAX_CHUNK): the largest that fit the shared-memory budget
+    int tile = 16, band = 0, chunk = 1;
+    for (; tile >= 1; tile >>= 1) {
+        band = 0;
+        for (int y0 = 0; y0 < oh; y0 += tile) {
+            const int y1 = (y0 + tile < oh ? y0 + tile : oh) - 1;
+            const int rows = vb[2 * y1] + vb[2 * y1 + 1] - vb[2 * y0];
+            if (rows > band) band = rows;
+        }
+        for (chunk = PRE_MAX_CHUNK; chunk > 1 && pre_smem_bytes(band, ow, chunk, k.span) > (size_t)PRE_MAX_SMEM; chunk >>= 1) {}
+        if (pre_smem_bytes(band, ow, chunk, k.span) <= (size_t)PRE_MAX_SMEM) break;
+    }
+    if (tile < 1) { plan.error = "image too large for the device resize (filter windows exceed shared memory)"; return nullptr; }
+    k.tile = tile; k.band = band; k.chunk = chunk;
+    cache.push_back(k);
+    return &cache.back();
+}
+
+inline void pre_finish_image(PrePlan& plan, PreImage& im, const PreTableKey& k) {
+    im.htab = k.htab; im.vtab = k.vtab; im.hks = k.hks; im.vks = k.vks;
+    im.tile_rows = k.tile; im.band_rows = k.band; im.out_h = k.oh; im.out_w = k.ow;
+    im.x_lo = k.x_lo; im.span = k.span; im.chunk_rows = k.chunk;
+    const int tiles = (k.oh + k.tile - 1) / k.tile;
+    if (tiles > plan.max_tiles) plan.max_tiles = tiles;
+    const size_t sm = pre_smem_bytes(k.band, k.ow, k.chunk, k.span);
+    if (sm > plan.smem) plan.smem = sm;
+}
+
 // Geometry of CLIPImageProcessor for one image (shortest edge -> S, int() truncation of the long edge, centre crop S x S), on the
-// padded canvas when pad_to_square. Tables are shared between images of the same canvas size.
+// padded canvas when pad_to_square. Output [n, 3, S, S].
 inline bool pre_plan(const int32_t* heights, const int32_t* widths, const int64_t* offsets, int n, int S, bool pad, PrePlan& plan) {
-    struct Key { int ch, cw, htab, vtab, hks, vks, tile, band; };
-    std::vector<Key> cache;
+    std::vector<PreTableKey> cache;
+    cache.reserve(n);
     plan.images.resize(n);
     for (int i = 0; i < n; ++i) {
         const int h = heights[i], w = widths[i];
@@ -179,43 +302,67 @@ inline bool pre_plan(const int32_t* heights, const int32_t* widths, const int64_
         const int side = h > w ? h : w;
         im.canvas_h = pad ? side : h; im.canvas_w = pad ? side : w;
         im.paste_x = pad ? (side - w) / 2 : 0; im.paste_y = pad ? (side - h) / 2 : 0;
-        const Key* hit = nullptr;
-        for (const Key& k : cache) if (k.ch == im.canvas_h && k.cw == im.canvas_w) { hit = &k; break; }
-        if (!hit) {
-            const int ch = im.canvas_h, cw = im.canvas_w;
-            // get_resize_output_image_size(shortest_edge = S, default_to_square = False): short -> S, long -> int(S * long / short)
-            const int nw = cw <= ch ? S : (int)((double)S * cw / ch);
-            const int nh = cw <= ch ? (int)((double)S * ch / cw) : S;
-            const int left = (nw - S) / 2, top = (nh - S) / 2;        // centre crop (both >= 0 since the short side == S)
-            Key k; k.ch = ch; k.cw = cw;
-            k.htab = (int)plan.tables.size();
-            k.hks = pre_build_table(cw, nw, left, S, plan.tables);
-            k.vtab = (int)plan.tables.size();
-            k.vks = pre_build_table(ch, nh, top, S, plan.tables);
-            // tile rows: as many as fit the shared-memory budget, at most 16
-            const int* vb = plan.tables.data() + k.vtab;
-            int tile = 16, band = 0;
-            for (; tile >= 1; tile >>= 1) {
-                band = 0;
-                for (int y0 = 0; y0 < S; y0 += tile) {
-                    const int y1 = (y0 + tile < S ? y0 + tile : S) - 1;
-                    const int rows = vb[2 * y1] + vb[2 * y1 + 1] - vb[2 * y0];
-                    if (rows > band) band = rows;
-                }
-                if ((size_t)band * S * 3 <= (size_t)PRE_MAX_SMEM) break;
-            }
-            if (tile < 1) { plan.error = "image too large for the device resize (vertical filter window exceeds shared memory)"; return false; }
-            k.tile = tile; k.band = band;
-            cache.push_back(k);
-            hit = &cache.back();
-        }
-        im.htab = hit->htab; im.vtab = hit->vtab; im.hks = hit->hks; im.vks = hit->vks;
-        im.tile_rows = hit->tile; im.band_rows = hit->band;
-        const int tiles = (S + im.tile_rows - 1) / im.tile_rows;
-        if (tiles > plan.max_tiles) plan.max_tiles = tiles;
-        const size_t sm = (size_t)im.band_rows * S * 3;
-        if (sm > plan.smem) plan.smem = sm;
+        const int ch = im.canvas_h, cw = im.canvas_w;
+        // get_resize_output_image_size(shortest_edge = S, default_to_square = False): short -> S, long -> int(S * long / short)
+        const int nw = cw <= ch ? S : (int)((double)S * cw / ch);
+        const int nh = cw <= ch ? (int)((double)S * ch / cw) : S;
+        const PreTableKey* k = pre_tables(plan, cache, ch, cw, nh, nw, (nh - S) / 2, (nw - S) / 2, S, S);   // centre crop
+        if (!k) return false;
+        pre_finish_image(plan, im, *k);
+        im.out_off = (long long)i * 3 * S * S;
     }
+    return true;
+}
+
+// qwen_vl_utils / Qwen2VLImageProcessor smart_resize (image_processing_qwen2_vl.py:62-87): both sides multiples of `factor`, pixel
+// count within [min_pixels, max_pixels]. Python's round() is round-half-even = nearbyint in the default rounding mode.
+inline bool pre_smart_resize(int height, int width, int factor, long long min_pixels, long long max_pixels, int& h_bar, int& w_bar) {
+    const int mx = height > width ? height : width, mn = height > width ? width : height;
+    if ((double)mx / mn > 200.0) return false;
+    h_bar = (int)std::nearbyint((double)height / factor) * factor;
+    w_bar = (int)std::nearbyint((double)width / factor) * factor;
+    if ((long long)h_bar * w_bar > max_pixels) {
+        const double beta = std::sqrt(((double)height * width) / (double)max_pixels);
+        h_bar = (int)std::floor((double)height / beta / factor) * factor;
+        w_bar = (int)std::floor((double)width / beta / factor) * factor;
+        if (h_bar < factor) h_bar = factor;
+        if (w_bar < factor) w_bar = factor;
+    } else if ((long long)h_bar * w_bar < min_pixels) {
+        const double beta = std::sqrt((double)min_pixels / ((double)height * width));
+        h_bar = (int)std::ceil((double)height * beta / factor) * factor;
+        w_bar = (int)std::ceil((double)width * beta / factor) * factor;
+    }
+    return true;
+}
+
+// Qwen still images: smart_resize, plain bicubic resize of the whole image (no canvas, no crop), patch-row output; image i's rows
+// start at sum_{j<i} gh_j * gw_j. grid_hw[i] = (gh, gw) in patches.
+inline bool pre_plan_qwen(const int32_t* heights, const int32_t* widths, const int64_t* offsets, int n, int patch, int merge, int temporal,
+                          long long min_pixels, long long max_pixels, PrePlan& plan, int32_t* grid_hw, long long* total_rows) {
+    std::vector<PreTableKey> cache;
+    cache.reserve(n);
+    plan.images.resize(n);
+    long long rows = 0;
+    const long long row_elems = 3LL * temporal * patch * patch;
+    for (int i = 0; i < n; ++i) {
+        const int h = heights[i], w = widths[i];
+        if (h <= 0 || w <= 0) { plan.error = "image with non-positive size"; return false; }
+        int rh, rw;
+        if (!pre_smart_resize(h, w, patch * merge, min_pixels, max_pixels, rh, rw)) {
+            plan.error = "absolute aspect ratio must be smaller than 200";
+            return false;
+        }
+        PreImage& im = plan.images[i];
+        im.src_off = offsets[i]; im.h = h; im.w = w;
+        im.canvas_h = h; im.canvas_w = w; im.paste_x = im.paste_y = 0;
+        const PreTableKey* k = pre_tables(plan, cache, h, w, rh, rw, 0, 0, rh, rw);
+        if (!k) return false;
+        pre_finish_image(plan, im, *k);
+        im.out_off = rows * row_elems;
+        if (grid_hw) { grid_hw[2 * i] = rh / patch; grid_hw[2 * i + 1] = rw / patch; }
+        rows += (long long)(rh / patch) * (rw / patch);
+    }
+    if (total_rows) *total_rows = rows;
     return true;
 }
 

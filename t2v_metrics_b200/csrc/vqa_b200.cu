@@ -980,20 +980,12 @@ extern "C" size_t vqa_clip_preprocess_workspace_bytes(const int32_t* heights, co
     return plan.bytes();
 }
 
-extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
-                                   int32_t n_images, int32_t out_size, int32_t pad_to_square, const uint8_t* background,
-                                   const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-    if (!src || !offsets || !heights || !widths || !background || !mean || !stdv || !out || !workspace)
-        return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
-    if (n_images <= 0 || out_size <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad size");
-    if (out_dtype != VQA_DTYPE_F32 && out_dtype != VQA_DTYPE_BF16) return fail(nullptr, VQA_ERR_INVALID_ARG, "out_dtype must be f32 or bf16");
-    PrePlan plan;
-    if (!pre_plan(heights, widths, offsets, n_images, out_size, pad_to_square != 0, plan)) return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+template <int LAYOUT>
+static int pre_launch(const PrePlan& plan, const void* src, int n_images, const uint8_t* background, const float* mean, const float* stdv,
+                      PrePatchGeom geom, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (workspace_bytes < plan.bytes()) return fail(nullptr, VQA_ERR_WORKSPACE, "pre-processing workspace too small");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    // pageable host -> device: the runtime stages the bytes before returning, so the vectors may die with this frame
+    // pageable host -> device: the runtime stages the bytes before returning, so the plan may die with the caller's frame
     cudaError_t e = cudaMemcpyAsync(ws, plan.images.data(), plan.images.size() * sizeof(PreImage), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(ws + plan.images_bytes(), plan.tables.data(), plan.tables.size() * sizeof(int), cudaMemcpyHostToDevice, st);
@@ -1004,17 +996,76 @@ extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, cons
     const float3 mu = make_float3(mean[0], mean[1], mean[2]), sd = make_float3(stdv[0], stdv[1], stdv[2]);
     dim3 grid(plan.max_tiles, n_images);
     if (out_dtype == VQA_DTYPE_F32) {
-        e = cudaFuncSetAttribute(clip_preprocess_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
+        e = cudaFuncSetAttribute(image_preprocess_kernel<float, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
         if (e == cudaSuccess)
-            clip_preprocess_kernel<float><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, out_size, bg,
-                                                                              mu, sd, static_cast<float*>(out));
+            image_preprocess_kernel<float, LAYOUT><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, bg,
+                                                                                        mu, sd, geom, static_cast<float*>(out));
     } else {
-        e = cudaFuncSetAttribute(clip_preprocess_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
+        e = cudaFuncSetAttribute(image_preprocess_kernel<bf16, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRE_MAX_SMEM);
         if (e == cudaSuccess)
-            clip_preprocess_kernel<bf16><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, out_size, bg,
-                                                                             mu, sd, static_cast<bf16*>(out));
+            image_preprocess_kernel<bf16, LAYOUT><<<grid, PRE_THREADS, plan.smem, st>>>(static_cast<const uint8_t*>(src), d_images, d_tables, bg,
+                                                                                       mu, sd, geom, static_cast<bf16*>(out));
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("pre-processing launch: ") + cudaGetErrorString(e));
     return VQA_OK;
+}
+
+extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                                   int32_t n_images, int32_t out_size, int32_t pad_to_square, const uint8_t* background,
+                                   const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    if (!src || !offsets || !heights || !widths || !background || !mean || !stdv || !out || !workspace)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    if (n_images <= 0 || out_size <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad size");
+    if (out_dtype != VQA_DTYPE_F32 && out_dtype != VQA_DTYPE_BF16) return fail(nullptr, VQA_ERR_INVALID_ARG, "out_dtype must be f32 or bf16");
+    PrePlan plan;
+    if (!pre_plan(heights, widths, offsets, n_images, out_size, pad_to_square != 0, plan)) return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+    return pre_launch<PRE_CHW>(plan, src, n_images, background, mean, stdv, PrePatchGeom{1, 1, 1}, out, out_dtype, workspace, workspace_bytes,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vqa_qwen_preprocess_plan(const int32_t* heights, const int32_t* widths, int32_t n_images, int32_t patch, int32_t merge,
+                                        int64_t min_pixels, int64_t max_pixels, int32_t* grid_hw, int64_t* total_patches,
+                                        size_t* workspace_bytes) {
+    if (!heights || !widths || n_images <= 0 || patch <= 0 || merge <= 0 || min_pixels <= 0 || max_pixels < min_pixels)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "bad argument");
+    PrePlan plan;
+    std::vector<int64_t> off(n_images, 0);
+    long long rows = 0;
+    if (!pre_plan_qwen(heights, widths, off.data(), n_images, patch, merge, 1, min_pixels, max_pixels, plan, grid_hw, &rows))
+        return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+    if (total_patches) *total_patches = rows;
+    if (workspace_bytes) *workspace_bytes = plan.bytes();
+    return VQA_OK;
+}
+
+extern "C" int vqa_qwen_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
+                                   int32_t patch, int32_t temporal_patch, int32_t merge, int64_t min_pixels, int64_t max_pixels,
+                                   const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    if (!src || !offsets || !heights || !widths || !mean || !stdv || !out || !workspace) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+    if (n_images <= 0 || patch <= 0 || merge <= 0 || temporal_patch <= 0 || min_pixels <= 0 || max_pixels < min_pixels)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "bad argument");
+    if (out_dtype != VQA_DTYPE_F32 && out_dtype != VQA_DTYPE_BF16) return fail(nullptr, VQA_ERR_INVALID_ARG, "out_dtype must be f32 or bf16");
+    PrePlan plan;
+    if (!pre_plan_qwen(heights, widths, offsets, n_images, patch, merge, temporal_patch, min_pixels, max_pixels, plan, nullptr, nullptr))
+        return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
+    const uint8_t no_bg[3] = {0, 0, 0};
+    return pre_launch<PRE_QWEN_PATCHES>(plan, src, n_images, no_bg, mean, stdv, PrePatchGeom{patch, merge, temporal_patch}, out, out_dtype,
+                                        workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Host-only: the fixed-point tap table of one resize axis, exactly as vqa_clip_preprocess builds it (for CPU tests of the host logic).
+// bounds: [count][2] (first source index, taps used), kk: [count][ksize] with ksize = return value (call with kk = NULL to size it).
+extern "C" int32_t vqa_resample_table(int32_t in_size, int32_t out_size, int32_t first, int32_t count, int32_t* bounds, int32_t* kk) {
+    if (in_size <= 0 || out_size <= 0 || first < 0 || count <= 0 || first + count > out_size) {
+        fail(nullptr, VQA_ERR_INVALID_ARG, "bad resample table request");
+        return 0;
+    }
+    std::vector<int> tab;
+    const int ksize = pre_build_table(in_size, out_size, first, count, tab);
+    if (bounds) memcpy(bounds, tab.data(), (size_t)count * 2 * sizeof(int));
+    if (kk) memcpy(kk, tab.data() + (size_t)count * 2, (size_t)count * ksize * sizeof(int));
+    return ksize;
 }

@@ -197,6 +197,15 @@ class ClipT5Engine:
         scores = self.score_tensors(d[0], d[1], d[2], d[3], image_index=d[4])
         return scores.cpu()
 
+    def score_images_u8(self, images_u8, input_ids: torch.Tensor, text_lens: torch.Tensor, labels: torch.Tensor,
+                        image_index: Optional[torch.Tensor] = None, pad: bool = True) -> torch.Tensor:
+        """End to end from DECODED images: uint8 HWC host (pinned) or device tensors -> device pre-processing kernel -> scores on
+        the host. The reference does the resize + normalise per image on the CPU (a4 in SURVEY 8a) before its forward."""
+        dev = self.device
+        pixels = clip_preprocess_u8(images_u8, self.cfg.image_size, dev, pad=pad)
+        d = [t.to(dev, non_blocking=True) if t is not None else None for t in (input_ids, text_lens, labels, image_index)]
+        return self.score_tensors(pixels, d[0], d[1], d[2], image_index=d[3]).cpu()
+
     def last_launch_count(self) -> int:
         return int(self.lib.vqa_last_launch_count(self._h))
 
@@ -289,7 +298,10 @@ def clip_preprocess_u8(images: Sequence[torch.Tensor], out_size: int, device, pa
         assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3, "images must be uint8 [h, w, 3]"
         hs.append(int(im.shape[0])); ws.append(int(im.shape[1])); offs.append(total)
         total += int(im.numel())
-    if all(im.is_cuda for im in images):
+    if isinstance(images, torch.Tensor):      # one packed [n, h, w, 3] batch of equal-size images: no staging copy
+        src = images.contiguous().view(-1)
+        src = src if src.is_cuda else src.to(dev, non_blocking=True)
+    elif all(im.is_cuda for im in images):
         src = images[0].contiguous().view(-1) if n == 1 else torch.cat([im.contiguous().view(-1) for im in images])
     else:
         stage = torch.empty(total, dtype=torch.uint8, pin_memory=True)
@@ -313,6 +325,56 @@ def clip_preprocess_u8(images: Sequence[torch.Tensor], out_size: int, device, pa
     _check(rc, None, "vqa_clip_preprocess")
     # src / wsb stay referenced by the caching allocator's stream ordering: both were allocated on the current stream
     return out
+
+
+def qwen_preprocess_plan(sizes_hw: Sequence[Sequence[int]], patch: int = 14, merge: int = 2, min_pixels: int = 56 * 56,
+                         max_pixels: int = 14 * 14 * 4 * 1280):
+    """Host-only geometry of the Qwen pre-processing (smart_resize): -> ([(1, gh, gw), ...], total patch rows, workspace bytes)."""
+    lib = _lib.load()
+    n = len(sizes_hw)
+    H = (C.c_int32 * n)(*[int(s[0]) for s in sizes_hw])
+    W = (C.c_int32 * n)(*[int(s[1]) for s in sizes_hw])
+    grid = (C.c_int32 * (2 * n))()
+    total, wsb = C.c_int64(0), C.c_size_t(0)
+    _check(lib.vqa_qwen_preprocess_plan(H, W, n, patch, merge, min_pixels, max_pixels, grid, C.byref(total), C.byref(wsb)), None,
+           "vqa_qwen_preprocess_plan")
+    return [(1, int(grid[2 * i]), int(grid[2 * i + 1])) for i in range(n)], int(total.value), int(wsb.value)
+
+
+def qwen_preprocess_u8(images: Sequence[torch.Tensor], device, patch: int = 14, temporal_patch: int = 2, merge: int = 2,
+                       min_pixels: int = 56 * 56, max_pixels: int = 14 * 14 * 4 * 1280, mean=CLIP_MEAN, std=CLIP_STD,
+                       out_dtype: torch.dtype = torch.float32):
+    """Decoded still images (uint8 HWC RGB, host or device) -> (pixel_patches [sum gh*gw, 3*temporal*patch^2] on the device,
+    [(1, gh, gw), ...]) by ONE kernel launch: smart_resize + PIL-exact bicubic + /255 + normalise + frame duplication + merge-order
+    patch rows -- bit-identical to models/vqascore_models/qwen_utils.qwen_image_to_patches (the CPU path)."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    n = len(images)
+    assert n > 0
+    hs, ws, offs, total = [], [], [], 0
+    for im in images:
+        assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3, "images must be uint8 [h, w, 3]"
+        hs.append(int(im.shape[0])); ws.append(int(im.shape[1])); offs.append(total)
+        total += int(im.numel())
+    grids, rows, need = qwen_preprocess_plan(list(zip(hs, ws)), patch, merge, min_pixels, max_pixels)
+    if isinstance(images, torch.Tensor):
+        src = images.contiguous().view(-1)
+        src = src if src.is_cuda else src.to(dev, non_blocking=True)
+    elif all(im.is_cuda for im in images):
+        src = images[0].contiguous().view(-1) if n == 1 else torch.cat([im.contiguous().view(-1) for im in images])
+    else:
+        stage = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        for im, o in zip(images, offs):
+            stage[o:o + im.numel()] = im.contiguous().view(-1)
+        src = stage.to(dev, non_blocking=True)
+    out = torch.empty(rows, 3 * temporal_patch * patch * patch, dtype=out_dtype, device=dev)
+    wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+    rc = lib.vqa_qwen_preprocess(_ptr(src), (C.c_int64 * n)(*offs), (C.c_int32 * n)(*hs), (C.c_int32 * n)(*ws), n, patch, temporal_patch,
+                                 merge, min_pixels, max_pixels, (C.c_float * 3)(*mean), (C.c_float * 3)(*std), _ptr(out),
+                                 _lib.VQA_DTYPE_F32 if out_dtype == torch.float32 else _lib.VQA_DTYPE_BF16, _ptr(wsb), wsb.numel(),
+                                 _stream_ptr(dev))
+    _check(rc, None, "vqa_qwen_preprocess")
+    return out, grids
 
 
 # ================================================================================================ Qwen2.5-VL

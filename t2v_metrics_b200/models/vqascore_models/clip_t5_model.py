@@ -94,11 +94,13 @@ class CLIPT5Model(VQAScoreModel):
 
     # ---- pre-processing ------------------------------------------------------------------------------------------
     def load_images(self, image: List[str]) -> torch.Tensor:
-        """image_loader -> expand2square(mean colour) -> CLIP preprocess; returns fp32 [n,3,S,S] on the device."""
-        tensors = [clip_preprocess(self.image_loader(p), self.cfg.image_size, pad=self.image_aspect_ratio == "pad")
-                   for p in image]
-        batch = torch.stack(tensors, dim=0).pin_memory()
-        return batch.to(self.engine.device, non_blocking=True)
+        """image_loader (PIL decode, host) -> uint8 HWC -> ONE device kernel doing expand2square(mean colour) + PIL-exact bicubic
+        resize + centre crop + /255 + normalise (engine.clip_preprocess_u8; bit-identical to the CPU path `clip_preprocess`, which
+        is what the reference runs per image on the host: mm_utils.py:128-139 + CLIPImageProcessor). fp32 [n,3,S,S] on the device."""
+        import numpy as np
+        from ...engine import clip_preprocess_u8
+        raw = [torch.from_numpy(np.ascontiguousarray(np.asarray(self.image_loader(p).convert("RGB"), dtype=np.uint8))) for p in image]
+        return clip_preprocess_u8(raw, self.cfg.image_size, self.engine.device, pad=self.image_aspect_ratio == "pad")
 
     def _tokenize(self, questions: List[str], answers: List[str]):
         ids = [t5_tokenizer_image_token(q, self.tokenizer)[: self.context_len] for q in questions]

@@ -79,11 +79,12 @@ class Qwen2VLModel(VQAScoreModel):
         """-> (patches fp32 [sum P, 1176] on the device, [(1, gh, gw), ...])"""
         if any(p[-4:].lower() in (".mp4", ".avi", ".mov", ".mkv") for p in image):
             raise NotImplementedError("video inputs are outside the B200 engine's hot-path scope")
-        ps, gs = [], []
-        for p in image:
-            x, g = qwen_image_to_patches(self.image_loader(p), self.cfg.patch_size, self.cfg.temporal_patch_size, self.cfg.spatial_merge_size)
-            ps.append(x); gs.append(g)
-        return torch.cat(ps, dim=0).pin_memory().to(self.engine.device, non_blocking=True), gs
+        # PIL decode on the host, everything else (smart_resize, PIL-exact bicubic, normalise, frame duplication, merge-order patch
+        # rows) in ONE device kernel -- bit-identical to qwen_utils.qwen_image_to_patches, the CPU path the reference runs per image
+        import numpy as np
+        from ...engine import qwen_preprocess_u8
+        raw = [torch.from_numpy(np.ascontiguousarray(np.asarray(self.image_loader(p).convert("RGB"), dtype=np.uint8))) for p in image]
+        return qwen_preprocess_u8(raw, self.engine.device, self.cfg.patch_size, self.cfg.temporal_patch_size, self.cfg.spatial_merge_size)
 
     @torch.no_grad()
     def forward(self, images: List[str], texts: List[str], fps=None, question_template: str = default_question_template,

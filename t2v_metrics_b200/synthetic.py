@@ -76,7 +76,7 @@ def synthetic_engine_weights(cfg: ClipT5Config, device, seed: int = 0) -> Dict[s
 
 
 def synthetic_batch(cfg: ClipT5Config, batch: int, text_len: int = 97, seed: int = 1, ragged: bool = False,
-                    label_ids=(2163, 1), source_size: int = 512, n_images: Optional[int] = None):
+                    label_ids=(2163, 1), source_size: int = 512, n_images: Optional[int] = None, raw_u8: bool = False):
     """HOST tensors of one step of BASELINE config 2: `batch` uniform-random uint8 source_size^2 RGB images, already taken
     through the reference pre-processing's geometry (a square image -> bicubic resize to image_size; for i.i.d. noise the
     resampled pixel statistics, not their values, are what matter to a throughput run, so the bench draws the resized
@@ -98,6 +98,8 @@ def synthetic_batch(cfg: ClipT5Config, batch: int, text_len: int = 97, seed: int
         ids[b, n:] = cfg.pad_token_id
     labels = torch.tensor([list(label_ids)] * batch, dtype=torch.int32)
     out = dict(pixels=pixels, input_ids=ids, text_lens=lens, labels=labels)
+    if raw_u8:          # the decoded source images themselves (uint8 HWC), for the end-to-end path with device pre-processing
+        out["raw_u8"] = torch.randint(0, 256, (ni, source_size, source_size, 3), generator=g, dtype=torch.uint8)
     if torch.cuda.is_available():
         out = {k: v.pin_memory() for k, v in out.items()}
     return out

@@ -188,6 +188,38 @@ def t_attention_perf(B=64, S=672, H=64, use_bias=1):
          mma_sync=os.environ.get("VQA_ATTN_MMA_SYNC", "0"))
 
 
+def t_preprocess_perf(n=64, size=512, out=336):
+    """Device pre-processing kernel alone: device-resident uint8 sources, HBM roofline = (source bytes + output bytes) / time;
+    plus the CPU (PIL) path on the host for the same images."""
+    import time
+    from PIL import Image
+    from oracle import clipt5_oracle as orc
+    from t2v_metrics_b200.engine import clip_preprocess_u8
+    n, size, out = int(n), int(size), int(out)
+    dev = "cuda:0"
+    raw = torch.randint(0, 256, (n, size, size, 3), dtype=torch.uint8)
+    d_raw = raw.to(dev)
+    dst = torch.empty(n, 3, out, out, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        clip_preprocess_u8(d_raw, out, dev, out=dst)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(20):
+        clip_preprocess_u8(d_raw, out, dev, out=dst)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 20
+    t0 = time.perf_counter()
+    m = min(n, 8)
+    ref = torch.stack([orc.clip_preprocess(Image.fromarray(raw[i].numpy()), out) for i in range(m)])
+    cpu_ms_per_image = (time.perf_counter() - t0) * 1000 / m
+    exact = bool(torch.equal(dst[:m].cpu(), ref))
+    by = raw.numel() + dst.numel() * 4
+    emit(test="preprocess_perf", n=n, size=size, out=out, ms=ms, us_per_image=1000 * ms / n, gbps=by / ms / 1e6, bytes=by,
+         cpu_pil_ms_per_image=cpu_ms_per_image, bit_exact=exact)
+
+
 def t_lmhead():
     from t2v_metrics_b200.engine import ops
     dev = "cuda:0"
