@@ -499,21 +499,15 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
         group_rows = max(512, min(8192, group_rows / 256 * 256));
     }
     p.group_m = max(1, group_rows / rows_per_tile);
-    // L2 residency: when W fits (<= 96 MB of the 126 MB L2) it is the operand every tile re-reads -> keep it (evict_last) and let
-    // the A rows stream (evict_first); otherwise the A panel of the current row group is what the sweep over N re-reads -> keep
-    // that and stream W. VQA_GEMM_L2_POLICY=<a><w> with digits 0 normal / 1 first / 2 last overrides (tuning).
+    // L2 eviction hints on the operand streams. Measured on B200 (profiles/r01_summary.md section 5): marking the re-read operand
+    // evict_last and the streamed one evict_first RAISED the step's GEMM DRAM reads from 445 GB to 694 GB and cost 5 % of throughput
+    // (an evict_first tile is dropped before the sibling CTAs that share it have fetched it), so the default is evict_normal on both.
+    // VQA_GEMM_L2_POLICY=<a><w> with digits 0 normal / 1 first / 2 last overrides (tuning).
     static const int env_pol = [] { const char* v = getenv("VQA_GEMM_L2_POLICY"); return (v && v[0] && v[1]) ? (v[0] - '0') * 10 + (v[1] - '0') : -1; }();
     const unsigned long long pol[3] = {L2_EVICT_NORMAL, L2_EVICT_FIRST, L2_EVICT_LAST};
-    const long long w_bytes = (long long)g.w_rows * p.K * 2;
-    const bool small_problem = (long long)p.M * p.K * 2 + w_bytes <= (64ll << 20);
+    p.a_policy = p.w_policy = L2_EVICT_NORMAL;
     if (env_pol >= 0 && env_pol / 10 < 3 && env_pol % 10 < 3) {
         p.a_policy = pol[env_pol / 10]; p.w_policy = pol[env_pol % 10];
-    } else if (small_problem) {
-        p.a_policy = p.w_policy = L2_EVICT_NORMAL;
-    } else if (w_bytes <= (96ll << 20)) {
-        p.a_policy = L2_EVICT_FIRST; p.w_policy = L2_EVICT_LAST;
-    } else {
-        p.a_policy = L2_EVICT_LAST; p.w_policy = L2_EVICT_FIRST;
     }
     const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_batches;
     int workers = num_sms / CG;

@@ -103,8 +103,11 @@ class CLIPT5Model(VQAScoreModel):
         return clip_preprocess_u8(raw, self.cfg.image_size, self.engine.device, pad=self.image_aspect_ratio == "pad")
 
     def _tokenize(self, questions: List[str], answers: List[str]):
-        ids = [t5_tokenizer_image_token(q, self.tokenizer)[: self.context_len] for q in questions]
-        labs = [t5_tokenizer_image_token(a, self.tokenizer)[: self.context_len] for a in answers]
+        cache = self.__dict__.setdefault("_chunk_cache", {})
+        if len(cache) > 65536:
+            cache.clear()
+        ids = [t5_tokenizer_image_token(q, self.tokenizer, chunk_cache=cache)[: self.context_len] for q in questions]
+        labs = [t5_tokenizer_image_token(a, self.tokenizer, chunk_cache=cache)[: self.context_len] for a in answers]
         pad = getattr(self.tokenizer, "pad_token_id", 0) or 0
         L, T = max(map(len, ids)), max(map(len, labs))
         input_ids = torch.full((len(ids), L), pad, dtype=torch.int32)

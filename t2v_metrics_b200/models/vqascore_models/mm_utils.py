@@ -1,5 +1,5 @@
 """Host-side pieces of the CLIP-FlanT5 path that survive in the reference's mm_utils.py, rebuilt for this engine."""
-from typing import Callable, List, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -22,14 +22,24 @@ def expand2square(pil_img: Image.Image, background_color) -> Image.Image:
     return canvas
 
 
-def t5_tokenizer_image_token(prompt: str, tokenizer, image_token_index: int = IMAGE_TOKEN_INDEX, return_tensors=None):
+def t5_tokenizer_image_token(prompt: str, tokenizer, image_token_index: int = IMAGE_TOKEN_INDEX, return_tensors=None,
+                             chunk_cache: Optional[dict] = None):
     """Tokenise every text chunk around '<image>' separately (each keeps its own trailing </s>) and join the chunks
-    with `image_token_index` (reference mm_utils.py:164-179)."""
+    with `image_token_index` (reference mm_utils.py:164-179).
+    `chunk_cache`: an exact memo chunk-string -> ids. The chunk before '<image>' is the constant system prompt and
+    M x N scoring repeats every caption M times, so the slow SentencePiece tokenizer (`use_fast=False`, mm_utils.py:198) runs once
+    per distinct chunk; whole chunks are the cache unit because sub-word tokenisation is not prefix-stable."""
     input_ids: List[int] = []
     for i, chunk in enumerate(prompt.split(DEFAULT_IMAGE_TOKEN)):
         if i > 0:
             input_ids.append(image_token_index)
-        input_ids.extend(tokenizer(chunk).input_ids)
+        if chunk_cache is None:
+            input_ids.extend(tokenizer(chunk).input_ids)
+        else:
+            ids = chunk_cache.get(chunk)
+            if ids is None:
+                ids = chunk_cache[chunk] = tuple(tokenizer(chunk).input_ids)
+            input_ids.extend(ids)
     if return_tensors is not None:
         if return_tensors == 'pt':
             return torch.tensor(input_ids, dtype=torch.long)

@@ -98,10 +98,15 @@ class Qwen2VLModel(VQAScoreModel):
         patches, grids = self.load_images(list(uniq.keys()))
         unit = self.cfg.spatial_merge_size ** 2
         prompts, answer_ids = [], []
+        cache = self.__dict__.setdefault("_prompt_cache", {})
+        if len(cache) > 65536:
+            cache.clear()
         for q, a, img in zip(questions, answers, index):
             t, gh, gw = grids[img]
-            prompts.append(build_prompt_ids(self.tokenizer, q, t * gh * gw // unit, self.cfg.image_token_id))
-            ids = list(self.tokenizer.encode(a, add_special_tokens=False))
+            prompts.append(build_prompt_ids(self.tokenizer, q, t * gh * gw // unit, self.cfg.image_token_id, cache))
+            ids = cache.get(("answer", a))
+            if ids is None:
+                ids = cache[("answer", a)] = tuple(self.tokenizer.encode(a, add_special_tokens=False))
             if not ids:
                 raise ValueError("empty answer")
             answer_ids.append(ids[0])      # max_new_tokens=1: only the first answer token is ever scored (qwen2vl_model.py:259-263)

@@ -10,7 +10,7 @@
 from __future__ import annotations
 
 import math
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -60,6 +60,13 @@ def qwen_image_to_patches(img: Image.Image, patch_size: int = 14, temporal_patch
     return x.reshape(gh * gw, 3 * temporal_patch_size * patch_size * patch_size).contiguous(), (1, gh, gw)
 
 
-def build_prompt_ids(tokenizer, question: str, n_image_tokens: int, image_token_id: int) -> List[int]:
-    enc = lambda s: list(tokenizer.encode(s, add_special_tokens=False))
+def build_prompt_ids(tokenizer, question: str, n_image_tokens: int, image_token_id: int, cache: Optional[dict] = None) -> List[int]:
+    """`cache`: exact memo string -> ids; the chat prefix is constant and M x N scoring repeats each question M times."""
+    def enc(s: str):
+        if cache is None:
+            return list(tokenizer.encode(s, add_special_tokens=False))
+        ids = cache.get(s)
+        if ids is None:
+            ids = cache[s] = tuple(tokenizer.encode(s, add_special_tokens=False))
+        return list(ids)
     return enc(CHAT_PREFIX) + [image_token_id] * n_image_tokens + enc(CHAT_SUFFIX.format(question=question))

@@ -36,6 +36,36 @@ def test_golden_vestiges_from_reference(golden_dir):
         assert orc.t5_tokenizer_image_token(case["prompt"], lambda c: FakeTok()(c).input_ids) == case["ids"]
 
 
+def test_tokenizer_chunk_cache_is_exact_and_saves_calls():
+    """the memo returns exactly what the uncached call returns and tokenises each distinct chunk once."""
+    class Counting(FakeTok):
+        calls = 0
+
+        def __call__(self, chunk):
+            Counting.calls += 1
+            return super().__call__(chunk)
+
+    tok, cache = Counting(), {}
+    prompts = [f"sys USER: <image>\nDoes this figure show \"{c}\"? ASSISTANT: " for c in ("a dog", "two cats", "a dog", "a dog")]
+    plain = [mm_utils.t5_tokenizer_image_token(p, FakeTok()) for p in prompts]
+    cached = [mm_utils.t5_tokenizer_image_token(p, tok, chunk_cache=cache) for p in prompts]
+    assert cached == plain
+    assert Counting.calls == 3            # the shared system chunk + two distinct caption chunks
+    from t2v_metrics_b200.models.vqascore_models.qwen_utils import build_prompt_ids
+
+    class QTok:
+        calls = 0
+
+        def encode(self, s, add_special_tokens=False):
+            QTok.calls += 1
+            return [5 + (ord(c) % 89) for c in s]
+
+    qc = {}
+    a = [build_prompt_ids(QTok(), q, 4, 600, qc) for q in ("x?", "y?", "x?")]
+    b = [build_prompt_ids(QTok(), q, 4, 600) for q in ("x?", "y?", "x?")]
+    assert a == b and a[0].count(600) == 4
+
+
 def test_tokenizer_each_chunk_keeps_its_eos():
     ids = mm_utils.t5_tokenizer_image_token("a <image>\nb", FakeTok())
     assert ids.count(-200) == 1 and ids[ids.index(-200) - 1] == 1 and ids[-1] == 1
