@@ -194,12 +194,15 @@ void vqa_destroy(vqa_handle* h);
  *   offsets / heights / widths   HOST arrays [n_images]
  *   pad_to_square  1 = image_aspect_ratio 'pad' (centre on a max(h, w) square of `background`), 0 = plain resize + centre crop
  *   out        DEVICE [n_images, 3, out_size, out_size], out_dtype VQA_DTYPE_F32 or VQA_DTYPE_BF16
- *   workspace  DEVICE, >= vqa_clip_preprocess_workspace_bytes(...) (0 = bad arguments, see vqa_last_error(NULL)) */
+ *   workspace  DEVICE, >= vqa_clip_preprocess_workspace_bytes(...) (0 = bad arguments, see vqa_last_error(NULL))
+ *   host_staging  optional HOST buffer of the same size, ideally pinned: the geometry + tap tables are written there and copied
+ *              with ONE asynchronous cudaMemcpyAsync; the caller must leave it untouched until `stream` has passed this call.
+ *              NULL: the tables are copied from the library's pageable memory (the runtime stages that copy synchronously). */
 size_t vqa_clip_preprocess_workspace_bytes(const int32_t* heights, const int32_t* widths, int32_t n_images, int32_t out_size,
                                            int32_t pad_to_square);
 int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
                         int32_t out_size, int32_t pad_to_square, const uint8_t* background, const float* mean, const float* stdv,
-                        void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+                        void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* host_staging, void* stream);
 
 /* Qwen2.5-VL still-image pre-processing on the device: smart_resize (qwen_vl_utils / image_processing_qwen2_vl.py:62-87) + PIL-exact
  * bicubic resize + /255 + normalise + frame duplication + 14x14 patch rows in 2x2 merge-block order
@@ -209,7 +212,8 @@ int vqa_qwen_preprocess_plan(const int32_t* heights, const int32_t* widths, int3
                              int64_t min_pixels, int64_t max_pixels, int32_t* grid_hw, int64_t* total_patches, size_t* workspace_bytes);
 int vqa_qwen_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
                         int32_t patch, int32_t temporal_patch, int32_t merge, int64_t min_pixels, int64_t max_pixels, const float* mean,
-                        const float* stdv, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+                        const float* stdv, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* host_staging,
+                        void* stream);
 
 /* Host-only helper (no GPU needed): the 22-bit fixed-point bicubic tap table of one resize axis (in_size -> out_size, output
  * pixels [first, first + count)), exactly as vqa_clip_preprocess builds it after Pillow's precompute_coeffs /

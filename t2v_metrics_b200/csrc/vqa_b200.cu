@@ -982,13 +982,23 @@ extern "C" size_t vqa_clip_preprocess_workspace_bytes(const int32_t* heights, co
 
 template <int LAYOUT>
 static int pre_launch(const PrePlan& plan, const void* src, int n_images, const uint8_t* background, const float* mean, const float* stdv,
-                      PrePatchGeom geom, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                      PrePatchGeom geom, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, void* host_staging,
+                      cudaStream_t st) {
     if (workspace_bytes < plan.bytes()) return fail(nullptr, VQA_ERR_WORKSPACE, "pre-processing workspace too small");
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    // pageable host -> device: the runtime stages the bytes before returning, so the plan may die with the caller's frame
-    cudaError_t e = cudaMemcpyAsync(ws, plan.images.data(), plan.images.size() * sizeof(PreImage), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ws + plan.images_bytes(), plan.tables.data(), plan.tables.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaError_t e;
+    if (host_staging) {
+        // caller-owned (pinned) staging: one truly asynchronous copy; the caller keeps the buffer untouched until the stream passes it
+        uint8_t* hs = static_cast<uint8_t*>(host_staging);
+        memcpy(hs, plan.images.data(), plan.images.size() * sizeof(PreImage));
+        memcpy(hs + plan.images_bytes(), plan.tables.data(), plan.tables.size() * sizeof(int));
+        e = cudaMemcpyAsync(ws, hs, plan.bytes(), cudaMemcpyHostToDevice, st);
+    } else {
+        // pageable host -> device: the runtime stages the bytes before returning, so the plan may die with the caller's frame
+        e = cudaMemcpyAsync(ws, plan.images.data(), plan.images.size() * sizeof(PreImage), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ws + plan.images_bytes(), plan.tables.data(), plan.tables.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    }
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("pre-processing table upload: ") + cudaGetErrorString(e));
     const PreImage* d_images = reinterpret_cast<const PreImage*>(ws);
     const int* d_tables = reinterpret_cast<const int*>(ws + plan.images_bytes());
@@ -1014,7 +1024,7 @@ static int pre_launch(const PrePlan& plan, const void* src, int n_images, const 
 extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
                                    int32_t n_images, int32_t out_size, int32_t pad_to_square, const uint8_t* background,
                                    const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   size_t workspace_bytes, void* host_staging, void* stream) {
     if (!src || !offsets || !heights || !widths || !background || !mean || !stdv || !out || !workspace)
         return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
     if (n_images <= 0 || out_size <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad size");
@@ -1022,7 +1032,7 @@ extern "C" int vqa_clip_preprocess(const void* src, const int64_t* offsets, cons
     PrePlan plan;
     if (!pre_plan(heights, widths, offsets, n_images, out_size, pad_to_square != 0, plan)) return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
     return pre_launch<PRE_CHW>(plan, src, n_images, background, mean, stdv, PrePatchGeom{1, 1, 1}, out, out_dtype, workspace, workspace_bytes,
-                               reinterpret_cast<cudaStream_t>(stream));
+                               host_staging, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vqa_qwen_preprocess_plan(const int32_t* heights, const int32_t* widths, int32_t n_images, int32_t patch, int32_t merge,
@@ -1043,7 +1053,7 @@ extern "C" int vqa_qwen_preprocess_plan(const int32_t* heights, const int32_t* w
 extern "C" int vqa_qwen_preprocess(const void* src, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int32_t n_images,
                                    int32_t patch, int32_t temporal_patch, int32_t merge, int64_t min_pixels, int64_t max_pixels,
                                    const float* mean, const float* stdv, void* out, int32_t out_dtype, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   size_t workspace_bytes, void* host_staging, void* stream) {
     if (!src || !offsets || !heights || !widths || !mean || !stdv || !out || !workspace) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
     if (n_images <= 0 || patch <= 0 || merge <= 0 || temporal_patch <= 0 || min_pixels <= 0 || max_pixels < min_pixels)
         return fail(nullptr, VQA_ERR_INVALID_ARG, "bad argument");
@@ -1053,7 +1063,7 @@ extern "C" int vqa_qwen_preprocess(const void* src, const int64_t* offsets, cons
         return fail(nullptr, VQA_ERR_INVALID_ARG, plan.error);
     const uint8_t no_bg[3] = {0, 0, 0};
     return pre_launch<PRE_QWEN_PATCHES>(plan, src, n_images, no_bg, mean, stdv, PrePatchGeom{patch, merge, temporal_patch}, out, out_dtype,
-                                        workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+                                        workspace, workspace_bytes, host_staging, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Host-only: the fixed-point tap table of one resize axis, exactly as vqa_clip_preprocess builds it (for CPU tests of the host logic).

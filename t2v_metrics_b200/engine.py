@@ -279,6 +279,39 @@ class ops:
 
 
 # ------------------------------------------------------------------------------------------------ image pre-processing
+class _PinnedRing:
+    """A few pinned host buffers handed to the library as `host_staging`, each guarded by a CUDA event recorded after the call that
+    used it, so a buffer is never rewritten before the stream has consumed it (keeps the pre-processing call fully asynchronous)."""
+
+    def __init__(self, slots: int = 4):
+        self.bufs = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def acquire(self, nbytes: int) -> torch.Tensor:
+        self.i = (self.i + 1) % len(self.bufs)
+        if self.events[self.i] is not None:
+            self.events[self.i].synchronize()
+        if self.bufs[self.i] is None or self.bufs[self.i].numel() < nbytes:
+            self.bufs[self.i] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, pin_memory=True)
+        return self.bufs[self.i]
+
+    def release(self, device):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[self.i] = ev
+
+
+_staging_rings: Dict[int, _PinnedRing] = {}
+
+
+def _staging(device: torch.device) -> _PinnedRing:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _staging_rings:
+        _staging_rings[idx] = _PinnedRing()
+    return _staging_rings[idx]
+
+
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
@@ -319,9 +352,12 @@ def clip_preprocess_u8(images: Sequence[torch.Tensor], out_size: int, device, pa
         out = torch.empty(n, 3, out_size, out_size, dtype=out_dtype, device=dev)
     assert out.is_cuda and out.is_contiguous() and out.shape == (n, 3, out_size, out_size) and out.dtype in (torch.float32, torch.bfloat16)
     bg = background if background is not None else tuple(int(x * 255) for x in mean)
+    ring = _staging(dev)
+    hs = ring.acquire(need)
     rc = lib.vqa_clip_preprocess(_ptr(src), O, H, W, n, out_size, 1 if pad else 0, (C.c_uint8 * 3)(*bg), (C.c_float * 3)(*mean),
                                  (C.c_float * 3)(*std), _ptr(out), _lib.VQA_DTYPE_F32 if out.dtype == torch.float32 else _lib.VQA_DTYPE_BF16,
-                                 _ptr(wsb), need, _stream_ptr(dev))
+                                 _ptr(wsb), need, hs.data_ptr(), _stream_ptr(dev))
+    ring.release(dev)
     _check(rc, None, "vqa_clip_preprocess")
     # src / wsb stay referenced by the caching allocator's stream ordering: both were allocated on the current stream
     return out
@@ -369,10 +405,13 @@ def qwen_preprocess_u8(images: Sequence[torch.Tensor], device, patch: int = 14, 
         src = stage.to(dev, non_blocking=True)
     out = torch.empty(rows, 3 * temporal_patch * patch * patch, dtype=out_dtype, device=dev)
     wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+    ring = _staging(dev)
+    stage_buf = ring.acquire(wsb.numel())
     rc = lib.vqa_qwen_preprocess(_ptr(src), (C.c_int64 * n)(*offs), (C.c_int32 * n)(*hs), (C.c_int32 * n)(*ws), n, patch, temporal_patch,
                                  merge, min_pixels, max_pixels, (C.c_float * 3)(*mean), (C.c_float * 3)(*std), _ptr(out),
                                  _lib.VQA_DTYPE_F32 if out_dtype == torch.float32 else _lib.VQA_DTYPE_BF16, _ptr(wsb), wsb.numel(),
-                                 _stream_ptr(dev))
+                                 stage_buf.data_ptr(), _stream_ptr(dev))
+    ring.release(dev)
     _check(rc, None, "vqa_qwen_preprocess")
     return out, grids
 
