@@ -107,10 +107,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 // CHAINS = 1: warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax; 256 TMEM columns, two CTAs per SM.
 // CHAINS = 2 ("ping-pong"): warp 0 TMA, warps 1-2 MMA issuers, warps 3-6 / 7-10 two softmax chains working on query tiles 2r and
 //   2r+1 against the SAME K/V tiles (loaded once, released when both chains' MMAs retired); 512 TMEM columns, one CTA per SM.
-//   Measured on B200 (profiles/r01_summary.md): per key tile the softmax warps spend ~1000 cycles each on the TMEM read of S
-//   (64 B/clk per SM) and on ex2 (16/clk per SM); two independent CTAs per SM drift into lock-step and queue on the same unit.
-//   Here a token (named barriers) lets only ONE chain at a time be in the "read S + max" phase, so the other one is necessarily in
-//   its "ex2 + store P" phase: the TMEM port and the MUFU pipe work concurrently by construction.
+//   A token (named barriers) lets only ONE chain at a time be in the "read S + max" phase, so the other one is necessarily in its
+//   "ex2 + store P" phase: the TMEM read port and the MUFU pipe cannot be asked for by both chains at once. Measured gain over two
+//   independent CTAs per SM: 2.5 % (profiles/r01_summary.md), so this variant is opt-in (VQA_ATTN_CHAINS=2).
 template <bool HAS_BIAS, int CHAINS>
 __global__ void __launch_bounds__(32 * (1 + 5 * CHAINS), CHAINS == 1 ? 2 : 1)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
@@ -504,10 +503,11 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.bias_const_dist = (bias_table && bias_const_dist > 0 && bias_const_dist <= S - 1) ? bias_const_dist : 0;
-    // VQA_ATTN_CHAINS=1 selects the two-CTAs-per-SM kernel (A/B); default: the two-chain ping-pong kernel when there is more than one
-    // query tile to pair up
+    // Default: one chain per CTA, two CTAs per SM. VQA_ATTN_CHAINS=2 selects the two-chain ping-pong variant (one CTA per SM): measured
+    // on B200 at B=64, H=64, S=672 it is 1.470 ms against 1.507 ms, i.e. separating the two chains' TMEM-read and ex2 phases with a
+    // token buys 2.5 % -- not enough to give up the second resident CTA (which hides CTA set-up and tails); kept for A/B runs.
     static const int env_chains = [] { const char* v = getenv("VQA_ATTN_CHAINS"); return (v && v[0]) ? atoi(v) : 0; }();
-    const bool two = env_chains ? env_chains == 2 : S > AT_BQ;
+    const bool two = env_chains == 2 && S > AT_BQ;
     return two ? launch_attn_tc_t<2>(tm, p, B, H, bias_table != nullptr, stream) : launch_attn_tc_t<1>(tm, p, B, H, bias_table != nullptr, stream);
 }
 
