@@ -4,7 +4,7 @@
 //    per-head [2S-1] table, no 1/sqrt(d) scale, key-padding mask (transformers/models/t5/modeling_t5.py:308-334),
 //    or (b) CLIP's plain scaled attention (transformers/models/clip/modeling_clip.py:261-336). Scores never
 //    touch HBM (the reference materialises [B,H,S,S] fp32). Online softmax in fp32.
-//  * t5_decoder_self_attn_kernel / t5_cross_attn_kernel: the T<=8 decoder rows (causal self-attention with
+//  * t5_decoder_self_attn_kernel / t5_cross_attn_kernel: the decoder rows (causal self-attention with
 //    unidirectional buckets; cross-attention with zero bias + encoder padding mask, modeling_t5.py:312-325).
 #pragma once
 #include "ptx.cuh"
@@ -240,43 +240,44 @@ inline size_t flash_smem_bytes(int S, bool has_bias) {
     return (size_t)5 * FA_BQ * FA_LD * 2 + (has_bias ? (size_t)(2 * S - 1) * 4 : 0) + 16;
 }
 
-// Decoder self-attention over T (<= 8) target positions: causal, unidirectional relative buckets, no scale.
-// qkv: [B*T, 3*H*64] packed. One warp per (b, h, query t); lanes cover d in pairs.
+// Decoder self-attention over the T target positions of each pair (T = 2 for the "Yes" answer, tens of tokens in VisualGPTScore
+// mode where the caption itself is the target): causal, unidirectional relative buckets, no scale (modeling_t5.py:253-344).
+// qkv: [B*T, 3*H*64] packed. One warp per (b, h, query t); lanes cover d in pairs; the <= T scores of the row live in shared
+// memory (dynamic: warps per block * T floats).
 __global__ void t5_decoder_self_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                             const __nv_bfloat16* __restrict__ rel_emb,  // [num_buckets, H]
                                             const int* __restrict__ bucket_lut,         // [2*max_dist+1] unidirectional
                                             int max_dist, int B, int T, int H, int round_scores) {
+    extern __shared__ float dec_sc[];
     const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (widx >= B * H * T) return;
     const int lane = threadIdx.x & 31;
+    float* sc = dec_sc + (size_t)(threadIdx.x >> 5) * T;
     const int tq = widx % T, h = (widx / T) % H, b = widx / (T * H);
     const int ld = 3 * H * 64;
     const __nv_bfloat16* qp = qkv + ((size_t)b * T + tq) * ld + h * 64;
     const float2 qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + 2 * lane));
-    float sc[8];
     float mx = -INFINITY;
-    for (int tk = 0; tk < T && tk < 8; ++tk) {
-        float v = -INFINITY;
-        if (tk <= tq) {
-            const __nv_bfloat16* kp = qkv + ((size_t)b * T + tk) * ld + H * 64 + h * 64;
-            const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + 2 * lane));
-            v = warp_sum(qv.x * kv.x + qv.y * kv.y);
-            if (round_scores) v = bf16_round(v);
-            int rel = tk - tq;
-            rel = min(max(rel, -max_dist), max_dist);
-            v += __bfloat162float(rel_emb[bucket_lut[rel + max_dist] * H + h]);
-            if (round_scores) v = bf16_round(v);
-        }
-        sc[tk] = v;
+    for (int tk = 0; tk <= tq; ++tk) {
+        const __nv_bfloat16* kp = qkv + ((size_t)b * T + tk) * ld + H * 64 + h * 64;
+        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + 2 * lane));
+        float v = warp_sum(qv.x * kv.x + qv.y * kv.y);
+        if (round_scores) v = bf16_round(v);
+        int rel = tk - tq;
+        rel = min(max(rel, -max_dist), max_dist);
+        v += __bfloat162float(rel_emb[bucket_lut[rel + max_dist] * H + h]);
+        if (round_scores) v = bf16_round(v);
+        if (lane == 0) sc[tk] = v;
         mx = fmaxf(mx, v);
     }
+    __syncwarp();
     float denom = 0.f;
-    for (int tk = 0; tk <= tq && tk < 8; ++tk) { sc[tk] = __expf(sc[tk] - mx); denom += sc[tk]; }
+    for (int tk = 0; tk <= tq; ++tk) denom += __expf(sc[tk] - mx);
     float ox = 0.f, oy = 0.f;
-    for (int tk = 0; tk <= tq && tk < 8; ++tk) {
+    for (int tk = 0; tk <= tq; ++tk) {
         const __nv_bfloat16* vp = qkv + ((size_t)b * T + tk) * ld + 2 * H * 64 + h * 64;
         const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp + 2 * lane));
-        const float pw = bf16_round(sc[tk] / denom);   // attn_weights are cast back to bf16 before the PV matmul
+        const float pw = bf16_round(__expf(sc[tk] - mx) / denom);   // attn_weights are cast back to bf16 before the PV matmul
         ox += pw * vv.x;
         oy += pw * vv.y;
     }

@@ -559,7 +559,9 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     if (!pixels || !input_ids || !text_lens || !labels || !out_scores || !workspace)
         return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
     if (B <= 0 || L <= 0 || T <= 0 || n_images <= 0) return fail(h, VQA_ERR_INVALID_ARG, "non-positive size");
-    if (T > 8) return fail(h, VQA_ERR_UNSUPPORTED, "label_len > 8 not supported by the decoder kernels");
+    if (T > 256) return fail(h, VQA_ERR_UNSUPPORTED, "label_len > 256 not supported by the decoder kernels");
+    if (T > 8 && h->cfg.cross_attention_mode != 0)
+        return fail(h, VQA_ERR_UNSUPPORTED, "label_len > 8 needs the absorbed cross-attention (cross_attention_mode = 0)");
     if (!image_index && n_images != B) return fail(h, VQA_ERR_INVALID_ARG, "image_index == NULL requires n_images == batch");
     if (pixel_dtype != VQA_DTYPE_F32 && pixel_dtype != VQA_DTYPE_BF16)
         return fail(h, VQA_ERR_INVALID_ARG, "pixel_dtype must be F32 or BF16");
@@ -708,7 +710,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * T * T * 64, st);
             ++*lc;
-            t5_decoder_self_attn_kernel<<<(B * H * T + 3) / 4, 128, 0, st>>>(P_(w.dqkv), P_(w.dattn), h->dec_rel, h->lut_unidir,
+            t5_decoder_self_attn_kernel<<<(B * H * T + 3) / 4, 128, 4 * T * sizeof(float), st>>>(P_(w.dqkv), P_(w.dattn), h->dec_rel, h->lut_unidir,
                                                                              c.rel_max_distance, B, T, H, rnd);
             TRY(cuda_ok(cudaSuccess, "decoder self attention"));
         }

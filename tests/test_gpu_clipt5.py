@@ -77,6 +77,31 @@ def test_engine_matches_oracle_and_golden(name, golden_dir, dev):
     assert bool(((s >= 0) & (s <= 1)).all())
 
 
+@pytest.mark.parametrize("T", [5, 12, 33])
+def test_long_answers_visualgptscore_mode(T, golden_dir, dev):
+    """VisualGPTScore mode of the v3.0 wrapper (question_template="", answer_template="{}", V_3.0_README.md:227-233): the caption
+    itself is the target, so the decoder runs T = caption length + 1 rows and the score is exp(mean log p) over them. Ragged
+    targets are padded with -100 (ignored by CrossEntropyLoss). Engine vs the oracle (fp32 and bf16 modes) on the tiny config."""
+    blob, cfg, sd = load_case("tiny", golden_dir)
+    g = torch.Generator().manual_seed(T)
+    inp = orc.make_synthetic_inputs(cfg, 3, 14, seed=7, ragged=True)
+    labels = torch.randint(2, cfg.vocab - 28, (3, T), generator=g)
+    labels[:, -1] = 1
+    labels[1, T - 2:] = -100                      # a shorter target in the same batch
+    labels[1, T - 3] = 1
+    inp["labels"] = labels
+    o32 = orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], labels, None, mode="fp32", return_all=True)
+    o16 = orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], labels, None, mode="bf16", return_all=True)
+    eng = make_engine(cfg, sd, dev)
+    s, lp = run_engine(eng, inp, dev)
+    gap = float((torch.log(o16["scores"]) - torch.log(o32["scores"])).abs().max())
+    err = float((torch.log(s) - torch.log(o32["scores"])).abs().max())
+    print(f"\n[T={T}] engine {s.tolist()} oracle fp32 {o32['scores'].tolist()} |dlog| {err:.3e} (oracle bf16-vs-fp32 {gap:.3e})")
+    assert err <= 2.0 * gap + 2e-2
+    valid = labels >= 0
+    assert float((lp[valid] - o16["logprobs"][valid]).abs().max()) <= 5e-2
+
+
 def test_engine_vs_transformers_on_the_same_gpu(golden_dir, dev):
     """The reference forward (HF CLIPVisionModel + T5ForConditionalGeneration, bf16 weights, autocast) on cuda vs the engine."""
     import hf_reference as hf

@@ -15,10 +15,13 @@ echo "== launch list" >> $L
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_bf16|attn_tc|attn_kernel|rmsnorm|layernorm|patchify|clip_embed|splice|decoder_embed|bias_table|lse_finalize|transpose_bsd|cross_softmax|t5_decoder|t5_cross" \
    -s 702 -c 702 --csv --log-file gpurun_out/r01_launches.csv python bench.py --ncu >> $L 2>&1; echo "launch list rc=$?" >> $L
 echo "== ncu full" >> $L
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:gemm_bf16 -s 560 -c 4 -o gpurun_out/r01_gemm_full python bench.py --ncu >> $L 2>&1; echo "ncu gemm rc=$?" >> $L
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:attn_tc_d64 -s 40 -c 1 -o gpurun_out/r01_attn_full python bench.py --ncu >> $L 2>&1; echo "ncu attn rc=$?" >> $L
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:gemm_bf16 -s 431 -c 1 -o gpurun_out/r01_lmhead_full python bench.py --ncu >> $L 2>&1; echo "ncu lmhead rc=$?" >> $L
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:t5_rmsnorm -s 10 -c 1 -o gpurun_out/r01_rmsnorm_full python bench.py --ncu >> $L 2>&1; echo "ncu rmsnorm rc=$?" >> $L
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:image_preprocess -s 3 -c 1 -o gpurun_out/r01_preprocess_full python tools/gpu_check.py preprocess_perf 64 512 336 >> $L 2>&1; echo "ncu preprocess rc=$?" >> $L
+timeout 400 ncu --set full --clock-control none -k regex:gemm_bf16 -s 560 -c 4 -o gpurun_out/r01_gemm_full python bench.py --ncu >> $L 2>&1; echo "ncu gemm rc=$?" >> $L
+timeout 400 ncu --set full --clock-control none -k regex:attn_tc_d64 -s 40 -c 1 -o gpurun_out/r01_attn_full python bench.py --ncu >> $L 2>&1; echo "ncu attn rc=$?" >> $L
+timeout 400 ncu --set full --clock-control none -k regex:gemm_bf16 -s 431 -c 1 -o gpurun_out/r01_lmhead_full python bench.py --ncu >> $L 2>&1; echo "ncu lmhead rc=$?" >> $L
+timeout 400 ncu --set full --clock-control none -k regex:t5_rmsnorm -s 10 -c 1 -o gpurun_out/r01_rmsnorm_full python bench.py --ncu >> $L 2>&1; echo "ncu rmsnorm rc=$?" >> $L
+timeout 300 ncu --set full --clock-control none -k regex:image_preprocess -s 3 -c 1 -o gpurun_out/r01_preprocess_full python tools/gpu_check.py preprocess_perf 64 512 336 >> $L 2>&1; echo "ncu preprocess rc=$?" >> $L
 ls -la gpurun_out/*.ncu-rep >> $L
+# the reports themselves are too big to travel back (64 MiB cap): keep their key metrics only
+python tools/ncu_summary.py gpurun_out/r01_gemm_full.ncu-rep gpurun_out/r01_attn_full.ncu-rep gpurun_out/r01_lmhead_full.ncu-rep gpurun_out/r01_rmsnorm_full.ncu-rep gpurun_out/r01_preprocess_full.ncu-rep > gpurun_out/r01_ncu_kernels.md 2>> $L
+rm -f gpurun_out/*.ncu-rep
 grep -vE "^==PROF|^==WARN|^$|Warning|warn" $L | cut -c1-1500 | tail -30
