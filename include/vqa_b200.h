@@ -236,11 +236,9 @@ int vqa_op_lmhead_logprob(const void* H, int32_t ldh, const void* W, int32_t ldw
                           const int32_t* labels, float* logprob, float* scratch, void* stream);
 
 /* Bidirectional attention, head_dim 64, packed qkv [B*S, 3*H*64] -> out [B*S, H*64].
- * bias_table: DEVICE float [H, 2S-1] (index key - query + S - 1) or NULL; seq_lens DEVICE int32 [B] or NULL.
- * bias_const_dist: 0, or d > 0 promising bias_table[h][.] is constant for key - query >= d and for key - query <= -d (T5:
- * relative_attention_max_distance) -- tiles that far from the diagonal then skip the per-element bias load. */
+ * bias_table: DEVICE float [H, 2S-1] (index key - query + S - 1) or NULL; seq_lens DEVICE int32 [B] or NULL. */
 int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                         const float* bias_table, float scale, int32_t round_scores, int32_t bias_const_dist, void* stream);
+                         const float* bias_table, float scale, int32_t round_scores, void* stream);
 
 /* T5LayerNorm / nn.LayerNorm on [rows, D] bf16. beta == NULL selects T5 RMS norm. */
 int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,

@@ -93,7 +93,7 @@ def load() -> C.CDLL:
     lib.vqa_op_gemm_bf16.restype = C.c_int
     lib.vqa_op_lmhead_logprob.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.vqa_op_lmhead_logprob.restype = C.c_int
-    lib.vqa_op_attention_d64.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, i32, i32, vp]
+    lib.vqa_op_attention_d64.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, i32, vp]
     lib.vqa_op_attention_d64.restype = C.c_int
     lib.vqa_op_norm.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp]
     lib.vqa_op_norm.restype = C.c_int

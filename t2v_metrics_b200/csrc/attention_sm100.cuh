@@ -25,7 +25,6 @@ struct AttnTcParams {
     int S, H;
     int q_col0, k_col0, v_col0;  // column of head 0 inside the packed [B*S, ld] buffer
     float scale_log2e;        // (softmax scale) * log2(e)
-    int bias_const_dist;      // > 0: bias_table[h][rel] is constant for rel >= d and for rel <= -d (T5: relative_attention_max_distance)
 };
 
 constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
@@ -33,6 +32,9 @@ constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
 
+inline size_t attn_tc_smem_bytes(int S) {
+    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
+}
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -87,41 +89,24 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// named barriers 1 and 2 carry the ping-pong token between the two softmax chains of a CTA (barrier 0 is __syncthreads)
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// One CTA owns one (sample, head) and walks its 128-row query tiles: TMEM allocation, barrier set-up and the bias table are paid once,
-// and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered per chain).
-//
-// CHAINS = 1: warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax; 256 TMEM columns, two CTAs per SM.
-// CHAINS = 2 ("ping-pong"): warp 0 TMA, warps 1-2 MMA issuers, warps 3-6 / 7-10 two softmax chains working on query tiles 2r and
-//   2r+1 against the SAME K/V tiles (loaded once, released when both chains' MMAs retired); 512 TMEM columns, one CTA per SM.
-//   A token (named barriers) lets only ONE chain at a time be in the "read S + max" phase, so the other one is necessarily in its
-//   "ex2 + store P" phase: the TMEM read port and the MUFU pipe cannot be asked for by both chains at once. Measured gain over two
-//   independent CTAs per SM: 2.5 % (profiles/r01_summary.md), so this variant is opt-in (VQA_ATTN_CHAINS=2).
-template <bool HAS_BIAS, int CHAINS>
-__global__ void __launch_bounds__(32 * (1 + 5 * CHAINS), CHAINS == 1 ? 2 : 1)
+// One CTA owns one (sample, head) and walks its 128-row query tiles back to back: TMEM allocation, barrier set-up and the
+// bias table are paid once, and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered),
+// so only the very first tile of a CTA sees the full HBM/L2 latency.
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(192, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
-    constexpr int KVS = CHAINS == 1 ? 2 : 3;                 // K/V stages
-    constexpr int FIRST_SM_WARP = 1 + CHAINS;                // first softmax warp
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const size_t row_base = (size_t)b * p.S;
     const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
     const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
-    const int rounds = (nq + CHAINS - 1) / CHAINS;
 
     // rows past the last valid query tile: deterministic zeros
     for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
@@ -132,46 +117,45 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                        // [CHAINS][2]
-    uint8_t* sK = smem + 2 * CHAINS * AT_TILE_BYTES;           // [KVS]
-    uint8_t* sV = sK + KVS * AT_TILE_BYTES;                    // [KVS]
-    constexpr int NTILES = 2 * CHAINS + 2 * KVS;
-    float* sBias = reinterpret_cast<float*>(smem + NTILES * AT_TILE_BYTES);   // entry i <-> rel = i - AT_BIAS_PAD, rel = key - query + S - 1
-    const uint32_t sBias_u32 = smem_u32(sBias);
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
+    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
+    float* sBias = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES);   // entry i <-> rel = i - AT_BIAS_PAD, rel = key - query + S - 1
     const int bias_n = 2 * p.S - 1 + 2 * AT_BIAS_PAD;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NTILES * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
-    uint64_t* kv_full = bars;                  // [KVS]
-    uint64_t* kv_empty = bars + KVS;           // [KVS]   one arrival per chain
-    uint64_t* chain_bars = bars + 2 * KVS;     // per chain: q_full[2] q_empty[2] s_full s_empty p_full o_done o_free  (9)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(chain_bars + 9 * CHAINS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
+    uint64_t* q_full = bars;          // [2]
+    uint64_t* q_empty = bars + 2;     // [2]
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
-        for (int i = 0; i < KVS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], CHAINS); }
-        for (int c = 0; c < CHAINS; ++c) {
-            uint64_t* cb = chain_bars + 9 * c;
-            mbar_init(&cb[0], 1); mbar_init(&cb[1], 1); mbar_init(&cb[2], 1); mbar_init(&cb[3], 1);
-            mbar_init(&cb[4], 1);      // s_full
-            mbar_init(&cb[5], 4);      // s_empty
-            mbar_init(&cb[6], 4);      // p_full
-            mbar_init(&cb[7], 1);      // o_done
-            mbar_init(&cb[8], 4);      // o_free
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
         }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        mbar_init(o_free, 4);
         fence_barrier_init();
         // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
-        for (int c = 0; c < CHAINS; ++c) {
-            if (c < nq) {
-                uint64_t* qf = chain_bars + 9 * c;
-                mbar_arrive_expect_tx(&qf[0], AT_TILE_BYTES);
-                tma_load_2d(sQ + (2 * c) * AT_TILE_BYTES, &tmap_qkv, &qf[0], p.q_col0 + h * AT_D, (int)(row_base + c * AT_BQ));
-            }
-        }
+        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
         mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
         tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
         tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
     }
     if (warp == 1) {
-        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS * CHAINS);
+        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
         tmem_relinquish<1>();
     }
     if (HAS_BIAS) {
@@ -197,64 +181,56 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const int total_kv = rounds * nkt;            // K/V tile loads of this CTA; tile index G = r * nkt + j
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int r = 0; r < rounds; ++r) {
-                for (int c = 0; c < CHAINS; ++c) {
-                    const int qi = r * CHAINS + c;
-                    if (r == 0 || qi >= nq) continue;          // (round 0 was issued during set-up)
-                    uint64_t* cb = chain_bars + 9 * c;
-                    const int qb = r & 1;
-                    mbar_wait(&cb[2 + qb], (((uint32_t)r >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&cb[qb], AT_TILE_BYTES);
-                    tma_load_2d(sQ + (2 * c + qb) * AT_TILE_BYTES, &tmap_qkv, &cb[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                if (qi > 0) {   // (tile 0 was issued during set-up)
+                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
                 }
                 for (int j = 0; j < nkt; ++j) {
-                    const int G = r * nkt + j;
-                    if (G == 0) continue;
-                    const int st = G % KVS;
-                    mbar_wait(&kv_empty[st], (((uint32_t)(G / KVS)) & 1u) ^ 1u);
+                    const int g = qi * nkt + j;
+                    if (g == 0) continue;
+                    const int st = g & 1;
+                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
                     tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
                     tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
                 }
             }
         }
-    } else if (warp < (uint32_t)FIRST_SM_WARP) {
-        // ===================== MMA issuer of chain `ch` =====================
-        const int ch = (int)warp - 1;
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint64_t* cb = chain_bars + 9 * ch;
-            uint64_t *s_full = &cb[4], *s_empty = &cb[5], *p_full = &cb[6], *o_done = &cb[7], *o_free = &cb[8];
-            const uint32_t tmem_S = tmem_base + ch * AT_TMEM_COLS, tmem_O = tmem_S + 128, tmem_P = tmem_S + 192;
             constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
             constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
-            const int my_rounds = (nq - ch + CHAINS - 1) / CHAINS;                    // rounds in which this chain has a query tile
-            const int my_tiles = my_rounds * nkt;
-            auto issue_pv = [&](int g) {          // g = r * nkt + j, also the K/V tile index G while this chain is active
-                const int j = g % nkt, r = g / nkt;
+            auto issue_pv = [&](int g) {
+                const int j = g % nkt, qi = g / nkt;
                 mbar_wait(p_full, (uint32_t)g & 1u);
-                if (j == 0 && r > 0) mbar_wait(o_free, (uint32_t)(r - 1) & 1u);       // previous query tile's O has been read out
+                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
                 tcgen05_fence_after();
-                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g % KVS) * AT_TILE_BYTES), AT_TILE_BYTES);
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < AT_BK / 16; ++ks)
                     umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
                                 (j > 0 || ks > 0) ? 1u : 0u);
-                umma_commit<1>(&kv_empty[g % KVS]);
+                umma_commit<1>(&kv_empty[g & 1]);
                 umma_commit<1>(o_done);
             };
-            for (int r = 0; r < my_rounds; ++r) {
-                const int qb = r & 1;
-                mbar_wait(&cb[qb], ((uint32_t)r >> 1) & 1u);
-                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + (2 * ch + qb) * AT_TILE_BYTES));
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
+                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
                 for (int j = 0; j < nkt; ++j) {
-                    const int g = r * nkt + j;
-                    const int st = g % KVS;
-                    mbar_wait(&kv_full[st], ((uint32_t)(g / KVS)) & 1u);
+                    const int g = qi * nkt + j;
+                    const int st = g & 1;
+                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
                     mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
                     tcgen05_fence_after();
                     const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
@@ -262,52 +238,28 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                     for (int k = 0; k < AT_D / 16; ++k)
                         umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
                     umma_commit<1>(s_full);
-                    if (j == nkt - 1) umma_commit<1>(&cb[2 + qb]);   // Q buffer reusable once this tile's QK^T retired
+                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
                     if (g > 0) issue_pv(g - 1);
                 }
             }
-            if (my_tiles > 0) issue_pv(my_tiles - 1);
-            // rounds without a query tile for this chain (odd tile count): still release the shared K/V stages
-            for (int G = my_tiles; G < total_kv; ++G) {
-                mbar_wait(&kv_full[G % KVS], ((uint32_t)(G / KVS)) & 1u);
-                umma_commit<1>(&kv_empty[G % KVS]);
-            }
+            issue_pv(total_tiles - 1);
         }
     } else {
         // ===================== softmax / correction / epilogue: one thread per query row =====================
-        const int ch = ((int)warp - FIRST_SM_WARP) >> 2;
-        const uint32_t quad = warp & 3u;                       // TMEM lane quarter this warp may access
+        const uint32_t quad = warp & 3u;
         const int row = quad * 32 + lane;
         const uint32_t lane_off = (quad * 32u) << 16;
-        uint64_t* cb = chain_bars + 9 * ch;
-        uint64_t *s_full = &cb[4], *s_empty = &cb[5], *p_full = &cb[6], *o_done = &cb[7], *o_free = &cb[8];
-        const uint32_t tmem_S = tmem_base + ch * AT_TMEM_COLS, tmem_O = tmem_S + 128, tmem_P = tmem_S + 192;
-        // ping-pong token (CHAINS == 2): chain 0 enters its read phase first; each chain hands the token over when its read phase ends
-        auto token_acquire = [&](int G) {
-            if (CHAINS == 2 && !(ch == 0 && G == 0)) named_bar_sync(1 + ch, 256);
-        };
-        auto token_release = [&]() {
-            if (CHAINS == 2) named_bar_arrive(2 - ch, 256);
-        };
         int g = 0;
-        for (int r = 0; r < rounds; ++r) {
-            const int qi = r * CHAINS + ch;
+        for (int qi = 0; qi < nq; ++qi) {
             const int q0 = qi * AT_BQ;
             const int qrow = q0 + row;
             __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
-            if (qi >= nq) {
-                // no query tile for this chain in the last round: only keep the token moving
-                for (int j = 0; j < nkt; ++j) { token_acquire(r * nkt + j); token_release(); }
-                continue;
-            }
             if (q0 + (int)quad * 32 >= len) {
                 // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
                 for (int j = 0; j < nkt; ++j, ++g) {
-                    token_acquire(r * nkt + j);
                     mbar_wait(s_full, (uint32_t)g & 1u);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_empty);
-                    token_release();
                     if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
                     __syncwarp();
                     if (lane == 0) mbar_arrive(p_full);
@@ -326,39 +278,35 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
             for (int j = 0; j < nkt; ++j, ++g) {
                 const int k0 = j * AT_BK;
                 const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
-                token_acquire(r * nkt + j);
                 mbar_wait(s_full, (uint32_t)g & 1u);
                 tcgen05_fence_after();
-                // all chunks of the tile are requested before the single wait: one TMEM round trip per tile, not four
                 float t[4][32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < nch) tmem_ld_32x32b_x32_f32(tmem_S + lane_off + c * 32, t[c]);
-                tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
+                    }
+                }
                 // S is in registers: hand the TMEM columns back so the next QK^T can start
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);
 
-                // Tiles whose keys are all at least `bias_const_dist` away from every query row of this warp see ONE bias value
-                // (T5 buckets saturate at max_distance), and without a bias table that value is 0: the scores then stay raw in
-                // registers, the max is taken on the raw scores (scale > 0) and scale, bias and -max fold into the single FFMA that
-                // feeds ex2. Only the tiles around the diagonal pay the per-element bias load and the extra add.
-                const int wq_lo = q0 + (int)quad * 32, wq_hi = wq_lo + 31;
-                bool uniform_bias = !HAS_BIAS;
-                float cbias = 0.f;
-                if (HAS_BIAS && p.bias_const_dist > 0) {
-                    if (k0 - wq_hi >= p.bias_const_dist) { uniform_bias = true; cbias = sBias[AT_BIAS_PAD + p.S - 1 + p.bias_const_dist]; }
-                    else if (wq_lo - (k0 + AT_BK - 1) >= p.bias_const_dist) { uniform_bias = true; cbias = sBias[AT_BIAS_PAD + p.S - 1 - p.bias_const_dist]; }
-                }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (c < nch) {
-                        if (!uniform_bias) {
-                            const uint32_t bp = sBias_u32 + (uint32_t)(bias_base + k0 + c * 32) * 4u;
+                        if (HAS_BIAS) {
+                            const float* bp = sBias + bias_base + k0 + c * 32;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, ld_shared_f32(bp + i * 4));
+                            for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
                         }
                         if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
 #pragma unroll
@@ -372,9 +320,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                         }
                     }
                 }
-                float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if (uniform_bias) tile_max = fmaf(tile_max, p.scale_log2e, cbias);   // back to the log2 domain (scale > 0)
-                token_release();                                // the scores are in registers: the other chain may read its S now
+                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
                 float corr = 1.f;
                 bool rescale = false;
@@ -406,17 +352,14 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 }
                 // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
                 float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-                // exponent = t * ea + eb: (1, -max) for biased scores already in the log2 domain, (scale, bias - max) for raw ones
-                const float ea = uniform_bias ? p.scale_log2e : 1.f;
-                const float eb = (uniform_bias ? cbias : 0.f) - m_run;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
                     if (c < nch) {
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            const float e0 = fast_exp2(fmaf(t[c][2 * i], ea, eb)),     e1 = fast_exp2(fmaf(t[c][2 * i + 1], ea, eb));
-                            const float e2 = fast_exp2(fmaf(t[c][2 * i + 2], ea, eb)), e3 = fast_exp2(fmaf(t[c][2 * i + 3], ea, eb));
+                            const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                            const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
                             ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
                             pk[i] = pack_bf16x2(e0, e1);
                             pk[i + 1] = pack_bf16x2(e2, e3);
@@ -442,7 +385,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 uint32_t ov[32];
                 tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
                 tmem_ld_wait();
-                if (c == 1) {   // O is in registers: the next query tile's first PV may overwrite it
+                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_free);
@@ -459,56 +402,37 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
                 }
             }
         }
-        if (CHAINS == 2 && ch == 0) named_bar_sync(1, 256);    // consume chain 1's last hand-over: every arrive has its sync
         tcgen05_fence_before();
     }
 
     __syncthreads();
     tcgen05_fence_after();
-    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS * CHAINS);
-}
-
-template <int CHAINS>
-inline size_t attn_tc_smem_bytes_t(int S) {
-    const int tiles = 2 * CHAINS + 2 * (CHAINS == 1 ? 2 : 3);
-    return 1024 + (size_t)tiles * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 8 * (2 * 3 + 9 * CHAINS) + 16;
-}
-
-template <int CHAINS>
-inline cudaError_t launch_attn_tc_t(const CUtensorMap& tm, const AttnTcParams& p, int B, int H, bool has_bias, cudaStream_t stream) {
-    const size_t smem = attn_tc_smem_bytes_t<CHAINS>(p.S);
-    static size_t max_set[2] = {0, 0};
-    const int which = has_bias ? 1 : 0;
-    if (smem > max_set[which]) {
-        cudaError_t e = has_bias ? cudaFuncSetAttribute(attn_tc_d64_kernel<true, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                 : cudaFuncSetAttribute(attn_tc_d64_kernel<false, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        max_set[which] = smem;
-    }
-    dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
-    const int threads = 32 * (1 + 5 * CHAINS);   // TMA warp + CHAINS MMA warps + 4 * CHAINS softmax warps
-    if (has_bias) attn_tc_d64_kernel<true, CHAINS><<<grid, threads, smem, stream>>>(tm, p);
-    else          attn_tc_d64_kernel<false, CHAINS><<<grid, threads, smem, stream>>>(tm, p);
-    return cudaGetLastError();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
 }
 
 // qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
                                   int B, int S, int H, const int* seq_lens, const float* bias_table, float scale,
-                                  cudaStream_t stream, int bias_const_dist = 0) {
+                                  cudaStream_t stream) {
     CUtensorMap tm;
     if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
     AttnTcParams p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
-    p.bias_const_dist = (bias_table && bias_const_dist > 0 && bias_const_dist <= S - 1) ? bias_const_dist : 0;
-    // Default: one chain per CTA, two CTAs per SM. VQA_ATTN_CHAINS=2 selects the two-chain ping-pong variant (one CTA per SM): measured
-    // on B200 at B=64, H=64, S=672 it is 1.470 ms against 1.507 ms, i.e. separating the two chains' TMEM-read and ex2 phases with a
-    // token buys 2.5 % -- not enough to give up the second resident CTA (which hides CTA set-up and tails); kept for A/B runs.
-    static const int env_chains = [] { const char* v = getenv("VQA_ATTN_CHAINS"); return (v && v[0]) ? atoi(v) : 0; }();
-    const bool two = env_chains == 2 && S > AT_BQ;
-    return two ? launch_attn_tc_t<2>(tm, p, B, H, bias_table != nullptr, stream) : launch_attn_tc_t<1>(tm, p, B, H, bias_table != nullptr, stream);
+    const size_t smem = attn_tc_smem_bytes(S);
+    static size_t max_set[2] = {0, 0};
+    const int which = bias_table ? 1 : 0;
+    if (smem > max_set[which]) {
+        cudaError_t e = bias_table ? cudaFuncSetAttribute(attn_tc_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(attn_tc_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[which] = smem;
+    }
+    dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
+    if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
+    else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -653,12 +577,15 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
             const int k0 = j * 128;
             mbar_wait(s_full, (uint32_t)j & 1u);
             tcgen05_fence_after();
-            // raw scores stay in registers (one TMEM round trip per tile); the max is taken on them (scale > 0) and the scale and
-            // -max fold into the single FFMA that feeds ex2
             float t[4][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32_f32(tmem_S + lane_off + c * 32, t[c]);
-            tmem_ld_wait();
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]) * p.scale_log2e;
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty);
@@ -680,7 +607,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                     mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
                 }
             }
-            float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2e;   // log2 domain
+            float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             if (tile_max == -INFINITY) tile_max = -1e30f;   // a padded query row may see no key at all in this tile
             float corr = 1.f;
             bool rescale = false;
@@ -711,14 +638,13 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                 }
             }
             float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-            const float ea = p.scale_log2e, eb = -m_run;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float e0 = fast_exp2(fmaf(t[c][2 * i], ea, eb)),     e1 = fast_exp2(fmaf(t[c][2 * i + 1], ea, eb));
-                    const float e2 = fast_exp2(fmaf(t[c][2 * i + 2], ea, eb)), e3 = fast_exp2(fmaf(t[c][2 * i + 3], ea, eb));
+                    const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
+                    const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
                     ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
                     pk[i] = pack_bf16x2(e0, e1);
                     pk[i + 1] = pack_bf16x2(e2, e3);

@@ -271,13 +271,13 @@ static cudaError_t run_layernorm(const bf16* x, const bf16* g, const bf16* b, bf
 }
 static cudaError_t run_flash(const bf16* q, const bf16* k, const bf16* v, int ldqkv, bf16* o, int ldo, int B, int S,
                              int H, const int* seq_lens, const float* bias_table, float scale, int round_scores,
-                             cudaStream_t st, int64_t* lc, int bias_const_dist = 0) {
+                             cudaStream_t st, int64_t* lc) {
     if (lc) ++*lc;
     static const bool legacy = env_flag("VQA_ATTN_MMA_SYNC");
     if (!legacy) {
         // tcgen05 kernel: q, k, v must be column slices of one packed buffer (they always are on this path)
         const int q_col0 = 0, k_col0 = (int)(k - q), v_col0 = (int)(v - q);
-        return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, st, bias_const_dist);
+        return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, st);
     }
     FlashParams p;
     p.q = q; p.k = k; p.v = v; p.o = o;
@@ -678,7 +678,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * S * S * 64, st);
             TRY(cuda_ok(run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
-                                  seq_lens, bias_table, 1.0f, rnd, st, lc, c.rel_max_distance), "t5 encoder attention"));
+                                  seq_lens, bias_table, 1.0f, rnd, st, lc), "t5 encoder attention"));
         }
         TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
         TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
@@ -939,11 +939,11 @@ extern "C" int vqa_op_lmhead_logprob(const void* Hs, int32_t ldh, const void* W,
 }
 
 extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                                    const float* bias_table, float scale, int32_t round_scores, int32_t bias_const_dist, void* stream) {
+                                    const float* bias_table, float scale, int32_t round_scores, void* stream) {
     if (!qkv || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
     const bf16* q = (const bf16*)qkv;
     cudaError_t e = run_flash(q, q + H * 64, q + 2 * H * 64, 3 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table,
-                              scale, round_scores, (cudaStream_t)stream, nullptr, bias_const_dist);
+                              scale, round_scores, (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

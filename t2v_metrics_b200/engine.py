@@ -260,11 +260,11 @@ class ops:
 
     @staticmethod
     def attention(qkv: torch.Tensor, B: int, S: int, H: int, seq_lens=None, bias_table=None, scale=1.0,
-                  round_scores=False, bias_const_dist: int = 0):
+                  round_scores=False):
         lib = _lib.load()
         out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device=qkv.device)
         rc = lib.vqa_op_attention_d64(_ptr(qkv), _ptr(out), B, S, H, _ptr(seq_lens), _ptr(bias_table), float(scale),
-                                      1 if round_scores else 0, int(bias_const_dist), _stream_ptr(qkv.device))
+                                      1 if round_scores else 0, _stream_ptr(qkv.device))
         _check(rc, None, "vqa_op_attention_d64")
         return out
 

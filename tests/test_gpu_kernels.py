@@ -116,18 +116,16 @@ def test_attention_matches_torch(ops, B, S, H, use_bias, ragged, scale):
 
 
 @pytest.mark.parametrize("S,dist,ragged", [(672, 128, False), (672, 128, True), (400, 40, True), (300, 299, False)])
-def test_attention_far_tiles_constant_bias(ops, S, dist, ragged):
-    """T5 buckets saturate at relative_attention_max_distance: the bias is one value per head and side for |key - query| >= dist.
-    Tiles that far from the diagonal take the raw-score path (max on raw scores, scale/bias/-max folded into one FFMA); the result
-    must equal the generic path (bias_const_dist = 0) up to fp32 re-association, and the torch reference."""
+def test_attention_saturating_t5_bias(ops, S, dist, ragged):
+    """T5 buckets saturate at relative_attention_max_distance: the bias is one value per head and side for |key - query| >= dist
+    (large magnitudes, many key tiles). The kernel against the torch reference."""
     torch.manual_seed(11)
     B, H = 2, 3
     qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 0.5).bfloat16()
     lens = torch.randint(S // 2, S + 1, (B,), device="cuda", dtype=torch.int32) if ragged else None
     rel = torch.arange(-(S - 1), S, device="cuda").clamp(-dist, dist) + dist                    # saturating buckets
     table = (torch.randn(H, 2 * dist + 1, device="cuda") * 2.0).bfloat16().float()[:, rel].contiguous()
-    out = ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=1.0, bias_const_dist=dist)
-    gen = ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=1.0, bias_const_dist=0)
+    out = ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=1.0)
     q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     idx = (torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None]) + S - 1
     sc = torch.matmul(q, k.transpose(-1, -2)) + table[:, idx][None]
@@ -137,7 +135,6 @@ def test_attention_far_tiles_constant_bias(ops, S, dist, ragged):
     ref = torch.matmul(torch.softmax(sc, -1), v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
     qmask = kmask.reshape(B * S)
     assert float((out[qmask].float() - ref[qmask]).abs().max()) < 0.02
-    assert float((out[qmask].float() - gen[qmask].float()).abs().max()) < 0.01
 
 
 def test_norms(ops):

@@ -176,14 +176,13 @@ def t_attention_perf(B=64, S=672, H=64, use_bias=1):
     rel = torch.arange(-(S - 1), S, device=dev).clamp(-dist, dist) + dist
     table = (torch.randn(H, 2 * dist + 1, device=dev) * 0.5)[:, rel].contiguous() if use_bias else None
     scale = 1.0 if use_bias else 0.125
-    cd = dist if (use_bias and os.environ.get("VQA_BIAS_CONST", "1") == "1") else 0
     for _ in range(3):
-        ops.attention(qkv, B, S, H, bias_table=table, scale=scale, bias_const_dist=cd)
+        ops.attention(qkv, B, S, H, bias_table=table, scale=scale)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(10):
-        ops.attention(qkv, B, S, H, bias_table=table, scale=scale, bias_const_dist=cd)
+        ops.attention(qkv, B, S, H, bias_table=table, scale=scale)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / 10
