@@ -29,7 +29,56 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // T5LayerNorm (transformers/models/t5/modeling_t5.py:55-68): y = w * bf16(x * rsqrt(mean(x^2) + eps)); fp32 variance.
-// One block per row; D % 8 == 0; D <= 8 * blockDim.x * VEC_PER_THREAD.
+// One WARP per row (8 rows per 256-thread block): the lane keeps its NV 16-byte vectors of the row in registers, the sum of squares
+// is a shuffle reduction (no shared memory, no block barrier), all NV loads of a lane are independent and in flight together.
+// D == 256 * NV (each lane owns vectors lane, lane + 32, ... so every load/store instruction of the warp is a contiguous 512 bytes).
+// Measured on B200 (gpurun run 25): faster than the block-per-row kernel below for the Qwen widths (1280 / 3584: 6.3 -> 4.95 ms per
+// step), slower for 4096-wide T5 rows (163 vs 122 us for 43008 rows), so the dispatcher keeps block-per-row from 4096 columns up.
+template <int NV>
+__global__ void __launch_bounds__(256) t5_rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ w,
+                                                             __nv_bfloat16* __restrict__ y, int rows, float eps) {
+    constexpr int D = 256 * NV;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (size_t)rows) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    const uint4* wr = reinterpret_cast<const uint4*>(w);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+    uint4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(u[e]);
+            ss = fmaf(f.x, f.x, ss);
+            ss = fmaf(f.y, f.y, ss);
+        }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint4 wv = __ldg(&wr[lane + 32 * i]);
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+        const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wv);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(u[e]);
+            const float2 g = unpack_bf16x2(wu[e]);
+            o[e] = pack_bf16x2(g.x * bf16_round(f.x * rstd), g.y * bf16_round(f.y * rstd));
+        }
+        yr[lane + 32 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Same norm for any D % 8 == 0 up to 8 * 256 * VPT: one block per row, block-wide reduction (T5-XXL's 4096 columns, and the odd widths of
+// test configs).
 template <int VPT>
 __global__ void __launch_bounds__(256) t5_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                         const __nv_bfloat16* __restrict__ w,

@@ -250,7 +250,19 @@ static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, in
 static cudaError_t run_rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, int D, float eps, cudaStream_t st,
                                int64_t* lc) {
     if (lc) ++*lc;
+    if (rows <= 0) return cudaSuccess;
+    if (D % 256 == 0 && D < 4096) {
+        const int blocks = (rows + 7) / 8;      // one warp per row
+#define VQA_RMS_CASE(NV) case NV: t5_rmsnorm_warp_kernel<NV><<<blocks, 256, 0, st>>>(x, w, y, rows, eps); break;
+        switch (D / 256) {
+            VQA_RMS_CASE(1) VQA_RMS_CASE(2) VQA_RMS_CASE(3) VQA_RMS_CASE(4) VQA_RMS_CASE(5) VQA_RMS_CASE(6) VQA_RMS_CASE(7) VQA_RMS_CASE(8)
+            VQA_RMS_CASE(9) VQA_RMS_CASE(10) VQA_RMS_CASE(11) VQA_RMS_CASE(12) VQA_RMS_CASE(13) VQA_RMS_CASE(14) VQA_RMS_CASE(15)
+        }
+#undef VQA_RMS_CASE
+        return cudaGetLastError();
+    }
     const int nvec = D / 8;
+    if (D % 8) return cudaErrorInvalidValue;
     if (nvec <= 256)       t5_rmsnorm_kernel<1><<<rows, 256, 0, st>>>(x, w, y, D, eps);
     else if (nvec <= 512)  t5_rmsnorm_kernel<2><<<rows, 256, 0, st>>>(x, w, y, D, eps);
     else if (nvec <= 1024) t5_rmsnorm_kernel<4><<<rows, 256, 0, st>>>(x, w, y, D, eps);

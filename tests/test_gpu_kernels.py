@@ -139,7 +139,7 @@ def test_attention_saturating_t5_bias(ops, S, dist, ragged):
 
 def test_norms(ops):
     torch.manual_seed(6)
-    for D in (4096, 2048, 256):
+    for D in (4096, 3584, 2048, 1280, 256, 128, 5120):   # warp-per-row (D % 256 == 0, <= 4096) and the generic block-per-row path
         x = torch.randn(333, D, device="cuda").bfloat16()
         g = (1 + 0.1 * torch.randn(D, device="cuda")).bfloat16()
         var = x.float().pow(2).mean(-1, keepdim=True)

@@ -150,3 +150,17 @@ def test_repetition_penalty_semantics():
     prompt = torch.tensor([3, 7, 7, 11])
     ref = torch.softmax(RepetitionPenaltyLogitsProcessor(1.05)(prompt[None], logits[None].clone())[0], -1)[7]
     assert abs(float(qo.answer_probability(logits, 7, 1.0, prompt, 1.05)) - float(ref)) < 1e-7
+
+
+def test_generation_config_penalty_lookup(tmp_path):
+    """the reference's scores pass through the processors of the checkpoint's generation_config.json; the plugin reads the
+    repetition penalty from the file beside the checkpoint, 1.0 (off) when there is none."""
+    import json
+    from t2v_metrics_b200.models.vqascore_models.qwen2vl_model import _generation_config_penalty
+    ckpt = tmp_path / "model.safetensors"
+    ckpt.write_bytes(b"")
+    assert _generation_config_penalty(str(ckpt)) == 1.0
+    (tmp_path / "generation_config.json").write_text(json.dumps({"repetition_penalty": 1.05, "temperature": 0.1}))
+    assert _generation_config_penalty(str(ckpt)) == 1.05
+    assert _generation_config_penalty(str(tmp_path)) == 1.05
+    assert _generation_config_penalty("/nonexistent/dir/model.bin") == 1.0

@@ -139,6 +139,24 @@ def t_norm():
         emit(test="layernorm", D=D, max_err=mx, mean_err=mean, ok=bool(mx < 0.05))
 
 
+def t_norm_perf(rows=43008, D=4096):
+    from t2v_metrics_b200.engine import ops
+    rows, D = int(rows), int(D)
+    x = torch.randn(rows, D, device="cuda:0").bfloat16()
+    g = torch.ones(D, device="cuda:0").bfloat16()
+    for _ in range(3):
+        ops.norm(x, g, None, 1e-6)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(20):
+        ops.norm(x, g, None, 1e-6)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 20
+    emit(test="norm_perf", rows=rows, D=D, ms=ms, gbps=4.0 * rows * D / ms / 1e6)
+
+
 def t_attention():
     from t2v_metrics_b200.engine import ops
     dev = "cuda:0"
