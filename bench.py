@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
         return
     if not args.model.startswith("clip-flant5"):
         # the headline metric (BASELINE.json) is the CLIP-FlanT5 one; the Qwen line is a secondary bench without a CPU arm
-        print(json.dumps(dict(impl="reference", unavailable=f"the CPU reference arm is implemented for clip-flant5-* only, not {args.model}")), flush=True)
+        emit(dict(impl="reference", unavailable=f"the CPU reference arm is implemented for clip-flant5-* only, not {args.model}"))
         return
     t0 = time.perf_counter()
     vals = []
@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=best["value"], unit="pairs/s", cores=best["cores"], kind=best["kind"], sample=best["sample"]),
                 e2e=dict(value=best["value"], unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, wall_s=round(time.perf_counter() - t0, 1))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ engine arm
@@ -206,7 +206,7 @@ def run_job(args, rank, world, dev, cfg, eng):
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         assert out.numel() == N and bool(torch.isfinite(out).all()) and float(out.min()) >= 0 and float(out.max()) <= 1
-        print(json.dumps(dict(
+        emit(dict(
             metric="VQAScore (image,text) pairs/sec @ clip-flant5-xxl, 512px", value=N / (ms_job * 1e-3), unit="pairs/s", n_gpus=world,
             steps=steps, warmup=3, ms_per_step=ms_job, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
             data="synthetic",
@@ -214,7 +214,7 @@ def run_job(args, rank, world, dev, cfg, eng):
                                  f"{B} + tail {per % B}, one all-gather of {N} fp32 scores; S_enc={L - 1 + cfg.num_patches}, T=2",
                         model=args.model, global_batch=B * world, seq_len=L - 1 + cfg.num_patches, parallelism=f"dp{world}",
                         l2_policy="inputs larger than L2"),
-            gpu_launches=int(eng.last_launch_count()) * (-(-n_local // B)) * steps, clocks=clocks)), flush=True)
+            gpu_launches=int(eng.last_launch_count()) * (-(-n_local // B)) * steps, clocks=clocks))
     if world > 1:
         dist.destroy_process_group()
 
@@ -344,7 +344,7 @@ def run_engine(args, rank, local_rank, world):
                 line["cpu_baseline"] = {k: v for k, v in cpu_reference_pairs_per_s(args.model, L).items() if k != "seconds_per_pair"}
             except Exception as e:  # noqa
                 line["cpu_baseline"] = dict(value=None, unit="pairs/s", cores=os.cpu_count(), kind="port", sample=f"failed: {e!r}")
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -457,13 +457,33 @@ def run_engine_qwen(args, rank, local_rank, world):
                     breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
                     e2e=dict(value=total / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=B * 4, ms_per_step=e2e_ms),
                     gpu_launches=int(launches) * args.steps, clocks=clocks, sample_scores=[float(x) for x in out[:4].float().cpu()])
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def reserve_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on stdout under torchrun), so
+    keep a private handle on the real stdout for the result line and point file descriptor 1 at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    reserve_stdout()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
