@@ -173,3 +173,28 @@ def test_qwen_batch_invariance(dev):
     for b in range(3):
         one = eng.score_prompts(inp["pixel_patches"][b * P:(b + 1) * P], [inp["grid_thw"][b]], [prompts[b]], [inp["answer_ids"][b]]).cpu()
         assert abs(float(torch.log(one[0]) - torch.log(full[b]))) < 2e-2
+
+
+@pytest.mark.parametrize("case", ["images", "video"])
+def test_qwen_engine_matches_committed_hf_golden(golden_dir, dev, case):
+    """Engine (through the C ABI) against tests/golden/qwen_tiny.pt = outputs of the real transformers model: plain answer probability
+    and the post-processor one (repetition penalty 1.3, temperature 0.5). Tolerance: 2x the bf16-vs-fp32 gap of the oracle + 2e-2 in log."""
+    from test_qwen_host import load_qwen_golden
+    blob, cfg, sd = load_qwen_golden(golden_dir)
+    c = blob["cases"][case]
+    inp, hf, spg = c["inputs"], c["hf"], c["second_per_grid_ts"]
+    o16 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
+                            mode="bf16", second_per_grid_ts=spg)
+    gap = float((torch.log(o16) - torch.log(hf["probs"])).abs().max())
+    eng = make_engine(cfg, sd, dev)
+    prompts = [x.tolist() for x in inp["input_ids"]]
+    p = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"], inp["image_of_sample"],
+                          second_per_grid_ts=spg).cpu()
+    e = float((torch.log(p) - torch.log(hf["probs"])).abs().max())
+    pp = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"], inp["image_of_sample"], temperature=0.5,
+                           repetition_penalty=1.3, second_per_grid_ts=spg).cpu()
+    ep = float((torch.log(pp) - torch.log(hf["probs_penalty_1p3_T_0p5"])).abs().max())
+    print(f"\n[qwen golden {case}] engine {p.tolist()} HF {hf['probs'].tolist()} |dlogp| {e:.3e}; penalised |dlogp| {ep:.3e}; "
+          f"oracle bf16-vs-HF fp32 {gap:.3e}")
+    assert e <= 2.0 * gap + 2e-2
+    assert ep <= 2.0 * gap / 0.5 + 2e-2

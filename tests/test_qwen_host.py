@@ -164,3 +164,35 @@ def test_generation_config_penalty_lookup(tmp_path):
     assert _generation_config_penalty(str(ckpt)) == 1.05
     assert _generation_config_penalty(str(tmp_path)) == 1.05
     assert _generation_config_penalty("/nonexistent/dir/model.bin") == 1.0
+
+
+def load_qwen_golden(golden_dir):
+    """tests/golden/qwen_tiny.pt (tools/make_golden_qwen.py): outputs of the real Qwen2_5_VLForConditionalGeneration; the weights are
+    regenerated from the seed and pinned by their checksum."""
+    import hashlib
+    import os
+    blob = torch.load(os.path.join(golden_dir, "qwen_tiny.pt"), weights_only=False)
+    cfg = qo.Qwen25VLConfig(**blob["config"])
+    sd = qo.make_synthetic_state_dict(cfg, seed=blob["weights_seed"])
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().view(torch.uint8).numpy().tobytes())
+    assert h.hexdigest() == blob["weights_sha256"], "synthetic weights differ from the ones the golden was generated with"
+    return blob, cfg, sd
+
+
+@pytest.mark.parametrize("case", ["images", "video"])
+def test_oracle_matches_committed_hf_golden(golden_dir, case):
+    """The oracle against the committed outputs of the real transformers model (fp32 logits, answer probability, and the probability
+    after RepetitionPenaltyLogitsProcessor(1.3) and temperature 0.5)."""
+    blob, cfg, sd = load_qwen_golden(golden_dir)
+    c = blob["cases"][case]
+    inp, hf = c["inputs"], c["hf"]
+    o = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
+                          mode="fp32", return_all=True, second_per_grid_ts=c["second_per_grid_ts"])
+    assert float((o["logits"] - hf["logits"]).abs().max()) < 5e-5
+    assert float((o["scores"] - hf["probs"]).abs().max()) < 1e-6
+    pen = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
+                            mode="fp32", temperature=0.5, repetition_penalty=1.3, second_per_grid_ts=c["second_per_grid_ts"])
+    assert float((torch.log(pen) - torch.log(hf["probs_penalty_1p3_T_0p5"])).abs().max()) < 1e-4
