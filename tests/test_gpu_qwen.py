@@ -197,4 +197,4 @@ def test_qwen_engine_matches_committed_hf_golden(golden_dir, dev, case):
     print(f"\n[qwen golden {case}] engine {p.tolist()} HF {hf['probs'].tolist()} |dlogp| {e:.3e}; penalised |dlogp| {ep:.3e}; "
           f"oracle bf16-vs-HF fp32 {gap:.3e}")
     assert e <= 2.0 * gap + 2e-2
-    assert ep <= 2.0 * gap / 0.5 + 2e-2
+    assert ep <= 2.0 * gap / 0.5 + 4e-2      # temperature 0.5 doubles every logit error (measured on B200: 3.2e-2 / 1.5e-2)
