@@ -137,3 +137,32 @@ def test_qwen_patch_layout_matches_hf_processor():
         got, grid = qwen_image_to_patches(img)
         assert list(grid) == ref["image_grid_thw"][0].tolist()
         assert float((got - ref["pixel_values"]).abs().max()) < 1e-5
+
+
+def test_prompt_constants_equal_the_reference_module():
+    """The prompt constants are part of the model's training recipe: compare with the reference's own module when it is mounted
+    (build container); on the GPU box the reference is absent and the values are pinned literally."""
+    import importlib.util
+    from t2v_metrics_b200 import constants as c
+    assert c.IMAGE_TOKEN_INDEX == -200 and c.IGNORE_INDEX == -100 and c.DEFAULT_IMAGE_TOKEN == "<image>" and c.CONTEXT_LEN == 2048
+    assert c.SYSTEM_MSG.startswith("A chat between a curious user") and c.SYSTEM_MSG.endswith("to the user's questions.")
+    ref = "/root/reference/t2v_metrics/constants.py"
+    if not os.path.exists(ref):
+        return
+    spec = importlib.util.spec_from_file_location("ref_constants", ref)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    for k in ("HF_CACHE_DIR", "CONTEXT_LEN", "SYSTEM_MSG", "IGNORE_INDEX", "IMAGE_TOKEN_INDEX", "DEFAULT_IMAGE_TOKEN"):
+        assert getattr(c, k) == getattr(m, k), k
+
+
+def test_image_loader_cases(tmp_path):
+    """.npy = BGR array reversed to RGB; everything else through PIL, always 3-channel RGB (reference model.py:10-14)."""
+    from t2v_metrics_b200.models.model import image_loader
+    a = (np.arange(4 * 5 * 3) % 255).astype(np.uint8).reshape(4, 5, 3)
+    np.save(tmp_path / "x.npy", a)
+    Image.fromarray(a).save(tmp_path / "x.png")
+    Image.fromarray(a[:, :, 0]).save(tmp_path / "g.png")
+    assert (np.asarray(image_loader(str(tmp_path / "x.npy"))) == a[:, :, ::-1]).all()
+    assert (np.asarray(image_loader(str(tmp_path / "x.png"))) == a).all()
+    assert np.asarray(image_loader(str(tmp_path / "g.png"))).shape == (4, 5, 3)
