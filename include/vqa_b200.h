@@ -183,6 +183,19 @@ int64_t vqa_last_launch_count(vqa_handle* h);
 int vqa_set_profile(vqa_handle* h, int32_t enable);
 int vqa_profile_read(vqa_handle* h, float* ms, double* flops, double* bytes, int64_t* scopes);
 
+/* Parity investigation aids: byte offsets, inside the caller-owned workspace of a call with the same sizes, of intermediate tensors
+ * that the reference exposes too (encoder_last_hidden_state, decoder_hidden_states[-1], ...). Valid after the stream has passed
+ * the scoring call. CLIP-FlanT5 (n >= 6): {encoder output, decoder output (both after the final T5LayerNorm), projector output,
+ * encoder / decoder residual streams, last vision-tower hidden state}. Qwen2.5-VL (n >= 4): {last-position hidden state after the
+ * final norm, merged vision features, residual stream, last-position residual}. */
+int vqa_clipt5_debug_layout(vqa_handle* h, int32_t batch, int32_t n_images, int32_t text_len, int32_t label_len, size_t* offsets,
+                            int32_t n);
+int vqa_qwen25vl_debug_layout(vqa_handle* h, int32_t batch, int32_t seq_len, int32_t n_patches, size_t* offsets, int32_t n);
+
+/* Process-wide override of the GEMM tile order (tuning): group_rows > 0 = A rows per M group, chunk_rows > 0 = W rows per
+ * L2-resident chunk, chunk_rows < 0 = one chunk; 0 = automatic. */
+int vqa_set_gemm_schedule(int32_t group_rows, int32_t chunk_rows);
+
 const char* vqa_last_error(vqa_handle* h);
 void vqa_destroy(vqa_handle* h);
 
@@ -236,9 +249,11 @@ int vqa_op_lmhead_logprob(const void* H, int32_t ldh, const void* W, int32_t ldw
                           const int32_t* labels, float* logprob, float* scratch, void* stream);
 
 /* Bidirectional attention, head_dim 64, packed qkv [B*S, 3*H*64] -> out [B*S, H*64].
- * bias_table: DEVICE float [H, 2S-1] (index key - query + S - 1) or NULL; seq_lens DEVICE int32 [B] or NULL. */
+ * bias_table: DEVICE float [H, 2S-1] (index key - query + S - 1) or NULL; seq_lens DEVICE int32 [B] or NULL.
+ * bias_const_from > 0: the caller guarantees bias_table[h][.] is constant for |key - query| >= bias_const_from on each side (T5's
+ * relative_attention_max_distance, modeling_t5.py:189-234), which lets far key tiles fold the bias into one FFMA; 0: no assumption. */
 int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                         const float* bias_table, float scale, int32_t round_scores, void* stream);
+                         const float* bias_table, float scale, int32_t bias_const_from, void* stream);
 
 /* T5LayerNorm / nn.LayerNorm on [rows, D] bf16. beta == NULL selects T5 RMS norm. */
 int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,

@@ -293,15 +293,17 @@ def qwen25vl_score(sd: Dict[str, torch.Tensor], cfg: Qwen25VLConfig, pixel_patch
 
 
 # ----------------------------------------------------------------------------------------------- synthetic weights / inputs
-def make_synthetic_state_dict(cfg: Qwen25VLConfig, seed: int = 0, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
-    g = torch.Generator().manual_seed(seed)
+def make_synthetic_state_dict(cfg: Qwen25VLConfig, seed: int = 0, dtype=torch.bfloat16, gen_device="cpu") -> Dict[str, torch.Tensor]:
+    # gen_device="cpu" is the seeded sequence behind the committed goldens; the full-width GPU tests draw 8 B parameters on the device
+    gd = torch.device(gen_device)
+    g = torch.Generator(device=gd).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
 
     def nrm(name, *shape, std=0.02):
-        sd[name] = (torch.randn(*shape, generator=g) * std).to(dtype)
+        sd[name] = (torch.randn(*shape, generator=g, device=gd) * std).to(dtype)
 
     def gain(name, n):
-        sd[name] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
+        sd[name] = (1.0 + 0.1 * torch.randn(n, generator=g, device=gd)).to(dtype)
 
     D, v = cfg.vit_hidden, "model.visual."
     nrm(v + "patch_embed.proj.weight", D, 3, cfg.temporal_patch_size, cfg.patch_size, cfg.patch_size, std=cfg.patch_dim ** -0.5)

@@ -31,6 +31,7 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
+constexpr int ATTN_POLY_DEFAULT = 2;   // score pairs of every 8 whose exp2 runs on the FMA pipe (0, 2 or 3)
 
 inline size_t attn_tc_smem_bytes(int S) {
     return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
@@ -100,7 +101,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // so only the very first tile of a CTA sees the full HBM/L2 latency.
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(192, 2)
-attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+attn_tc_d64_v1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -410,29 +411,494 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// v2 softmax stage. Same CTA skeleton and barrier protocol as v1 above (TMA warp, MMA warp, four softmax warps, two CTAs per SM);
+// what changes is the work per score, which is what bounds this kernel (head_dim 64: 512 tensor-core cycles per 128x128 tile against
+// >= 1024 MUFU cycles for its 16384 exponentials):
+//   * the row maximum is taken over the RAW scores (FMNMX3, two scores per instruction); the reference point of the exponentials is
+//     the upper bound  scale * max_j s_ij + max(bias window)  -- softmax is invariant to it, P just carries a common factor <= 1;
+//   * scale, bias and reference are applied with packed fp32x2 FFMA2 / FADD2 (two scores per instruction);
+//   * the T5 bias of a "near" tile (|key tile - query tile| <= near_tiles) comes from a sliding-window table in shared memory,
+//     Q[x] = (b[x], b[x+1], b[x+2], b[x+3]), so a row reads its 128 biases with 32 conflict-free LDS.128 (lane l's window is lane 0's
+//     shifted by -l entries = -16 B); tiles further out see one constant per side (T5 buckets saturate at max_distance) folded into
+//     the FFMA2 addend, as do bias-free heads (CLIP);
+//   * POLY of every 8 score pairs take their exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error
+//     7.5e-5, well under the bf16 rounding of P) instead of the MUFU;
+//   * all tcgen05.ld of a tile are issued back to back and waited on once.
+struct AttnTc2Params {
+    __nv_bfloat16* o; int ldo;
+    const int* seq_lens; const float* bias_table;   // [H, 2S-1] fp32 (natural-log domain) or nullptr
+    int S, H, q_col0, k_col0, v_col0;
+    float scale_log2e;
+    int near_tiles;     // key tiles with |kt - qt| <= near_tiles read the bias table; beyond, the table's end values (constant there)
+};
+
+inline size_t attn_tc2_smem_bytes(int near_tiles, bool has_bias) {
+    const size_t nq = has_bias ? (size_t)(2 * (128 * near_tiles + 127) + 1) : 0;
+    return 1024 + 6 * AT_TILE_BYTES + nq * 16 + 32 /*reduction scratch*/ + 14 * 8 + 16;
+}
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// exp2 of two values on the FMA pipe: x = n + f, n = rint(x) via the 1.5*2^23 trick, 2^f by a degree-3 minimax polynomial on
+// [-0.5, 0.5] (max relative error 7.5e-5), 2^n by adding n to the exponent field. x is clamped at -125 (result ~ 2^-125 ~ 0).
+__device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    x0 = fmaxf(x0, -125.f); x1 = fmaxf(x1, -125.f);
+    const uint64_t xc = pack2(x0, x1);
+    const uint64_t y = fadd2(xc, pack2(12582912.f, 12582912.f));
+    const uint64_t yf = fadd2(y, pack2(-12582912.f, -12582912.f));
+    const uint64_t f = ffma2(yf, pack2(-1.f, -1.f), xc);
+    uint64_t pl = ffma2(f, pack2(0.0551716648f, 0.0551716648f), pack2(0.2426111251f, 0.2426111251f));
+    pl = ffma2(pl, f, pack2(0.6932609677f, 0.6932609677f));
+    pl = ffma2(pl, f, pack2(0.9999280572f, 0.9999280572f));
+    float y0, y1, p0, p1;
+    unpack2(y, y0, y1);
+    unpack2(pl, p0, p1);
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(y0) << 23));
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(y1) << 23));
+}
+
+// One 32-key chunk of the exponential pass: sv = raw scores (fp32 bits) of this thread's row, out = 16 packed bf16 pairs of P.
+//   NEAR:  t = s * c + bias[j] - m      (bias from the sliding-window table)
+//   !NEAR: t = s * c + addc             (addc = constant bias - m)
+template <bool NEAR, int POLY>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t (&pk)[16], uint32_t bq /*shared-space byte address*/,
+                                              uint64_t cc, uint64_t addc, uint64_t& acc0, uint64_t& acc1) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint64_t t0 = pack2(__uint_as_float(sv[4 * q]), __uint_as_float(sv[4 * q + 1]));
+        uint64_t t1 = pack2(__uint_as_float(sv[4 * q + 2]), __uint_as_float(sv[4 * q + 3]));
+        if (NEAR) {
+            uint64_t b01, b23;   // four consecutive biases of this row: one conflict-free LDS.128 (see the kernel's header comment)
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bq + q * 64));
+            t0 = fadd2(ffma2(t0, cc, b01), addc);
+            t1 = fadd2(ffma2(t1, cc, b23), addc);
+        } else {
+            t0 = ffma2(t0, cc, addc);
+            t1 = ffma2(t1, cc, addc);
+        }
+        float e0, e1, e2, e3;
+        // pairs 2q and 2q+1 of this chunk's 16: POLY of every 8 pairs go to the FMA pipe, spread so MUFU and FMA work interleave
+        if (((2 * q) & 7) < POLY) exp2_poly2(t0, e0, e1);
+        else { float a, b_; unpack2(t0, a, b_); e0 = fast_exp2(a); e1 = fast_exp2(b_); }
+        if (((2 * q + 1) & 7) < POLY) exp2_poly2(t1, e2, e3);
+        else { float a, b_; unpack2(t1, a, b_); e2 = fast_exp2(a); e3 = fast_exp2(b_); }
+        acc0 = fadd2(acc0, pack2(e0, e1));
+        acc1 = fadd2(acc1, pack2(e2, e3));
+        pk[2 * q] = pack_bf16x2(e0, e1);
+        pk[2 * q + 1] = pack_bf16x2(e2, e3);
+    }
+}
+
+template <bool HAS_BIAS, int POLY>
+__global__ void __launch_bounds__(192, 2)
+attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const size_t row_base = (size_t)b * p.S;
+    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
+    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
+
+    // rows past the last valid query tile: deterministic zeros
+    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
+        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
+        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (nq == 0) return;
+
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
+    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
+    float4* sBiasQ = reinterpret_cast<float4*>(smem + 6 * AT_TILE_BYTES);   // Q[x] = log2e * (b[x-W], .., b[x-W+3]), x in [0, 2W]
+    const int Wn = 128 * p.near_tiles + 127;
+    const int nQ = HAS_BIAS ? 2 * Wn + 1 : 0;
+    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (size_t)nQ * 16);   // [8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8);
+    uint64_t* q_full = bars;          // [2]
+    uint64_t* q_empty = bars + 2;     // [2]
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        mbar_init(o_free, 4);
+        fence_barrier_init();
+        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
+        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
+        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
+        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
+        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    const float LOG2E = 1.4426950408889634f;
+    float b_left = 0.f, b_right = 0.f;      // constant bias (log2 domain) of far tiles to the left / right of the diagonal
+    if (HAS_BIAS) {
+        const int width = 2 * p.S - 1;
+        const float* src = p.bias_table + (size_t)h * width;
+        b_left = __ldg(src) * LOG2E;
+        b_right = __ldg(src + width - 1) * LOG2E;
+        float lmax = -INFINITY;
+        for (int x = threadIdx.x; x < nQ; x += blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = min(max(x + k - Wn + (p.S - 1), 0), width - 1);   // rel = x + k - W, clamped to the table
+                v[k] = __ldg(src + idx) * LOG2E;
+            }
+            sBiasQ[x] = make_float4(v[0], v[1], v[2], v[3]);
+            lmax = fmaxf(lmax, v[0]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) sRed[warp] = lmax;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                if (qi > 0) {   // (tile 0 was issued during set-up)
+                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+                }
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    if (g == 0) continue;
+                    const int st = g & 1;
+                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
+            auto issue_pv = [&](int g) {
+                const int j = g % nkt, qi = g / nkt;
+                mbar_wait(p_full, (uint32_t)g & 1u);
+                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
+                tcgen05_fence_after();
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < AT_BK / 16; ++ks)
+                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
+                                (j > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[g & 1]);
+                umma_commit<1>(o_done);
+            };
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
+                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    const int st = g & 1;
+                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
+                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit<1>(s_full);
+                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
+                    if (g > 0) issue_pv(g - 1);
+                }
+            }
+            issue_pv(total_tiles - 1);
+        }
+    } else {
+        // ===================== softmax / correction / epilogue: one thread per query row =====================
+        const uint32_t quad = warp & 3u;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (quad * 32u) << 16;
+        float bmax_near = 0.f;
+        if (HAS_BIAS) {
+            bmax_near = sRed[0];
+#pragma unroll
+            for (int i = 1; i < 6; ++i) bmax_near = fmaxf(bmax_near, sRed[i]);
+        }
+        const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
+        int g = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q0 = qi * AT_BQ;
+            const int qrow = q0 + row;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+            if (q0 + (int)quad * 32 >= len) {
+                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
+                for (int j = 0; j < nkt; ++j, ++g) {
+                    mbar_wait(s_full, (uint32_t)g & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full);
+                }
+                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            float m_run = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < nkt; ++j, ++g) {
+                const int k0 = j * AT_BK;
+                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
+                const int dt = j - qi;
+                const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
+                mbar_wait(s_full, (uint32_t)g & 1u);
+                tcgen05_fence_after();
+                uint32_t sv[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
+                tmem_ld_wait();
+                // S is in registers: hand the TMEM columns back so the next QK^T can start
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
+
+                // ---- pass 1: row maximum of the raw scores (masked keys -> -inf)
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (k0 + c * 32 + i >= len) sv[c][i] = 0xff800000u;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            mx0 = fmax3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+                            mx1 = fmax3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+                            mx2 = fmax3(mx2, __uint_as_float(sv[c][i + 4]), __uint_as_float(sv[c][i + 5]));
+                            mx3 = fmax3(mx3, __uint_as_float(sv[c][i + 6]), __uint_as_float(sv[c][i + 7]));
+                        }
+                    }
+                }
+                const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
+                const float tile_max = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), p.scale_log2e, bias_ub);
+                // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
+                float corr = 1.f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_run = tile_max;
+                } else {
+                    const bool need = tile_max > m_run + 8.f;
+                    rescale = __any_sync(0xffffffffu, need);
+                    if (rescale) {
+                        const float m_new = fmaxf(m_run, tile_max);
+                        corr = fast_exp2(m_run - m_new);
+                        m_run = m_new;
+                    }
+                }
+                if (j > 0) {
+                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                    tcgen05_fence_after();
+                    if (rescale) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                        }
+                    }
+                }
+                // ---- pass 2: exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                if (near) {
+                    const uint64_t negm = pack2(-m_run, -m_run);
+                    const uint32_t bq = smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * 16u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[16];
+                        if (c < nch) softmax_chunk<true, POLY>(sv[c], pk, bq + c * 512, cc, negm, acc0, acc1);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                        }
+                        tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                    }
+                } else {
+                    const float a = (dt < 0 ? b_left : b_right) - m_run;
+                    const uint64_t addc = pack2(a, a);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[16];
+                        if (c < nch) softmax_chunk<false, POLY>(sv[c], pk, 0u, cc, addc, acc0, acc1);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                        }
+                        tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                    }
+                }
+                {
+                    float a0, a1, a2, a3;
+                    unpack2(acc0, a0, a1);
+                    unpack2(acc1, a2, a3);
+                    l_run = l_run * corr + ((a0 + a1) + (a2 + a3));
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            // ---- epilogue of this query tile: O / l
+            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+            tcgen05_fence_after();
+            const float inv = (qrow < len) ? 1.f / l_run : 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_wait();
+                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_free);
+                }
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
+}
+
 // qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
+// bias_const_from: the bias table is constant (per head and side) for |key - query| >= bias_const_from (T5: relative_attention_max_distance);
+// <= 0 or >= S: no such guarantee, every tile reads the table.
+template <bool HAS_BIAS, int POLY>
+inline cudaError_t launch_attn_tc2_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
+    auto kernel = attn_tc_d64_kernel<HAS_BIAS, POLY>;
+    static std::atomic<size_t> max_set[64];   // per device: largest dynamic smem size opted into so far
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > max_set[dev & 63].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[dev & 63].store(smem, std::memory_order_release);
+    }
+    dim3 grid(1, p.H, B);   // one CTA per (sample, head); it loops over the query tiles
+    kernel<<<grid, 192, smem, stream>>>(tm, p);
+    return cudaGetLastError();
+}
+
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
-                                  int B, int S, int H, const int* seq_lens, const float* bias_table, float scale,
+                                  int B, int S, int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
                                   cudaStream_t stream) {
     CUtensorMap tm;
-    if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
-    AttnTcParams p;
+    if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    static const int variant = [] { const char* v = getenv("VQA_ATTN_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();
+    if (variant == 1) {   // A/B: the round-1 kernel
+        AttnTcParams p;
+        p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
+        p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+        p.scale_log2e = scale * 1.4426950408889634f;
+        const size_t smem = attn_tc_smem_bytes(S);
+        cudaError_t e = bias_table ? cudaFuncSetAttribute(attn_tc_d64_v1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(attn_tc_d64_v1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid(1, H, B);
+        if (bias_table) attn_tc_d64_v1_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
+        else            attn_tc_d64_v1_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
+        return cudaGetLastError();
+    }
+    AttnTc2Params p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
-    const size_t smem = attn_tc_smem_bytes(S);
-    static size_t max_set[2] = {0, 0};
-    const int which = bias_table ? 1 : 0;
-    if (smem > max_set[which]) {
-        cudaError_t e = bias_table ? cudaFuncSetAttribute(attn_tc_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                   : cudaFuncSetAttribute(attn_tc_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        max_set[which] = smem;
+    const int n_tiles = (S + 127) / 128;
+    int near = n_tiles;                                  // every tile reads the table
+    if (bias_table && bias_const_from > 0 && bias_const_from < S) near = min(n_tiles, (bias_const_from - 1 + 127) / 128);
+    p.near_tiles = bias_table ? near : 0;
+    const size_t smem = attn_tc2_smem_bytes(p.near_tiles, bias_table != nullptr);
+    const int poly = variant >= 10 ? variant - 10 : ATTN_POLY_DEFAULT;   // VQA_ATTN_VARIANT=10/12/13: POLY 0/2/3
+    if (bias_table) {
+        if (poly == 0) return launch_attn_tc2_t<true, 0>(tm, p, B, smem, stream);
+        if (poly == 2) return launch_attn_tc2_t<true, 2>(tm, p, B, smem, stream);
+        return launch_attn_tc2_t<true, 3>(tm, p, B, smem, stream);
     }
-    dim3 grid(1, H, B);   // one CTA per (sample, head); it loops over the query tiles
-    if (bias_table) attn_tc_d64_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
-    else            attn_tc_d64_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
-    return cudaGetLastError();
+    if (poly == 0) return launch_attn_tc2_t<false, 0>(tm, p, B, smem, stream);
+    if (poly == 2) return launch_attn_tc2_t<false, 2>(tm, p, B, smem, stream);
+    return launch_attn_tc2_t<false, 3>(tm, p, B, smem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -14,6 +14,9 @@
 #include "ptx.cuh"
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <unordered_map>
 
 namespace vqa {
 
@@ -52,8 +55,8 @@ struct GemmParams {
     int num_batches;
     int a_row_off, a_k_off, w_row_off, w_k_off;
     long long c_batch_stride;
-    // scheduling
-    int num_m_tiles, num_n_tiles, group_m;
+    // scheduling: W is cut into chunks of `chunk_n` N tiles; inside a chunk, groups of `group_m` M tiles sweep the chunk's N tiles
+    int num_m_tiles, num_n_tiles, group_m, chunk_n;
     // L2 eviction priority of the two operand streams (ptx.cuh L2_EVICT_*), chosen per launch by launch_gemm_t
     unsigned long long a_policy, w_policy;
 };
@@ -150,17 +153,25 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int num_tiles = tiles_per_batch * p.num_batches;
     const int num_workers = gridDim.x / CG;
     const int worker = blockIdx.x / CG;
-    const int tiles_per_group = p.group_m * p.num_n_tiles;
+    const int tiles_per_chunk = p.num_m_tiles * p.chunk_n;
 
+    // Tile order (L2 blocking): W chunk (chunk_n N tiles, sized to stay resident in L2) -> group of group_m M tiles -> the chunk's
+    // N tiles -> the group's M tiles (fastest). One wave of CTAs therefore shares group_m A row panels and a few W panels, the W chunk
+    // is re-read from L2 by every M group, and A streams through once per chunk.
     auto tile_coords = [&](int t, int& batch, int& m_blk, int& n_blk) {
         batch = t / tiles_per_batch;
         t -= batch * tiles_per_batch;
-        int g = t / tiles_per_group;
-        int r = t - g * tiles_per_group;
-        int m_first = g * p.group_m;
-        int gm = min(p.group_m, p.num_m_tiles - m_first);
+        const int c = t / tiles_per_chunk;
+        t -= c * tiles_per_chunk;
+        const int n_first = c * p.chunk_n;
+        const int cn = min(p.chunk_n, p.num_n_tiles - n_first);
+        const int tiles_per_group = p.group_m * cn;
+        const int g = t / tiles_per_group;
+        const int r = t - g * tiles_per_group;
+        const int m_first = g * p.group_m;
+        const int gm = min(p.group_m, p.num_m_tiles - m_first);
         m_blk = m_first + r % gm;
-        n_blk = r / gm;
+        n_blk = n_first + r / gm;
     };
 
     if (warp == 0) {
@@ -454,6 +465,52 @@ inline bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows,
     return r == CUDA_SUCCESS;
 }
 
+// process-wide tuning overrides (vqa_set_gemm_schedule); 0 = automatic
+static int g_gemm_group_rows_override = 0;
+static int g_gemm_chunk_rows_override = 0;
+
+// The same (base, shape) pairs come back on every forward (weights and workspace slices are stable), and encoding a CUtensorMap costs
+// a driver call: keep the encoded maps per thread. The map only describes address + extents, so a hit is valid whatever lives there.
+struct TmapKey {
+    const void* base; uint64_t rows, cols, ld; uint32_t box_rows;
+    bool operator==(const TmapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        h ^= (k.ld * 0x165667B19E3779F9ull + k.box_rows + (h << 6) + (h >> 2));
+        return (size_t)h;
+    }
+};
+inline bool tmap_bf16_2d_cached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    const TmapKey key{base, rows, cols, ld, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) { memcpy(map, &it->second, sizeof(CUtensorMap)); return true; }
+    if (!make_tmap_bf16_2d(map, base, rows, cols, ld, box_rows)) return false;
+    if (cache.size() > 16384) cache.clear();
+    cache.emplace(key, *map);
+    return true;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remember which devices have it for this kernel.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    template <typename F>
+    cudaError_t ensure(F&& set) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        e = set();
+        if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
+
 struct GemmLaunch {
     const __nv_bfloat16* A; int lda;   // [a_rows, a_cols] visible to TMA (defaults: M x K)
     const __nv_bfloat16* W; int ldw;   // [w_rows, w_cols] visible to TMA (defaults: N x K; 2*d_ff rows for GATED)
@@ -466,39 +523,57 @@ template <int BLOCK_N, int CG, int EPI>
 inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t stream) {
     using Cfg = GemmConfig<BLOCK_N, CG>;
     auto kernel = gemm_bf16_sm100_kernel<BLOCK_N, CG, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    static PerDeviceOnce attr;
+    {
+        cudaError_t e = attr.ensure([&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     CUtensorMap ta, tb;
     const uint64_t a_rows = g.a_rows ? (uint64_t)g.a_rows : (uint64_t)g.p.M;
     const uint64_t a_cols = g.a_cols ? (uint64_t)g.a_cols : (uint64_t)g.p.K;
     const uint64_t w_cols = g.w_cols ? (uint64_t)g.w_cols : (uint64_t)g.p.K;
-    if (!make_tmap_bf16_2d(&ta, g.A, a_rows, a_cols, (uint64_t)g.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-    if (!make_tmap_bf16_2d(&tb, g.W, (uint64_t)g.w_rows, w_cols, (uint64_t)g.ldw, Cfg::B_HALF_ROWS))
+    if (!tmap_bf16_2d_cached(&ta, g.A, a_rows, a_cols, (uint64_t)g.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+    if (!tmap_bf16_2d_cached(&tb, g.W, (uint64_t)g.w_rows, w_cols, (uint64_t)g.ldw, Cfg::B_HALF_ROWS))
         return cudaErrorInvalidValue;
     GemmParams p = g.p;
     if (p.num_batches < 1) p.num_batches = 1;
     const int rows_per_tile = Cfg::BLOCK_M * CG;
     p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    // Tile order: groups of `group_rows` A rows sweep all N tiles before the next group starts, so the group's A panel
-    // (group_rows x K) stays in L2 while W streams. Measured on B200 (profiles/r01_summary.md, DRAM bytes per launch): a
-    // ~32 MB A panel minimises re-reads when W is larger than L2 (FFN wi: 9.6 / 4.3 / 3.1 / 6.7 GB at 1024 / 2048 / 4096 /
-    // 8192 rows); when W itself fits in L2 a small group is best. VQA_GEMM_GROUP_ROWS overrides (tuning).
+    // Tile order = L2 blocking (see tile_coords). Either the W chunk or the A row group is the L2-resident operand:
+    //   * W-stationary: W cut into chunks of <= ~L2_RESIDENT bytes, small A groups stream past each chunk; DRAM reads ~ A * n_chunks + W
+    //   * A-stationary: one chunk (all of W streams), A groups of ~L2_RESIDENT bytes;                      DRAM reads ~ W * n_groups + A
+    // and the cheaper of the two by that model is taken. Measured DRAM bytes per launch for the encoder shapes are in
+    // profiles/r02_gemm_raster.md. vqa_set_gemm_schedule() / VQA_GEMM_GROUP_ROWS / VQA_GEMM_CHUNK_ROWS override (tuning).
     static const int env_rows = [] { const char* v = getenv("VQA_GEMM_GROUP_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
-    int group_rows;
-    if (env_rows > 0) {
-        group_rows = env_rows;
-    } else if ((long long)g.w_rows * p.K * 2 <= (96ll << 20)) {
-        group_rows = 1024;
+    static const int env_chunk = [] { const char* v = getenv("VQA_GEMM_CHUNK_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
+    const int ov_rows = g_gemm_group_rows_override > 0 ? g_gemm_group_rows_override : env_rows;
+    const int ov_chunk = g_gemm_chunk_rows_override != 0 ? g_gemm_chunk_rows_override : env_chunk;
+    const long long w_bytes = (long long)g.w_rows * p.K * 2, a_bytes = (long long)p.M * p.K * 2;
+    const long long resident = 36ll << 20;
+    int group_rows, chunk_rows;   // chunk_rows < 0: no chunking (all N tiles in one chunk)
+    if (w_bytes <= resident) {
+        group_rows = 1024; chunk_rows = -1;
     } else {
-        group_rows = (int)((32ll << 20) / ((long long)p.K * 2));
-        group_rows = max(512, min(8192, group_rows / 256 * 256));
+        const long long n_chunks = (w_bytes + resident - 1) / resident;
+        const long long n_groups = (a_bytes + resident - 1) / resident;
+        const long long cost_w = a_bytes * n_chunks + w_bytes, cost_a = w_bytes * n_groups + a_bytes;
+        if (cost_w <= cost_a) {
+            const long long rows = ((long long)g.w_rows + n_chunks - 1) / n_chunks;
+            chunk_rows = (int)((rows + BLOCK_N - 1) / BLOCK_N * BLOCK_N);
+            group_rows = 1024;
+        } else {
+            chunk_rows = -1;
+            group_rows = (int)((32ll << 20) / ((long long)p.K * 2));
+            group_rows = max(512, min(8192, group_rows / 256 * 256));
+        }
     }
+    if (ov_rows > 0) group_rows = ov_rows;
+    if (ov_chunk != 0) chunk_rows = ov_chunk;
     p.group_m = max(1, group_rows / rows_per_tile);
+    // the gated epilogue's W tile holds BLOCK_N/2 gate rows + BLOCK_N/2 up rows: a chunk of `chunk_rows` W rows = chunk_rows / BLOCK_N tiles either way
+    p.chunk_n = chunk_rows > 0 ? max(1, chunk_rows / BLOCK_N) : p.num_n_tiles;
+    if (p.chunk_n > p.num_n_tiles) p.chunk_n = p.num_n_tiles;
     // L2 eviction hints on the operand streams. Measured on B200 (profiles/r01_summary.md section 5): marking the re-read operand
     // evict_last and the streamed one evict_first RAISED the step's GEMM DRAM reads from 445 GB to 694 GB and cost 5 % of throughput
     // (an evict_first tile is dropped before the sibling CTAs that share it have fetched it), so the default is evict_normal on both.

@@ -281,31 +281,13 @@ static cudaError_t run_layernorm(const bf16* x, const bf16* g, const bf16* b, bf
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
+// q, k, v are column slices of one packed buffer (they always are on this path). bias_const_from: see launch_attn_tc.
 static cudaError_t run_flash(const bf16* q, const bf16* k, const bf16* v, int ldqkv, bf16* o, int ldo, int B, int S,
-                             int H, const int* seq_lens, const float* bias_table, float scale, int round_scores,
+                             int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
                              cudaStream_t st, int64_t* lc) {
     if (lc) ++*lc;
-    static const bool legacy = env_flag("VQA_ATTN_MMA_SYNC");
-    if (!legacy) {
-        // tcgen05 kernel: q, k, v must be column slices of one packed buffer (they always are on this path)
-        const int q_col0 = 0, k_col0 = (int)(k - q), v_col0 = (int)(v - q);
-        return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, st);
-    }
-    FlashParams p;
-    p.q = q; p.k = k; p.v = v; p.o = o;
-    p.ldq = p.ldk = p.ldv = ldqkv; p.ldo = ldo;
-    p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H; p.scale = scale; p.round_scores = round_scores;
-    const size_t smem = flash_smem_bytes(S, bias_table != nullptr);
-    static size_t max_set = 0;
-    if (smem > max_set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
-        max_set = smem;
-    }
-    dim3 grid((S + FA_BQ - 1) / FA_BQ, H, B);
-    flash_attn_d64_kernel<<<grid, 128, smem, st>>>(p);
-    return cudaGetLastError();
+    const int q_col0 = 0, k_col0 = (int)(k - q), v_col0 = (int)(v - q);
+    return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, bias_const_from, st);
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI: lifecycle
@@ -690,7 +672,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * S * S * 64, st);
             TRY(cuda_ok(run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
-                                  seq_lens, bias_table, 1.0f, rnd, st, lc), "t5 encoder attention"));
+                                  seq_lens, bias_table, 1.0f, c.rel_max_distance, st, lc), "t5 encoder attention"));
         }
         TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
         TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
@@ -793,6 +775,40 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         TRY(cuda_ok(cudaSuccess, "lse finalize"));
     }
 #undef TRY
+    return VQA_OK;
+}
+
+// Byte offsets inside the caller's workspace of the tensors a parity investigation wants to look at after a call has completed.
+extern "C" int vqa_clipt5_debug_layout(vqa_handle* h, int32_t batch, int32_t n_images, int32_t text_len, int32_t label_len,
+                                       size_t* offsets, int32_t n) {
+    if (!h || h->kind != 0 || !offsets || n < 6 || batch <= 0 || n_images <= 0 || text_len <= 0 || label_len <= 0)
+        return fail(h, VQA_ERR_INVALID_ARG, "bad debug layout argument");
+    const ClipT5Workspace w = plan_workspace(h, batch, n_images, text_len, label_len);
+    offsets[0] = w.xn;      // encoder output after the final T5LayerNorm  [B*S, d_model] bf16
+    offsets[1] = w.yn;      // decoder output after the final T5LayerNorm  [B*T, d_model] bf16
+    offsets[2] = w.proj2;   // projector output                            [NI*(P+1), d_model] bf16 (row 0 of each image = CLS)
+    offsets[3] = w.x;       // encoder residual stream before the final norm
+    offsets[4] = w.y;       // decoder residual stream before the final norm
+    offsets[5] = w.hv;      // vision tower hidden states of the last executed layer [NI*(P+1), vit_hidden]
+    return VQA_OK;
+}
+
+extern "C" int vqa_qwen25vl_debug_layout(vqa_handle* h, int32_t batch, int32_t seq_len, int32_t n_patches, size_t* offsets, int32_t n) {
+    if (!h || h->kind != 1 || !offsets || n < 4 || batch <= 0 || seq_len <= 0 || n_patches <= 0)
+        return fail(h, VQA_ERR_INVALID_ARG, "bad debug layout argument");
+    const QwenWorkspace w = qwen_plan(h->qwen->cfg, batch, seq_len, n_patches);
+    offsets[0] = w.lastn;       // last-position hidden state after the final RMSNorm [B, hidden] bf16
+    offsets[1] = w.vfeat_orig;  // merged vision features in processor order         [n_patches / merge^2, out_hidden] bf16
+    offsets[2] = w.x;           // language-model residual stream                     [B*S, hidden] bf16
+    offsets[3] = w.last;        // last-position residual before the final norm       [B, hidden] bf16
+    return VQA_OK;
+}
+
+// Process-wide override of the GEMM tile order (tuning / A-B measurements): group_rows > 0 = A rows per M group, chunk_rows > 0 = W rows
+// per L2-resident chunk, chunk_rows < 0 = no chunking; 0 = automatic choice (gemm_sm100.cuh launch_gemm_t).
+extern "C" int vqa_set_gemm_schedule(int32_t group_rows, int32_t chunk_rows) {
+    g_gemm_group_rows_override = group_rows;
+    g_gemm_chunk_rows_override = chunk_rows;
     return VQA_OK;
 }
 
@@ -951,11 +967,11 @@ extern "C" int vqa_op_lmhead_logprob(const void* Hs, int32_t ldh, const void* W,
 }
 
 extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                                    const float* bias_table, float scale, int32_t round_scores, void* stream) {
-    if (!qkv || !out) return fail(nullptr, VQA_ERR_INVALID_ARG, "null pointer");
+                                    const float* bias_table, float scale, int32_t bias_const_from, void* stream) {
+    if (!qkv || !out || B <= 0 || S <= 0 || H <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
     const bf16* q = (const bf16*)qkv;
     cudaError_t e = run_flash(q, q + H * 64, q + 2 * H * 64, 3 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table,
-                              scale, round_scores, (cudaStream_t)stream, nullptr);
+                              scale, bias_const_from, (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -209,6 +209,22 @@ class ClipT5Engine:
     def last_launch_count(self) -> int:
         return int(self.lib.vqa_last_launch_count(self._h))
 
+    def debug_tensors(self, batch: int, n_images: int, text_len: int, label_len: int) -> Dict[str, torch.Tensor]:
+        """Views into the workspace of the LAST call with these sizes (synchronise first): encoder / decoder outputs after their
+        final norms, projector output, residual streams. Parity investigations only."""
+        off = (C.c_size_t * 6)()
+        _check(self.lib.vqa_clipt5_debug_layout(self._h, batch, n_images, text_len, label_len, off, 6), self._h, "vqa_clipt5_debug_layout")
+        cfg = self.cfg
+        S = text_len - 1 + cfg.num_patches
+        ws = self._workspace
+
+        def view(o, rows, cols):
+            return ws[o:o + rows * cols * 2].view(torch.bfloat16).view(rows, cols)
+        return dict(enc_out=view(off[0], batch * S, cfg.d_model).view(batch, S, cfg.d_model),
+                    dec_out=view(off[1], batch * label_len, cfg.d_model).view(batch, label_len, cfg.d_model),
+                    proj=view(off[2], n_images * (cfg.num_patches + 1), cfg.d_model).view(n_images, cfg.num_patches + 1, cfg.d_model),
+                    vit_hidden=view(off[5], n_images * (cfg.num_patches + 1), cfg.vit_hidden).view(n_images, cfg.num_patches + 1, cfg.vit_hidden))
+
     def set_profile(self, enable: bool):
         _check(self.lib.vqa_set_profile(self._h, 1 if enable else 0), self._h, "vqa_set_profile")
 
@@ -260,11 +276,13 @@ class ops:
 
     @staticmethod
     def attention(qkv: torch.Tensor, B: int, S: int, H: int, seq_lens=None, bias_table=None, scale=1.0,
-                  round_scores=False):
+                  bias_const_from: int = 0):
+        """bias_const_from > 0 promises that bias_table[h] is constant for |key - query| >= bias_const_from on either side (T5:
+        relative_attention_max_distance); 0 makes no assumption."""
         lib = _lib.load()
         out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device=qkv.device)
         rc = lib.vqa_op_attention_d64(_ptr(qkv), _ptr(out), B, S, H, _ptr(seq_lens), _ptr(bias_table), float(scale),
-                                      1 if round_scores else 0, _stream_ptr(qkv.device))
+                                      int(bias_const_from), _stream_ptr(qkv.device))
         _check(rc, None, "vqa_op_attention_d64")
         return out
 
@@ -565,6 +583,17 @@ class QwenVLEngine:
                                          _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_score")
         return (out, logp) if return_logprobs else out
+
+    def debug_tensors(self, batch: int, seq_len: int, n_patches: int) -> Dict[str, torch.Tensor]:
+        """Views into the workspace of the LAST call with these sizes (synchronise first). Parity investigations only."""
+        off = (C.c_size_t * 4)()
+        _check(self.lib.vqa_qwen25vl_debug_layout(self._h, batch, seq_len, n_patches, off, 4), self._h, "vqa_qwen25vl_debug_layout")
+        cfg, ws = self.cfg, self._workspace
+        unit = cfg.spatial_merge_size ** 2
+
+        def view(o, rows, cols):
+            return ws[o:o + rows * cols * 2].view(torch.bfloat16).view(rows, cols)
+        return dict(last_hidden=view(off[0], batch, cfg.hidden), vision_feats=view(off[1], n_patches // unit, cfg.out_hidden))
 
     def score_prompts(self, pixel_patches, grid_thw, prompts, answer_ids, image_of_sample=None, temperature: float = 1.0,
                       repetition_penalty: float = 1.0, second_per_grid_ts=None):

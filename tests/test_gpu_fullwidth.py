@@ -1,0 +1,167 @@
+"""Parity at PRODUCTION width, against the reference's own arithmetic at the reference's own precision, on the same GPU.
+
+The comparator is the real `transformers` modules the reference delegates to, with bf16 weights and bf16 autocast exactly as the
+reference runs them (t2v_metrics/models/vqascore_models/mm_utils.py:228 `.to(bf16)`, v3.0 `@torch.autocast('cuda', bf16)`;
+qwen2vl_model.py:110-133 `torch_dtype=bfloat16, attn_implementation='sdpa'`, :222-230 `generate(max_new_tokens=1, output_scores=True)`),
+built on this GPU with weights generated on the device. The lm_head rows of the answer tokens are calibrated on the reference's own
+final hidden states so the scores spread over (0.1, 0.9): an absolute tolerance on a probability that sits at 1/vocab would be vacuous.
+
+Tolerance: |score_engine - score_reference| <= 1e-3 (BASELINE.json north_star). The fp32 reference and the intermediate tensors are
+printed for information only (-s).
+"""
+import dataclasses
+import gc
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clipt5_oracle as orc
+from oracle import qwen25vl_oracle as qo
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def _free():
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30)), float((a - b).abs().max())
+
+
+def run_clipt5_case(cfg, dev, B, L, lens, label_ids=(2163, 1), with_fp32=True, tag=""):
+    import hf_reference as hf
+    from t2v_metrics_b200.config import ClipT5Config
+    from t2v_metrics_b200.engine import ClipT5Engine
+    sd = orc.make_synthetic_state_dict(cfg, seed=0, device=dev, gen_device=dev)
+    inp = orc.make_synthetic_inputs(cfg, B, L, seed=1, label_ids=label_ids)
+    # ragged text lengths inside one padded batch: re-terminate the shortened rows like make_synthetic_inputs does
+    for b, n in enumerate(lens):
+        row = inp["input_ids"][b]
+        if n < L:
+            slot = int((row == orc.IMAGE_TOKEN_INDEX).nonzero()[0])
+            if slot >= n - 1:                         # keep the image slot inside the shortened prompt
+                row[slot] = 5
+                row[1] = orc.IMAGE_TOKEN_INDEX
+            row[n - 1] = 1
+            row[n:] = cfg.pad_token_id
+            inp["text_lens"][b] = n
+    mods = hf.build_hf_modules(cfg, sd, dtype=torch.bfloat16, device=dev)
+    fwd = lambda m, ac: hf.hf_clipt5_forward(cfg, m, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], autocast_bf16=ac,
+                                             return_all=True)
+    # ---- calibrate the answer rows of lm_head on the REFERENCE's final decoder states (bf16 autocast run)
+    r0 = fwd(mods, True)
+    offsets = torch.linspace(-2.0, 2.0, B)
+    lm = mods[2].lm_head.weight
+    for t, tok in enumerate(label_ids):
+        row = hf.calibrate_rows(r0["dec_hidden"][:, t], lm, tok, offsets)
+        lm.data[tok] = row.to(lm.device)
+        sd["lm_head.weight"][tok] = row.to(sd["lm_head.weight"].device)
+    ref = fwd(mods, True)
+    # ---- engine
+    eng = ClipT5Engine(ClipT5Config(**dataclasses.asdict(cfg)), dev)
+    eng.load_state_dict(sd)
+    i32 = lambda t: t.to(dev, torch.int32)
+    s, lp = eng.score_tensors(inp["pixels"].to(dev), i32(inp["input_ids"]), i32(inp["text_lens"]), i32(inp["labels"]), return_logprobs=True)
+    torch.cuda.synchronize()
+    s, lp = s.cpu(), lp.cpu()
+    dbg = eng.debug_tensors(B, B, L, len(label_ids))
+    mask = ref["mask"]
+    enc_rel = _rel(dbg["enc_out"].cpu()[mask], ref["enc"][mask])
+    dec_rel = _rel(dbg["dec_out"].cpu(), ref["dec_hidden"].cpu())
+    proj_rel = _rel(dbg["proj"].cpu()[:, 1:], ref["proj"])
+    err = float((s - ref["scores"]).abs().max())
+    print(f"\n[{tag}] engine     {[round(float(x), 5) for x in s]}\n[{tag}] HF bf16 GPU {[round(float(x), 5) for x in ref['scores']]}"
+          f"\n[{tag}] max|dscore| {err:.3e}   max|dlogp| {float((lp - ref['logprobs']).abs().max()):.3e}"
+          f"\n[{tag}] rel.err (max abs): projector {proj_rel[0]:.2e} ({proj_rel[1]:.2e}) | encoder out {enc_rel[0]:.2e} ({enc_rel[1]:.2e}) | "
+          f"decoder out {dec_rel[0]:.2e} ({dec_rel[1]:.2e}) | launches {eng.last_launch_count()}")
+    out = dict(engine=s, ref=ref["scores"], err=err)
+    if with_fp32:
+        try:
+            del mods, eng, dbg
+            _free()
+            m32 = hf.build_hf_modules(cfg, sd, dtype=torch.float32, device=dev)
+            r32 = fwd(m32, False)
+            out["fp32"] = r32["scores"]
+            print(f"[{tag}] HF fp32 GPU {[round(float(x), 5) for x in r32['scores']]}   |HF bf16 - HF fp32| {float((ref['scores'] - r32['scores']).abs().max()):.3e}"
+                  f"   |engine - HF fp32| {float((s - r32['scores']).abs().max()):.3e}")
+            del m32
+        except torch.OutOfMemoryError:
+            print(f"[{tag}] fp32 reference skipped (out of memory)")
+    del sd
+    _free()
+    return out
+
+
+def test_clipt5_xxl_matches_reference_bf16_on_this_gpu(dev):
+    """clip-flant5-xxl dims, 24 + 24 layers, B = 4, S_enc = 672 (97 ids incl. the image slot; two rows shorter), T = 2."""
+    r = run_clipt5_case(orc.ClipT5Config.xxl(), dev, B=4, L=97, lens=[97, 97, 80, 66], tag="xxl")
+    assert float(r["ref"].min()) > 0.08 and float(r["ref"].max()) < 0.92 and float(r["ref"].max() - r["ref"].min()) > 0.5
+    assert r["err"] <= TOL, r
+
+
+def test_clipt5_xl_matches_reference_bf16_on_this_gpu(dev):
+    """clip-flant5-xl dims (BASELINE config 1's model), full depth."""
+    r = run_clipt5_case(orc.ClipT5Config.xl(), dev, B=4, L=97, lens=[97, 90, 97, 70], tag="xl")
+    assert float(r["ref"].min()) > 0.08 and float(r["ref"].max()) < 0.92
+    assert r["err"] <= TOL, r
+
+
+def test_qwen25vl_7b_matches_reference_bf16_on_this_gpu(dev):
+    """Qwen2.5-VL-7B dims, B = 2, 448x448 images (1024 patches -> 256 vision tokens) + 64 text ids: the reference recipe
+    (generate(max_new_tokens=1, output_scores=True) per sample, softmax(scores / T)[answer]) on the real HF model vs ONE engine prefill."""
+    import hf_reference as hf
+    from t2v_metrics_b200.config import Qwen25VLConfig
+    from t2v_metrics_b200.engine import QwenVLEngine
+    cfg = qo.Qwen25VLConfig.qwen25_vl_7b()
+    B, answer = 2, 9454
+    sd = qo.make_synthetic_state_dict(cfg, seed=0, gen_device=dev)
+    inp = qo.make_synthetic_inputs(cfg, B, (448, 448), 64, seed=1, ragged=True, answer_id=answer)
+    model = hf.build_hf_qwen(cfg, sd, dtype=torch.bfloat16, device=dev, attn="sdpa")
+    score = lambda m, T=1.0: hf.hf_qwen_reference_scores(m, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"],
+                                                          temperature=T, return_hidden=True)
+    _, hid = score(model)
+    row = hf.calibrate_rows(hid, model.lm_head.weight, answer, torch.tensor([-1.5, 1.5]))
+    model.lm_head.weight.data[answer] = row.to(dev)
+    sd["lm_head.weight"][answer] = row.to(sd["lm_head.weight"].device)
+    ref, hid = score(model)
+    refT, _ = score(model, 0.7)
+    fields = {f.name for f in dataclasses.fields(Qwen25VLConfig)}
+    eng = QwenVLEngine(Qwen25VLConfig(**{k: v for k, v in dataclasses.asdict(cfg).items() if k in fields}), dev)
+    eng.load_state_dict(sd)
+    prompts = [x.tolist() for x in inp["input_ids"]]
+    p = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"])
+    torch.cuda.synchronize()
+    S = max(len(x) for x in prompts)
+    dbg = eng.debug_tensors(B, S, inp["pixel_patches"].shape[0])
+    hrel = _rel(dbg["last_hidden"].cpu(), hid.cpu())
+    pT = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"], temperature=0.7).cpu()
+    p = p.cpu()
+    err, errT = float((p - ref).abs().max()), float((pT - refT).abs().max())
+    print(f"\n[qwen-7b] engine {p.tolist()}  HF bf16 sdpa GPU {ref.tolist()}  max|dp| {err:.3e}; T=0.7: engine {pT.tolist()} HF {refT.tolist()} "
+          f"max|dp| {errT:.3e}\n[qwen-7b] last hidden state rel.err {hrel[0]:.2e} (max abs {hrel[1]:.2e}) | launches {eng.last_launch_count()}")
+    try:
+        del model
+        _free()
+        m32 = hf.build_hf_qwen(cfg, sd, dtype=torch.float32, device=dev, attn="eager")
+        r32, _ = score(m32)
+        print(f"[qwen-7b] HF fp32 eager GPU {r32.tolist()}  |HF bf16 - HF fp32| {float((ref - r32).abs().max()):.3e}  |engine - HF fp32| "
+              f"{float((p - r32).abs().max()):.3e}")
+        del m32
+    except torch.OutOfMemoryError:
+        print("[qwen-7b] fp32 reference skipped (out of memory)")
+    del sd, eng
+    _free()
+    assert float(ref.min()) > 0.08 and float(ref.max()) < 0.92 and float(ref.max() - ref.min()) > 0.4
+    assert err <= TOL and errT <= 2 * TOL, (p, ref, pT, refT)

@@ -7,20 +7,9 @@ from t2v_metrics_b200 import qwen_host
 
 
 def hf_model(cfg):
-    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
-    c = Qwen2_5_VLConfig(
-        text_config=dict(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers,
-                         num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads, rms_norm_eps=cfg.rms_eps,
-                         rope_parameters=dict(rope_type="default", rope_theta=cfg.rope_theta, mrope_section=list(cfg.mrope_section)),
-                         tie_word_embeddings=False, max_position_embeddings=4096, use_sliding_window=False),
-        vision_config=dict(depth=cfg.vit_depth, hidden_size=cfg.vit_hidden, intermediate_size=cfg.vit_mlp, num_heads=cfg.vit_heads,
-                           patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
-                           spatial_merge_size=cfg.spatial_merge_size, window_size=cfg.window_size,
-                           fullatt_block_indexes=list(cfg.fullatt_block_indexes), out_hidden_size=cfg.out_hidden,
-                           tokens_per_second=cfg.tokens_per_second, hidden_act="silu"),
-        image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id, tie_word_embeddings=False)
-    c._attn_implementation = "eager"
-    return Qwen2_5_VLForConditionalGeneration(c).eval()
+    from transformers import Qwen2_5_VLForConditionalGeneration
+    from hf_reference import hf_qwen_config
+    return Qwen2_5_VLForConditionalGeneration(hf_qwen_config(cfg)).eval()
 
 
 TINY = dict(hidden=256, heads=2, kv_heads=1, mrope_section=(16, 24, 24))   # head_dim 128 like the 7B model
