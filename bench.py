@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--pairs", type=int, default=0, help="clip-flant5: SURVEY 8(d) config 4 -- a JOB of this many pairs sharded "
                     "contiguously over the ranks in batches of --batch (+ tail), one all-gather; a step = the whole job; strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-eager-bf16-on-this-GPU comparison point (hf_gpu_baseline)")
+    ap.add_argument("--config1", action="store_true", help="--impl reference: BASELINE config 1 only (clip-flant5-xl, the reference's 4 PNGs x 4 prompts, batch 1, CPU)")
     ap.add_argument("--ncu", action="store_true", help="profiling pass: 2 device steps only, no JSON (run under ncu)")
     return ap.parse_args()
 
@@ -53,13 +55,16 @@ def measured_peaks():
 
 
 def measured_traffic(model):
-    """DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/r01_gemm_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-            t = json.load(f)
-        return t.get(model)
-    except Exception:
-        return None
+    """DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/r02_gemm_traffic.json, else round 1's), or None."""
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            if t.get(model):
+                return t.get(model)
+        except Exception:
+            pass
+    return None
 
 
 class ClockSampler:
@@ -97,59 +102,252 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU (reference) leg
-def cpu_reference_pairs_per_s(model: str, text_len: int):
-    """The reference algorithm on the host cores: oracle/clipt5_oracle.py (CPU restatement of the transformers T5/CLIP
-    forward the reference delegates to; the reference package itself cannot be imported offline), fp32,
-    batch = 1 as in the reference's own CPU-runnable config. Bounded sample: the full-WIDTH model at depth 1 and depth 2
-    (ViT/encoder/decoder layers), one pair each; per-layer cost = t2 - t1, extrapolated to 23/24/24 layers."""
+CONFIG1_IMAGES = ("0.png", "1.png", "0_DALLE3.png", "1_DALLE3.png")          # tests/golden/ref_images (copied from the reference's images/)
+CONFIG1_TEXTS = ("someone talks on the phone angrily while another person sits happily",       # V_3.0_README.md:121-123
+                 "someone talks on the phone happily while another person sits angrily",
+                 "a person holds a phone next to another person who is smiling",
+                 "two people sit on a sofa and neither of them has a phone")
+
+
+def host_threads():
+    """Threads the CPU arm may really use: the affinity mask, capped by the cgroup CPU quota, counted in PHYSICAL cores (one per SMT
+    sibling set). os.cpu_count() ignores all three and oversubscribes a containerised box."""
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        except Exception:
+            cores.add(str(c))
+    n = len(cores)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]))))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                        n = min(n, max(1, q // int(g.read().strip())))
+            break
+        except Exception:
+            continue
+    return max(1, n), len(cpus)
+
+
+def _stats(times):
+    t = sorted(times)
+    return dict(pair_seconds_min=round(t[0], 3), pair_seconds_median=round(t[len(t) // 2], 3), pair_seconds_max=round(t[-1], 3))
+
+
+def cpu_reference_clipt5(model: str, text_len: int, timed_pairs: int, budget_s: float, config1: bool = False):
+    """The reference algorithm MEASURED on the host cores, batch 1, full depth, fp32: the real transformers modules the reference
+    delegates to (T5ForConditionalGeneration + CLIPVisionModel; the reference package itself cannot be imported offline)
+    composed like the v3.0 wrapper by oracle/hf_reference.py. One warm-up pair, then up to `timed_pairs` timed pairs (at least 3;
+    stops early once `budget_s` is spent). Weights: HF init scales, values cycled out of a 4 M-entry pool (drawing 11 B normals on the
+    host takes minutes and the timing of dense fp32 GEMMs does not depend on the values).
+    config1 = BASELINE config 1: clip-flant5-xl, the reference's four PNGs x four prompts, the pair's PIL decode + expand2square +
+    bicubic resize + normalise inside the timed region (the reference's forward() does it per call)."""
     import torch
     from oracle import clipt5_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    base = orc.ClipT5Config.xxl() if model.endswith("xxl") else orc.ClipT5Config.xl()
-    import dataclasses
-    times = {}
-    for depth in (1, 2):
-        cfg = dataclasses.replace(base, vit_layers=depth + 1, enc_layers=depth, dec_layers=depth)
-        sd = orc.make_synthetic_state_dict(cfg, seed=0)
-        inp = orc.make_synthetic_inputs(cfg, 1, text_len, seed=1)
-        orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32")  # warm-up
-        best = float("inf")
-        for _ in range(2):
-            t0 = time.perf_counter()
-            orc.clipt5_score(sd, cfg, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"], mode="fp32")
-            best = min(best, time.perf_counter() - t0)
-        times[depth] = best
-        del sd
-    per_layer = max(times[2] - times[1], 1e-9)
-    full = times[1] + (base.enc_layers - 1) * per_layer
-    return dict(value=1.0 / full, unit="pairs/s", cores=os.cpu_count(), kind="port",
-                sample=(f"1 pair, fp32, full-width {model}: depth-1 pass {times[1]:.2f}s, depth-2 pass {times[2]:.2f}s; "
-                        f"per-layer-triple {per_layer:.2f}s extrapolated to {base.enc_layers} layers = {full:.1f}s/pair"),
-                seconds_per_pair=full)
+    from oracle import hf_reference as hf
+    threads, logical = host_threads()
+    torch.set_num_threads(threads)
+    cfg = orc.ClipT5Config.xxl() if model.endswith("xxl") else orc.ClipT5Config.xl()
+    if os.environ.get("VQA_BENCH_TINY"):          # CLI smoke test of this code path on a laptop-sized model (tests/test_bench_cli.py)
+        cfg = orc.ClipT5Config.tiny()
+    t_build = time.perf_counter()
+    pool = torch.randn((1 << 22) + 12345, generator=torch.Generator().manual_seed(0))
+    sd = orc.make_synthetic_state_dict(cfg, dtype=torch.float32, pool=pool)
+    mods = hf.build_hf_modules(cfg, sd, dtype=torch.float32, device="cpu", fast_construct=True, assign=True)
+    del sd
+    t_build = time.perf_counter() - t_build
+    if config1:
+        from PIL import Image
+        img_dir = os.path.join(ROOT, "tests", "golden", "ref_images")
+        work = [(os.path.join(img_dir, im), ti) for im in CONFIG1_IMAGES for ti in range(len(CONFIG1_TEXTS))]
+    else:
+        work = [(None, i) for i in range(timed_pairs + 1)]
+
+    def one_pair(item):
+        path, seed = item
+        inp = orc.make_synthetic_inputs(cfg, 1, text_len, seed=100 + seed)        # token ids: no tokenizer offline (SURVEY 8d)
+        if path is not None:
+            inp["pixels"] = orc.clip_preprocess(Image.open(path), cfg.image_size, pad=True)[None]
+        return float(hf.hf_clipt5_forward(cfg, mods, inp["pixels"], inp["input_ids"], inp["text_lens"], inp["labels"])[0])
+
+    one_pair(work[0])                                                                 # warm-up (page-in, thread pool, oneDNN primitives)
+    times, scores, t_start = [], [], time.perf_counter()
+    for item in (work if config1 else work[1:]):
+        t0 = time.perf_counter()
+        scores.append(one_pair(item))
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 3 and (time.perf_counter() - t_start) > budget_s and not config1:
+            break
+        if len(times) >= timed_pairs and not config1:
+            break
+    total = sum(times)
+    what = (f"BASELINE config 1: {model}, {len(CONFIG1_IMAGES)} reference PNGs x {len(CONFIG1_TEXTS)} prompts = {len(times)} pairs, PIL pre-processing inside"
+            if config1 else f"{len(times)} synthetic pairs (336px CLIP input, {text_len} ids, S_enc = {text_len - 1 + cfg.num_patches}, T = 2)")
+    return dict(value=len(times) / total, unit="pairs/s", cores=threads, kind="port",
+                sample=(f"MEASURED, not extrapolated: {what}; batch 1, full depth ({cfg.vit_layers - 1} ViT + {cfg.enc_layers} + {cfg.dec_layers} T5 layers), "
+                        f"fp32, transformers {_tf_version()} T5ForConditionalGeneration + CLIPVisionModel (the modules the reference delegates to; glue "
+                        f"restated in oracle/hf_reference.py), torch.set_num_threads({threads}) = physical cores in the affinity mask / cgroup quota "
+                        f"({logical} logical CPUs visible); 1 warm-up pair; model build {t_build:.0f}s not timed"),
+                pairs_timed=len(times), seconds_per_pair=total / len(times), effective_tflops=round(FLOPS_PER_PAIR[model] * len(times) / total / 1e12, 3),
+                score_range=[round(min(scores), 6), round(max(scores), 6)], **_stats(times))
+
+
+def cpu_reference_qwen(model: str, timed_pairs: int, budget_s: float, video: bool = False):
+    """BASELINE config 3 / 5 on the host cores: the real Qwen2_5_VLForConditionalGeneration (fp32, eager) driven exactly like the reference
+    drives it -- one sample at a time, generate(max_new_tokens=1, output_scores=True), softmax(scores)[answer]
+    (t2v_metrics/models/vqascore_models/qwen2vl_model.py:190-289)."""
+    import torch
+    from oracle import qwen25vl_oracle as qo
+    from oracle import hf_reference as hf
+    threads, logical = host_threads()
+    torch.set_num_threads(threads)
+    cfg = qo.Qwen25VLConfig.qwen25_vl_7b()
+    if os.environ.get("VQA_BENCH_TINY"):
+        cfg = qo.Qwen25VLConfig.tiny(hidden=256, heads=2, kv_heads=1, mrope_section=(16, 24, 24))
+    t_build = time.perf_counter()
+    pool = torch.randn((1 << 22) + 12345, generator=torch.Generator().manual_seed(0))
+    sd = qo.make_synthetic_state_dict(cfg, dtype=torch.float32, pool=pool)
+    m = hf.build_hf_qwen(cfg, sd, dtype=torch.float32, device="cpu", attn="sdpa", fast_construct=True, assign=True)
+    del sd
+    t_build = time.perf_counter() - t_build
+    hw, frames = ((224, 224), 8) if video else ((448, 448), 1)
+
+    def one_pair(seed):
+        inp = qo.make_synthetic_inputs(cfg, 1, hw, 64, seed=100 + seed, frames=frames)
+        return float(hf.hf_qwen_reference_scores(m, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"],
+                                                 video=video, second_per_grid_ts=[1.0] if video else None)[0])
+    one_pair(0)
+    times, t_start = [], time.perf_counter()
+    for i in range(1, timed_pairs + 1):
+        t0 = time.perf_counter()
+        one_pair(i)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 3 and (time.perf_counter() - t_start) > budget_s:
+            break
+    total = sum(times)
+    return dict(value=len(times) / total, unit="pairs/s", cores=threads, kind="port",
+                sample=(f"MEASURED: {len(times)} synthetic samples ({'16-frame 224x224 video, grid 8x16x16' if video else '448x448 image, 1024 patches'} + 64 text ids), "
+                        f"one generate(max_new_tokens=1, output_scores=True) per sample as the reference does, fp32, sdpa, transformers {_tf_version()} "
+                        f"Qwen2_5_VLForConditionalGeneration at 7B dims, torch.set_num_threads({threads}) ({logical} logical CPUs visible); 1 warm-up; "
+                        f"model build {t_build:.0f}s not timed"),
+                pairs_timed=len(times), seconds_per_pair=total / len(times), **_stats(times))
+
+
+def _tf_version():
+    try:
+        import transformers
+        return transformers.__version__
+    except Exception:
+        return "?"
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU path on this box's host cores, on the engine arm's config (clip-flant5-xxl shapes), every
+    reported pair measured at full depth. A step = one (image, text) pair at batch 1 -- the bounded sample of the 64-pair batch that the CPU
+    finishes in seconds; `steps` is the number of pairs actually timed (the requested --steps is echoed as steps_requested) so that
+    ms_per_step x steps is the real timed region. BASELINE config 1 (xl, the reference's PNGs) is measured in the same run (`config1`)."""
     if rank != 0:
         return
-    if not args.model.startswith("clip-flant5"):
-        # the headline metric (BASELINE.json) is the CLIP-FlanT5 one; the Qwen line is a secondary bench without a CPU arm
-        emit(dict(impl="reference", unavailable=f"the CPU reference arm is implemented for clip-flant5-* only, not {args.model}"))
-        return
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        vals.append(cpu_reference_pairs_per_s(args.model, args.text_len))
-    best = max(vals, key=lambda v: v["value"])
-    line = dict(impl="reference", metric="VQAScore (image,text) pairs/sec @ clip-flant5-xxl, 512px", value=best["value"],
-                unit="pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 * best["seconds_per_pair"] * args.batch, higher_is_better=True, scaling="weak",
+    if args.model.startswith("qwen"):
+        best = cpu_reference_qwen(args.model, timed_pairs=max(3, min(args.steps, 6)), budget_s=150.0, video=args.video)
+        metric = "VQAScore (video,text) pairs/sec @ qwen2.5-vl-7b, 16x224px" if args.video else "VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px"
+        workload = f"{args.model} VQAScore on the host CPU, one sample per generate() call"
+        cfg1 = None
+    else:
+        cfg1 = cpu_reference_clipt5("clip-flant5-xl", args.text_len, 16, 0.0, config1=True)
+        best = cfg1 if args.config1 else cpu_reference_clipt5(args.model, args.text_len, timed_pairs=max(3, min(args.steps, 8)), budget_s=150.0)
+        metric = "VQAScore (image,text) pairs/sec @ clip-flant5-xxl, 512px"
+        workload = (f"{'clip-flant5-xl' if args.config1 else args.model} VQAScore: the engine arm's pairs (336px CLIP input, {args.text_len} ids incl. image slot, "
+                    f"S_enc=672, labels [Yes,</s>]) one pair per step at batch 1 on the host CPU")
+    n = best["pairs_timed"]
+    line = dict(impl="reference", metric=metric, value=best["value"], unit="pairs/s", n_gpus=args.gpus, steps=n, steps_requested=args.steps,
+                warmup=1, warmup_requested=args.warmup, ms_per_step=1000.0 * best["seconds_per_pair"], higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"{args.model} VQAScore, batch=1 on host CPU, 336px CLIP input, {args.text_len} ids (S_enc=672), T=2",
-                            model=args.model),
-                cpu_baseline=dict(value=best["value"], unit="pairs/s", cores=best["cores"], kind=best["kind"], sample=best["sample"]),
+                config=dict(workload=workload, model=args.model, global_batch=1, seq_len=args.text_len - 1 + 576 if not args.model.startswith("qwen") else None,
+                            parallelism="cpu"),
+                cpu_baseline={k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 e2e=dict(value=best["value"], unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0, wall_s=round(time.perf_counter() - t0, 1))
+                timing={k: v for k, v in best.items() if k.startswith("pair_seconds") or k in ("pairs_timed", "effective_tflops")},
+                gpu_launches=0)
+    if cfg1 is not None and not args.config1:
+        line["config1"] = {k: v for k, v in cfg1.items() if k != "seconds_per_pair"}
+    line["wall_s"] = round(time.perf_counter() - t0, 1)
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------ HF on the same GPU ("the kernel to beat")
+def hf_gpu_baseline_clipt5(cfg, dev, host, steps=3):
+    """the reference's arithmetic as it would run on this B200 WITHOUT this repo -- transformers eager T5 / CLIP,
+    bf16 weights + bf16 autocast (mm_utils.py:228, v3.0 @torch.autocast), cuBLAS GEMMs, eager attention materialising [B,H,S,S] scores --
+    on the same batch of 64 pre-processed pairs. Device-resident inputs, CUDA events."""
+    import dataclasses
+    import torch
+    from oracle import clipt5_oracle as orc
+    from oracle import hf_reference as hf
+    ocfg = orc.ClipT5Config(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(orc.ClipT5Config)})
+    sd = orc.make_synthetic_state_dict(ocfg, seed=0, device=dev, gen_device=dev)
+    mods = hf.build_hf_modules(ocfg, sd, dtype=torch.bfloat16, device=dev, assign=True)
+    del sd
+    pix = host["pixels"].to(dev)
+    ids, lens, labels = host["input_ids"].long(), host["text_lens"].long(), host["labels"].long()
+    fwd = lambda: hf.hf_clipt5_forward(ocfg, mods, pix, ids, lens, labels, autocast_bf16=True)
+    fwd()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fwd()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del mods
+    torch.cuda.empty_cache()
+    return dict(value=pix.shape[0] / (ms * 1e-3), unit="pairs/s", ms_per_step=ms, steps=steps, warmup=1,
+                what=f"transformers {_tf_version()} eager bf16 (T5ForConditionalGeneration + CLIPVisionModel composed as the v3.0 wrapper, "
+                     "bf16 weights + autocast, cuBLAS, eager attention) on this GPU, same batch, inputs resident in HBM",
+                peak_gib=round(peak, 1), finite=bool(torch.isfinite(out).all()))
+
+
+def hf_gpu_baseline_qwen(cfg, dev, host, video, steps=2):
+    """The reference's Qwen recipe on this GPU: bf16, sdpa, one generate(max_new_tokens=1, output_scores=True) per sample
+    (qwen2vl_model.py:110-133, 190-289)."""
+    import dataclasses
+    import torch
+    from oracle import qwen25vl_oracle as qo
+    from oracle import hf_reference as hf
+    ocfg = qo.Qwen25VLConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(qo.Qwen25VLConfig) if hasattr(cfg, f.name)})
+    sd = qo.make_synthetic_state_dict(ocfg, seed=0, gen_device=dev)
+    m = hf.build_hf_qwen(ocfg, sd, dtype=torch.bfloat16, device=dev, attn="sdpa", assign=True)
+    del sd
+    B = len(host["prompts"])
+    pix = host["pixel_patches"].to(dev)
+    ids = [torch.tensor(p) for p in host["prompts"]]
+    fwd = lambda: hf.hf_qwen_reference_scores(m, ocfg, pix, host["grid_thw"], ids, host["answer_ids"], video=video,
+                                              second_per_grid_ts=[1.0] * B if video else None)
+    fwd()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = fwd()
+    torch.cuda.synchronize(dev)
+    ms = (time.perf_counter() - t0) * 1000.0 / steps
+    del m
+    torch.cuda.empty_cache()
+    return dict(value=B / (ms * 1e-3), unit="pairs/s", ms_per_step=ms, steps=steps, warmup=1,
+                what=f"transformers {_tf_version()} Qwen2_5_VLForConditionalGeneration bf16 sdpa on this GPU, the reference's loop: one "
+                     "generate(max_new_tokens=1, output_scores=True) + softmax per sample, patches resident in HBM", finite=bool(torch.isfinite(out).all()))
 
 
 # ------------------------------------------------------------------------------------------------ engine arm
@@ -271,13 +469,11 @@ def run_engine(args, rank, local_rank, world):
         out = step_device()
     sync_all()
 
-    # ---- timed region 1: inputs resident in HBM (kernel-side throughput) + per-category device timing
-    eng.set_profile(True)
+    # ---- timed region 1: inputs resident in HBM, profiling OFF (this is `value`)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    prof_acc = {}
     sync_all()
     ev0.record()
     for _ in range(args.steps):
@@ -285,14 +481,30 @@ def run_engine(args, rank, local_rank, world):
     ev1.record()
     sync_all()
     ms_local = ev0.elapsed_time(ev1)
-    prof = eng.read_profile()          # categories of the last step
     launches = eng.last_launch_count()
-    eng.set_profile(False)
     t = torch.tensor([ms_local], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- separate profiled pass (per-launch CUDA events inside the library): breakdown + roofline of the GEMM kernel, same steps back to back
+    eng.set_profile(True)
+    prof_steps = max(1, min(args.steps, 3))
+    acc = None
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    pe0.record()
+    for _ in range(prof_steps):
+        step_device()
+        torch.cuda.synchronize(dev)
+        pr = eng.read_profile()
+        acc = pr if acc is None else {k: tuple(a + b for a, b in zip(acc[k], pr[k])) for k in pr}
+    pe1.record()
+    torch.cuda.synchronize(dev)
+    prof = {k: tuple(x / prof_steps for x in v) for k, v in acc.items()}     # per-step averages
+    prof_ms_step = pe0.elapsed_time(pe1) / prof_steps
+    eng.set_profile(False)
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H inside)
     for _ in range(2):
@@ -330,20 +542,30 @@ def run_engine(args, rank, local_rank, world):
                           traffic=traffic.get("dram_bytes_per_launch") if traffic else None, traffic_source=traffic.get("source") if traffic else None,
                           algorithmic_bytes_per_launch=gemm_bytes / max(gemm_n, 1),
                           kernel="gemm_bf16_sm100_kernel (all tcgen05 GEMM launches of the step)",
-                          flops_per_launch=gemm_flops / max(gemm_n, 1), launches=gemm_n, device_ms=gemm_ms, peak_source=peaks["source"],
-                          whole_step_tflops=(value / world) * fpp / 1e12 if fpp else None),
+                          flops_per_launch=gemm_flops / max(gemm_n, 1), launches=int(gemm_n), device_ms=gemm_ms, peak_source=peaks["source"],
+                          whole_step_tflops=(value / world) * fpp / 1e12 if fpp else None,
+                          whole_step_frac_of_peak=((value / world) * fpp / 1e12 / peaks["tflops"]) if fpp else None),
             breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
+            breakdown_note=f"separate profiled pass of {prof_steps} steps ({prof_ms_step:.1f} ms/step with the library's per-launch CUDA events on); "
+                           "`value` is timed with profiling off",
             e2e=dict(value=total_pairs / (e2e_ms_step * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      ms_per_step=e2e_ms_step,
                      path="ClipT5Engine.score_images_u8: pinned uint8 512x512 images + ids -> H2D -> vqa_clip_preprocess -> "
                           "vqa_clipt5_score -> D2H scores"),
             gpu_launches=int(launches) * args.steps, clocks=clocks,
             sample_scores=[round(float(x), 6) for x in out[:4].float().cpu()])
+        if world == 1 and not args.no_hf_baseline:
+            try:
+                line["hf_gpu_baseline"] = hf_gpu_baseline_clipt5(cfg, dev, host)
+                line["hf_gpu_baseline"]["speedup_value_over_hf"] = round(value / line["hf_gpu_baseline"]["value"], 2)
+            except Exception as e:  # noqa
+                line["hf_gpu_baseline"] = dict(value=None, unit="pairs/s", what=f"failed: {e!r}")
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = {k: v for k, v in cpu_reference_pairs_per_s(args.model, L).items() if k != "seconds_per_pair"}
+                line["cpu_baseline"] = {k: v for k, v in cpu_reference_clipt5(args.model, L, timed_pairs=3, budget_s=30.0).items()
+                                        if k != "seconds_per_pair"}
             except Exception as e:  # noqa
-                line["cpu_baseline"] = dict(value=None, unit="pairs/s", cores=os.cpu_count(), kind="port", sample=f"failed: {e!r}")
+                line["cpu_baseline"] = dict(value=None, unit="pairs/s", cores=host_threads()[0], kind="port", sample=f"failed: {e!r}")
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -393,10 +615,20 @@ def run_engine_qwen(args, rank, local_rank, world):
         s = eng.score_tensors(d_pix, host["grid_thw"], d_idx["input_ids"], d_idx["seq_lens"], d_idx["feat_index"], d_idx["position_ids"], d_ans)
         return gather_scores(s, total) if world > 1 else s
 
+    # e2e inputs: what the plugin's forward() starts from -- decoded uint8 images (config 3) or, for the video shape, the processor's fp32
+    # patch rows (frame sampling / decoding is CPU work outside the path) -- plus the prompts as python id lists
+    g = torch.Generator().manual_seed(7 + rank)
+    raw_u8 = None if video else torch.randint(0, 256, (B, hw[0], hw[1], 3), generator=g, dtype=torch.uint8).pin_memory()
+
     def step_host():
-        t = {k: v.to(dev, non_blocking=True) for k, v in idx.items()}
-        s = eng.score_tensors(host["pixel_patches"].to(dev, non_blocking=True), host["grid_thw"], t["input_ids"], t["seq_lens"],
-                              t["feat_index"], t["position_ids"], ans_h.to(dev, non_blocking=True))
+        # the work Qwen2VLModel.forward does per call: (device) smart_resize + patch layout of the decoded images, the mRoPE / window /
+        # splice index arrays built on the host (qwen_host.build_batch_indices), H2D of ids + indices, one prefill, D2H of the scores
+        from t2v_metrics_b200.engine import qwen_preprocess_u8
+        if raw_u8 is not None:
+            patches, grids = qwen_preprocess_u8(raw_u8, dev)
+        else:
+            patches, grids = host["pixel_patches"].to(dev, non_blocking=True), host["grid_thw"]
+        s = eng.score_prompts(patches, grids, host["prompts"], host["answer_ids"], second_per_grid_ts=[1.0] * B if video else None)
         if world > 1:
             s = gather_scores(s, total)
         return s.cpu()
@@ -404,7 +636,6 @@ def run_engine_qwen(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     sync_all()
-    eng.set_profile(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -415,14 +646,22 @@ def run_engine_qwen(args, rank, local_rank, world):
         out = step_device()
     ev1.record()
     sync_all()
-    prof = eng.read_profile()
     launches = eng.last_launch_count()
-    eng.set_profile(False)
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    # separate profiled pass (library-side per-launch CUDA events)
+    eng.set_profile(True)
+    prof_steps, acc = max(1, min(args.steps, 3)), None
+    for _ in range(prof_steps):
+        step_device()
+        torch.cuda.synchronize(dev)
+        pr = eng.read_profile()
+        acc = pr if acc is None else {k: tuple(a + b for a, b in zip(acc[k], pr[k])) for k in pr}
+    prof = {k: tuple(x / prof_steps for x in v) for k, v in acc.items()}
+    eng.set_profile(False)
     for _ in range(2):
         step_host()
     sync_all()
@@ -434,7 +673,7 @@ def run_engine_qwen(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t) / args.steps
-    h2d = host["pixel_patches"].numel() * 4 + sum(v.numel() * 4 for v in idx.values()) + B * 4
+    h2d = (raw_u8.numel() if raw_u8 is not None else host["pixel_patches"].numel() * 4) + sum(v.numel() * 4 for v in idx.values()) + B * 4
     if rank == 0:
         peaks = measured_peaks()
         gemm_ms, gemm_flops, gemm_n, gemm_bytes = prof["gemm"]
@@ -455,8 +694,23 @@ def run_engine_qwen(args, rank, local_rank, world):
                                   flops_per_launch=gemm_flops / max(gemm_n, 1), peak_source=peaks["source"],
                                   whole_step_tflops=(value / world) * flops_pair / 1e12),
                     breakdown_ms={k: round(v[0], 3) for k, v in prof.items()},
-                    e2e=dict(value=total / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=B * 4, ms_per_step=e2e_ms),
+                    e2e=dict(value=total / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=B * 4, ms_per_step=e2e_ms,
+                             path=("QwenVLEngine: pinned uint8 images -> H2D -> vqa_qwen_preprocess" if raw_u8 is not None else
+                                   "QwenVLEngine: fp32 processor patch rows -> H2D") +
+                                  " -> qwen_host.build_batch_indices (host) -> H2D indices -> vqa_qwen25vl_score -> D2H scores"),
                     gpu_launches=int(launches) * args.steps, clocks=clocks, sample_scores=[float(x) for x in out[:4].float().cpu()])
+        if world == 1 and not args.no_hf_baseline:
+            try:
+                line["hf_gpu_baseline"] = hf_gpu_baseline_qwen(cfg, dev, host, video)
+                line["hf_gpu_baseline"]["speedup_value_over_hf"] = round(value / line["hf_gpu_baseline"]["value"], 2)
+            except Exception as e:  # noqa
+                line["hf_gpu_baseline"] = dict(value=None, unit="pairs/s", what=f"failed: {e!r}")
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = {k: v for k, v in cpu_reference_qwen(args.model, timed_pairs=3, budget_s=30.0, video=video).items()
+                                        if k != "seconds_per_pair"}
+            except Exception as e:  # noqa
+                line["cpu_baseline"] = dict(value=None, unit="pairs/s", cores=host_threads()[0], kind="port", sample=f"failed: {e!r}")
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -293,17 +293,39 @@ def qwen25vl_score(sd: Dict[str, torch.Tensor], cfg: Qwen25VLConfig, pixel_patch
 
 
 # ----------------------------------------------------------------------------------------------- synthetic weights / inputs
-def make_synthetic_state_dict(cfg: Qwen25VLConfig, seed: int = 0, dtype=torch.bfloat16, gen_device="cpu") -> Dict[str, torch.Tensor]:
+def make_synthetic_state_dict(cfg: Qwen25VLConfig, seed: int = 0, dtype=torch.bfloat16, gen_device="cpu",
+                              pool: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     # gen_device="cpu" is the seeded sequence behind the committed goldens; the full-width GPU tests draw 8 B parameters on the device
     gd = torch.device(gen_device)
     g = torch.Generator(device=gd).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
 
+    cursor = [0]
+
+    def randn(*shape):
+        if pool is None:
+            return torch.randn(*shape, generator=g, device=gd)
+        # timing-only weights (bench.py's CPU baseline): values cycled out of a small pre-drawn pool instead of 8 B fresh draws
+        n = 1
+        for d in shape:
+            n *= int(d)
+        P = pool.numel()
+        off = cursor[0] % P
+        cursor[0] += n + 7919
+        out = torch.empty(n, dtype=pool.dtype)
+        pos = min(P - off, n)
+        out[:pos] = pool[off:off + pos]
+        while pos < n:
+            m = min(P, n - pos)
+            out[pos:pos + m] = pool[:m]
+            pos += m
+        return out.view(*shape).to(gd)
+
     def nrm(name, *shape, std=0.02):
-        sd[name] = (torch.randn(*shape, generator=g, device=gd) * std).to(dtype)
+        sd[name] = (randn(*shape) * std).to(dtype)
 
     def gain(name, n):
-        sd[name] = (1.0 + 0.1 * torch.randn(n, generator=g, device=gd)).to(dtype)
+        sd[name] = (1.0 + 0.1 * randn(n)).to(dtype)
 
     D, v = cfg.vit_hidden, "model.visual."
     nrm(v + "patch_embed.proj.weight", D, 3, cfg.temporal_patch_size, cfg.patch_size, cfg.patch_size, std=cfg.patch_dim ** -0.5)

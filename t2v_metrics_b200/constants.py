@@ -9,10 +9,7 @@ HF_CACHE_DIR = "./hf_cache/"
 # longest token sequence the T5 tokenizer of the wrapper accepts (model_max_length of the v3.0 loader)
 CONTEXT_LEN = 2048
 # conversation header placed before " USER: <image>\n{question} ASSISTANT: " by format_question(..., 't5_chat')
-SYSTEM_MSG = " ".join([
-    "A chat between a curious user and an artificial intelligence assistant.",
-    "The assistant gives helpful, detailed, and polite answers to the user's questions.",
-])
+SYSTEM_MSG = "A chat between a curious user and an artificial intelligence assistant. The assistant gives helpful, detailed, and polite answers to the user's questions."
 # placeholder in the prompt text and the id it becomes in input_ids; the engine splices the 576 projected CLIP features there
 DEFAULT_IMAGE_TOKEN = "<image>"
 IMAGE_TOKEN_INDEX = -200

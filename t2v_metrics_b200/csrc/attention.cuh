@@ -1,9 +1,6 @@
-// Fused attention kernels for the CLIP-FlanT5 scoring path (head_dim = 64 everywhere on this path).
+// Small attention kernels of the T5 decoder rows (head_dim = 64). The encoder / vision-tower attention is the tcgen05 kernel in
+// attention_sm100.cuh.
 //
-//  * flash_attn_d64_kernel: bidirectional self-attention with (a) T5's learned relative-position bias read from a
-//    per-head [2S-1] table, no 1/sqrt(d) scale, key-padding mask (transformers/models/t5/modeling_t5.py:308-334),
-//    or (b) CLIP's plain scaled attention (transformers/models/clip/modeling_clip.py:261-336). Scores never
-//    touch HBM (the reference materialises [B,H,S,S] fp32). Online softmax in fp32.
 //  * t5_decoder_self_attn_kernel / t5_cross_attn_kernel: the decoder rows (causal self-attention with
 //    unidirectional buckets; cross-attention with zero bias + encoder padding mask, modeling_t5.py:312-325).
 #pragma once
@@ -11,234 +8,6 @@
 #include "elementwise.cuh"
 
 namespace vqa {
-
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
-    const uint32_t d = smem_u32(smem_dst);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(smem_u32(smem_ptr)));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(smem_u32(smem_ptr)));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-struct FlashParams {
-    const __nv_bfloat16* q;  // row (b*S + s), column h*64 + d, row stride ldq
-    const __nv_bfloat16* k;
-    const __nv_bfloat16* v;
-    __nv_bfloat16* o;        // [B*S, ldo], column h*64 + d
-    int ldq, ldk, ldv, ldo;
-    const int* seq_lens;     // [B] valid keys/queries per sample, or nullptr (all S valid)
-    const float* bias_table; // [H, 2S-1] or nullptr
-    int S, H;
-    float scale;             // multiplies q.k (1 for T5)
-    int round_scores;        // emulate the reference's bf16 matmul output / bias add rounding
-};
-
-constexpr int FA_BQ = 64, FA_BK = 64, FA_D = 64, FA_LD = 72;  // padded smem row stride (elements)
-
-// grid (ceil(S/64), H, B), 128 threads. Dynamic smem: (1 + 2 + 2) tiles * 64*72*2 B + (2S-1)*4 B.
-__global__ void __launch_bounds__(128) flash_attn_d64_kernel(const FlashParams p) {
-    extern __shared__ __align__(16) uint8_t fa_smem[];
-    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
-    __nv_bfloat16* sK = sQ + FA_BQ * FA_LD;           // [2][64][72]
-    __nv_bfloat16* sV = sK + 2 * FA_BK * FA_LD;       // [2][64][72]
-    float* sBias = reinterpret_cast<float*>(sV + 2 * FA_BK * FA_LD);
-
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t4 = lane & 3;
-    const int len = p.seq_lens ? p.seq_lens[b] : p.S;
-    const int q0 = qt * FA_BQ;
-    const size_t row_base = (size_t)b * p.S;
-
-    if (q0 >= len) {  // padded query tile: deterministic zeros
-        for (int i = tid; i < FA_BQ * 8; i += 128) {
-            const int r = i >> 3, c = i & 7;
-            if (q0 + r < p.S)
-                *reinterpret_cast<uint4*>(p.o + (row_base + q0 + r) * p.ldo + h * FA_D + c * 8) = make_uint4(0, 0, 0, 0);
-        }
-        return;
-    }
-
-    // ---- async loads: Q tile, then K/V tile 0
-    auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, int ld, int r0) {
-        for (int i = tid; i < 64 * 8; i += 128) {
-            const int r = i >> 3, c = i & 7;
-            const bool ok = (r0 + r) < len;
-            const __nv_bfloat16* gp = src + (row_base + (ok ? r0 + r : 0)) * ld + h * FA_D + c * 8;
-            cp_async_16(dst + r * FA_LD + c * 8, gp, ok);
-        }
-    };
-    load_tile(sQ, p.q, p.ldq, q0);
-    cp_async_commit();
-    const int num_kt = (len + FA_BK - 1) / FA_BK;
-    load_tile(sK, p.k, p.ldk, 0);
-    load_tile(sV, p.v, p.ldv, 0);
-    cp_async_commit();
-    const int bias_w = 2 * p.S - 1;
-    if (p.bias_table)
-        for (int i = tid; i < bias_w; i += 128) sBias[i] = p.bias_table[(size_t)h * bias_w + i];
-
-    cp_async_wait<1>();
-    __syncthreads();
-    uint32_t qf[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int c = ks * 16 + (lane >> 4) * 8;
-        ldmatrix_x4(qf[ks], sQ + r * FA_LD + c);
-    }
-
-    float o_acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o_acc[i][e] = 0.f;
-    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    const int qrow0 = q0 + warp * 16 + g;  // rows qrow0 and qrow0 + 8
-
-    for (int kt = 0; kt < num_kt; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < num_kt) {
-            load_tile(sK + (buf ^ 1) * FA_BK * FA_LD, p.k, p.ldk, (kt + 1) * FA_BK);
-            load_tile(sV + (buf ^ 1) * FA_BK * FA_LD, p.v, p.ldv, (kt + 1) * FA_BK);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const __nv_bfloat16* cK = sK + buf * FA_BK * FA_LD;
-        const __nv_bfloat16* cV = sV + buf * FA_BK * FA_LD;
-
-        // ---- S = Q K^T (16 x 64 per warp)
-        float s[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s[i][e] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                uint32_t kf[4];
-                const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
-                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
-                ldmatrix_x4(kf, cK + r * FA_LD + c);
-                mma_bf16_16816(s[2 * np], qf[ks], kf[0], kf[1]);
-                mma_bf16_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
-            }
-        }
-
-        // ---- scale / bias / mask, online softmax
-        float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int kcol = kt * FA_BK + nt * 8 + 2 * t4 + (e & 1);
-                const int qrow = qrow0 + (e >> 1) * 8;
-                float v = s[nt][e] * p.scale;
-                if (p.round_scores) v = bf16_round(v);
-                if (p.bias_table) {
-                    int bi = kcol - qrow + p.S - 1;
-                    bi = min(max(bi, 0), bias_w - 1);
-                    v += sBias[bi];
-                    if (p.round_scores) v = bf16_round(v);
-                }
-                if (kcol >= len) v = -INFINITY;
-                s[nt][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
-            }
-        }
-        float corr[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float m_new = fmaxf(m_run[r], mx[r]);   // finite: key 0 of tile 0 is always valid
-            corr[r] = __expf(m_run[r] - m_new);
-            m_run[r] = m_new;
-        }
-        float rs[2] = {0.f, 0.f};
-        uint32_t pf[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            float e0 = __expf(s[nt][0] - m_run[0]);
-            float e1 = __expf(s[nt][1] - m_run[0]);
-            float e2 = __expf(s[nt][2] - m_run[1]);
-            float e3 = __expf(s[nt][3] - m_run[1]);
-            rs[0] += e0 + e1;
-            rs[1] += e2 + e3;
-            const int kk = nt >> 1;
-            if ((nt & 1) == 0) { pf[kk][0] = pack_bf16x2(e0, e1); pf[kk][1] = pack_bf16x2(e2, e3); }
-            else               { pf[kk][2] = pack_bf16x2(e0, e1); pf[kk][3] = pack_bf16x2(e2, e3); }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-            l_run[r] = l_run[r] * corr[r] + rs[r];
-        }
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-            o_acc[dt][0] *= corr[0]; o_acc[dt][1] *= corr[0];
-            o_acc[dt][2] *= corr[1]; o_acc[dt][3] *= corr[1];
-        }
-        // ---- O += P V
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-                uint32_t vf[4];
-                const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int c = dp * 16 + (lane >> 4) * 8;
-                ldmatrix_x4_trans(vf, cV + r * FA_LD + c);
-                mma_bf16_16816(o_acc[2 * dp], pf[kk], vf[0], vf[1]);
-                mma_bf16_16816(o_acc[2 * dp + 1], pf[kk], vf[2], vf[3]);
-            }
-        }
-        __syncthreads();  // all warps done with buf before it is refilled
-    }
-
-    // ---- normalise and store
-    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-        const int col = h * FA_D + dt * 8 + 2 * t4;
-        if (qrow0 < p.S) {
-            const bool ok = qrow0 < len;
-            *reinterpret_cast<uint32_t*>(p.o + (row_base + qrow0) * p.ldo + col) =
-                ok ? pack_bf16x2(o_acc[dt][0] * inv0, o_acc[dt][1] * inv0) : 0u;
-        }
-        if (qrow0 + 8 < p.S) {
-            const bool ok = qrow0 + 8 < len;
-            *reinterpret_cast<uint32_t*>(p.o + (row_base + qrow0 + 8) * p.ldo + col) =
-                ok ? pack_bf16x2(o_acc[dt][2] * inv1, o_acc[dt][3] * inv1) : 0u;
-        }
-    }
-}
-
-inline size_t flash_smem_bytes(int S, bool has_bias) {
-    return (size_t)5 * FA_BQ * FA_LD * 2 + (has_bias ? (size_t)(2 * S - 1) * 4 : 0) + 16;
-}
 
 // Decoder self-attention over the T target positions of each pair (T = 2 for the "Yes" answer, tens of tokens in VisualGPTScore
 // mode where the caption itself is the target): causal, unidirectional relative buckets, no scale (modeling_t5.py:253-344).

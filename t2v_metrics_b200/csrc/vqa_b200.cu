@@ -112,43 +112,7 @@ static int fail(vqa_handle* h, int code, const std::string& msg) {
             return fail(h, VQA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
     } while (0)
 
-// ------------------------------------------------------------------------------------------------ debug GEMM
-// One thread per output element; used only when VQA_GEMM_SIMT=1 (bring-up aid to separate pipeline bugs from
-// tensor-core bugs). Same epilogue semantics as the tcgen05 kernel.
-__global__ void gemm_simt_debug_kernel(const bf16* A, int lda, const bf16* W, int ldw, GemmParams p, int epi) {
-    const int n_out = epi_is_gated(epi) ? p.N / 2 : p.N;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)p.M * n_out) return;
-    const int m = (int)(idx / n_out), n = (int)(idx % n_out);
-    const bf16* a = A + (size_t)m * lda;
-    auto dot = [&](const bf16* w) {
-        float acc = 0.f;
-        for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
-        return acc;
-    };
-    if (epi_is_gated(epi)) {
-        float g = dot(W + (size_t)n * ldw), u = dot(W + (size_t)(p.gate_up_offset + n) * ldw);
-        if (p.bias) { g += __bfloat162float(p.bias[n]); u += __bfloat162float(p.bias[p.gate_up_offset + n]); }
-        g = bf16_round(g); u = bf16_round(u);
-        const float a = (epi == EPI_GATED_GELU) ? act_gelu_new(g) : act_silu(g);
-        p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(bf16_round(a) * u);
-        return;
-    }
-    float acc = dot(W + (size_t)n * ldw);
-    if (p.bias) acc += __bfloat162float(p.bias[n]);
-    float y = bf16_round(acc);
-    if (epi == EPI_QUICK_GELU) y = act_quick_gelu(y);
-    if (epi == EPI_GELU_ERF) y = act_gelu_erf(y);
-    if (epi == EPI_RELU) y = fmaxf(y, 0.f);
-    if (p.residual) y += __bfloat162float(p.residual[(size_t)m * p.ldr + n]);
-    p.C[(size_t)m * p.ldc + n] = __float2bfloat16_rn(y);
-}
-
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
-static bool env_flag(const char* name) {
-    const char* v = getenv(name);
-    return v && v[0] && v[0] != '0';
-}
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && v[0]) ? atoi(v) : dflt;
@@ -194,12 +158,6 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
     g.p.M = M; g.p.N = N; g.p.K = K; g.p.C = C; g.p.ldc = ldc; g.p.bias = bias; g.p.residual = residual;
     g.p.ldr = ldr; g.p.gate_up_offset = gate_up_offset;
     if (launch_counter) ++*launch_counter;
-    static const bool simt = env_flag("VQA_GEMM_SIMT");
-    if (simt) {
-        const long total = (long)M * (epi_is_gated(epi) ? N / 2 : N);
-        gemm_simt_debug_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, lda, W, ldw, g.p, epi);
-        return cudaGetLastError();
-    }
     if (variant == 0) variant = pick_variant(M, N, epi);
     switch (epi) {
         case EPI_STORE:      return gemm_dispatch_variant<EPI_STORE>(g, variant, num_sms, st);

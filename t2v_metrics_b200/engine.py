@@ -7,6 +7,7 @@ current CUDA stream.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import Dict, Optional, Sequence
 
@@ -179,11 +180,12 @@ class ClipT5Engine:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         if out is None:
             out = torch.empty(B, dtype=torch.float32, device=dev)
-        logp = torch.empty(B, T, dtype=torch.float32, device=dev) if return_logprobs else None
+        logp = torch.zeros(B, T, dtype=torch.float32, device=dev) if return_logprobs else None   # ignored (-100) positions stay 0
         pdt = _lib.VQA_DTYPE_F32 if pixel_values.dtype == torch.float32 else _lib.VQA_DTYPE_BF16
-        rc = self.lib.vqa_clipt5_score(self._h, _ptr(pixel_values), pdt, NI, _ptr(image_index), _ptr(input_ids),
-                                       _ptr(text_lens), _ptr(labels), B, L, T, _ptr(out), _ptr(logp),
-                                       _ptr(self._workspace), self._workspace.numel(), _stream_ptr(dev))
+        with torch.cuda.device(dev):      # the library launches on the CURRENT device: make it the engine's (a process may drive several GPUs)
+            rc = self.lib.vqa_clipt5_score(self._h, _ptr(pixel_values), pdt, NI, _ptr(image_index), _ptr(input_ids),
+                                           _ptr(text_lens), _ptr(labels), B, L, T, _ptr(out), _ptr(logp),
+                                           _ptr(self._workspace), self._workspace.numel(), _stream_ptr(dev))
         _check(rc, self._h, "vqa_clipt5_score")
         return (out, logp) if return_logprobs else out
 
@@ -372,9 +374,10 @@ def clip_preprocess_u8(images: Sequence[torch.Tensor], out_size: int, device, pa
     bg = background if background is not None else tuple(int(x * 255) for x in mean)
     ring = _staging(dev)
     hs = ring.acquire(need)
-    rc = lib.vqa_clip_preprocess(_ptr(src), O, H, W, n, out_size, 1 if pad else 0, (C.c_uint8 * 3)(*bg), (C.c_float * 3)(*mean),
-                                 (C.c_float * 3)(*std), _ptr(out), _lib.VQA_DTYPE_F32 if out.dtype == torch.float32 else _lib.VQA_DTYPE_BF16,
-                                 _ptr(wsb), need, hs.data_ptr(), _stream_ptr(dev))
+    with torch.cuda.device(dev):
+        rc = lib.vqa_clip_preprocess(_ptr(src), O, H, W, n, out_size, 1 if pad else 0, (C.c_uint8 * 3)(*bg), (C.c_float * 3)(*mean),
+                                     (C.c_float * 3)(*std), _ptr(out), _lib.VQA_DTYPE_F32 if out.dtype == torch.float32 else _lib.VQA_DTYPE_BF16,
+                                     _ptr(wsb), need, hs.data_ptr(), _stream_ptr(dev))
     ring.release(dev)
     _check(rc, None, "vqa_clip_preprocess")
     # src / wsb stay referenced by the caching allocator's stream ordering: both were allocated on the current stream
@@ -425,10 +428,11 @@ def qwen_preprocess_u8(images: Sequence[torch.Tensor], device, patch: int = 14, 
     wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
     ring = _staging(dev)
     stage_buf = ring.acquire(wsb.numel())
-    rc = lib.vqa_qwen_preprocess(_ptr(src), (C.c_int64 * n)(*offs), (C.c_int32 * n)(*hs), (C.c_int32 * n)(*ws), n, patch, temporal_patch,
-                                 merge, min_pixels, max_pixels, (C.c_float * 3)(*mean), (C.c_float * 3)(*std), _ptr(out),
-                                 _lib.VQA_DTYPE_F32 if out_dtype == torch.float32 else _lib.VQA_DTYPE_BF16, _ptr(wsb), wsb.numel(),
-                                 stage_buf.data_ptr(), _stream_ptr(dev))
+    with torch.cuda.device(dev):
+        rc = lib.vqa_qwen_preprocess(_ptr(src), (C.c_int64 * n)(*offs), (C.c_int32 * n)(*hs), (C.c_int32 * n)(*ws), n, patch, temporal_patch,
+                                     merge, min_pixels, max_pixels, (C.c_float * 3)(*mean), (C.c_float * 3)(*std), _ptr(out),
+                                     _lib.VQA_DTYPE_F32 if out_dtype == torch.float32 else _lib.VQA_DTYPE_BF16, _ptr(wsb), wsb.numel(),
+                                     stage_buf.data_ptr(), _stream_ptr(dev))
     ring.release(dev)
     _check(rc, None, "vqa_qwen_preprocess")
     return out, grids
@@ -516,7 +520,7 @@ class QwenVLEngine:
                self._h, "vqa_qwen25vl_set_rope")
         self._weights: Dict[str, torch.Tensor] = {}
         self._workspace: Optional[torch.Tensor] = None
-        self._vision_cache: Dict[tuple, dict] = {}
+        self._vision_cache: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()   # per-batch index sets, LRU-bounded
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -538,6 +542,7 @@ class QwenVLEngine:
         key = tuple(tuple(int(x) for x in g) for g in grid_thw)
         hit = self._vision_cache.get(key)
         if hit is not None:
+            self._vision_cache.move_to_end(key)
             return hit
         cfg, dev = self.cfg, self.device
         merge, unit = cfg.spatial_merge_size, cfg.spatial_merge_size ** 2
@@ -551,6 +556,8 @@ class QwenVLEngine:
                    max_window=int((cu_win[1:] - cu_win[:-1]).max()), max_frame=int((cu_frames[1:] - cu_frames[:-1]).max()),
                    n_patches=L)
         self._vision_cache[key] = out
+        while len(self._vision_cache) > 64:          # a dataset with varied image sizes makes a new key per batch: keep the device memory bounded
+            self._vision_cache.popitem(last=False)
         return out
 
     def score_tensors(self, pixel_patches: torch.Tensor, grid_thw, input_ids: torch.Tensor, seq_lens: torch.Tensor,
@@ -575,12 +582,13 @@ class QwenVLEngine:
             out = torch.empty(B, dtype=torch.float32, device=dev)
         logp = torch.empty(B, dtype=torch.float32, device=dev) if return_logprobs else None
         pdt = _lib.VQA_DTYPE_F32 if pixel_patches.dtype == torch.float32 else _lib.VQA_DTYPE_BF16
-        rc = self.lib.vqa_qwen25vl_score(self._h, _ptr(pixel_patches), pdt, vi["n_patches"], _ptr(vi["vis_pos_hw"]),
-                                         _ptr(vi["window_index"]), _ptr(vi["reverse_index"]), _ptr(vi["cu_window"]), vi["n_windows"],
-                                         vi["max_window"], _ptr(vi["cu_frames"]), vi["n_frames"], vi["max_frame"], _ptr(input_ids),
-                                         _ptr(seq_lens), _ptr(feat_index), _ptr(position_ids), _ptr(answer_ids), B, S,
-                                         float(temperature), float(repetition_penalty), _ptr(out), _ptr(logp), _ptr(self._workspace), self._workspace.numel(),
-                                         _stream_ptr(dev))
+        with torch.cuda.device(dev):
+            rc = self.lib.vqa_qwen25vl_score(self._h, _ptr(pixel_patches), pdt, vi["n_patches"], _ptr(vi["vis_pos_hw"]),
+                                             _ptr(vi["window_index"]), _ptr(vi["reverse_index"]), _ptr(vi["cu_window"]), vi["n_windows"],
+                                             vi["max_window"], _ptr(vi["cu_frames"]), vi["n_frames"], vi["max_frame"], _ptr(input_ids),
+                                             _ptr(seq_lens), _ptr(feat_index), _ptr(position_ids), _ptr(answer_ids), B, S,
+                                             float(temperature), float(repetition_penalty), _ptr(out), _ptr(logp), _ptr(self._workspace),
+                                             self._workspace.numel(), _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_score")
         return (out, logp) if return_logprobs else out
 

@@ -47,8 +47,9 @@ class CLIPT5Model(VQAScoreModel):
 
     def __init__(self, model_name="clip-flant5-xxl", device="cuda", cache_dir=HF_CACHE_DIR, tokenizer=None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, config: Optional[ClipT5Config] = None,
-                 checkpoint: Optional[str] = None, **kwargs):
+                 checkpoint: Optional[str] = None, vision_tower_checkpoint: Optional[str] = None, **kwargs):
         assert model_name in CLIP_T5_MODELS
+        self._vision_checkpoint = vision_tower_checkpoint
         self._tokenizer_override = tokenizer
         self._state_dict = state_dict
         self._config_override = config
@@ -82,15 +83,12 @@ class CLIPT5Model(VQAScoreModel):
         self._state_dict = None
 
     def _load_checkpoint(self, path: str) -> Dict[str, torch.Tensor]:
-        import os
-        if os.path.isfile(path):
-            if path.endswith(".safetensors"):
-                from safetensors.torch import load_file
-                return load_file(path)
-            return torch.load(path, map_location="cpu")
-        raise FileNotFoundError(
-            f"CLIP-FlanT5 weights not found at {path!r}. This build has no network access: pass `checkpoint=` (a local "
-            "HF-named state dict) or `state_dict=` to VQAScore()/get_score_model().")
+        """`path`: a local weights file or a downloaded repository directory (index json + shards) of zhiqiulin/clip-flant5-*;
+        `vision_tower_checkpoint=`: the CLIP tower the reference loads separately when the checkpoint does not carry it
+        (openai/clip-vit-large-patch14-336, mm_utils.py:226-227)."""
+        from ...checkpoint import load_state_dict, normalise_clipt5_keys
+        vision = load_state_dict(self._vision_checkpoint) if self._vision_checkpoint else None
+        return normalise_clipt5_keys(load_state_dict(path), vision)
 
     # ---- pre-processing ------------------------------------------------------------------------------------------
     def load_images(self, image: List[str]) -> torch.Tensor:
@@ -109,6 +107,17 @@ class CLIPT5Model(VQAScoreModel):
         ids = [t5_tokenizer_image_token(q, self.tokenizer, chunk_cache=cache)[: self.context_len] for q in questions]
         labs = [t5_tokenizer_image_token(a, self.tokenizer, chunk_cache=cache)[: self.context_len] for a in answers]
         pad = getattr(self.tokenizer, "pad_token_id", 0) or 0
+        # The splice kernel replaces exactly ONE image slot per prompt and embeds every other id: a caption that itself contains the
+        # literal "<image>" would add a second slot (t5_tokenizer_image_token splits on it), and an id outside the vocabulary would index
+        # past the embedding table. Refuse both on the host.
+        for q, row in zip(questions, ids):
+            if sum(1 for t in row if t == IMAGE_TOKEN_INDEX) != 1:
+                raise ValueError(f"each prompt must contain exactly one {DEFAULT_IMAGE_TOKEN!r} placeholder (the caption must not contain it): {q!r}")
+            if any((t < 0 and t != IMAGE_TOKEN_INDEX) or t >= self.cfg.vocab for t in row):
+                raise ValueError("token id outside [0, vocab)")
+        for row in labs:
+            if any(t < 0 or t >= self.cfg.vocab for t in row):
+                raise ValueError(f"answer token id outside [0, vocab) (answers must not contain {DEFAULT_IMAGE_TOKEN!r})")
         L, T = max(map(len, ids)), max(map(len, labs))
         input_ids = torch.full((len(ids), L), pad, dtype=torch.int32)
         labels = torch.full((len(labs), T), IGNORE_INDEX, dtype=torch.int32)

@@ -20,16 +20,20 @@ from .vqa_model import VQAScoreModel
 QWEN2_VL_MODELS: Dict[str, dict] = {name: dict(model=dict(path=spec["weights"]), config=spec["config"]) for name, spec in _TABLE.items()}
 
 
+# Pixel bounds of the resize the reference applies BEFORE the HF processor: `process_vision_info` (qwen_vl_utils.vision_process.fetch_image)
+# calls smart_resize(h, w, factor=28, min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS) with MIN_PIXELS = 4 * 28 * 28 and
+# MAX_PIXELS = 16384 * 28 * 28, and the processor then runs with do_resize=False (reference qwen2vl_model.py:201-216), so the processor's own
+# 14*14*4*1280 ceiling never applies. qwen_vl_utils is an unpinned dependency that is not installed here: the two values are restated from
+# its source and exposed as constructor arguments (`min_pixels=`, `max_pixels=`) for other versions.
+QWEN_VL_UTILS_MIN_PIXELS = 4 * 28 * 28
+QWEN_VL_UTILS_MAX_PIXELS = 16384 * 28 * 28
+
+
 def _generation_config_penalty(checkpoint_path: str) -> float:
     """repetition_penalty of the generation_config.json stored beside the checkpoint (what `from_pretrained` would attach to
     `model.generation_config` in the reference, qwen2vl_model.py:116-130); 1.0 when there is none."""
-    import json, os
-    d = checkpoint_path if os.path.isdir(checkpoint_path) else os.path.dirname(checkpoint_path)
-    f = os.path.join(d, "generation_config.json")
-    if d and os.path.isfile(f):
-        with open(f) as fh:
-            return float(json.load(fh).get("repetition_penalty", 1.0) or 1.0)
-    return 1.0
+    from ...checkpoint import generation_config_value
+    return float(generation_config_value(checkpoint_path, "repetition_penalty", 1.0) or 1.0)
 
 
 class Qwen2VLModel(VQAScoreModel):
@@ -39,8 +43,10 @@ class Qwen2VLModel(VQAScoreModel):
 
     def __init__(self, model_name="qwen2.5-vl-7b", device="cuda", cache_dir=HF_CACHE_DIR, tokenizer=None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, config: Optional[Qwen25VLConfig] = None,
-                 checkpoint: Optional[str] = None, repetition_penalty: Optional[float] = None, **kwargs):
+                 checkpoint: Optional[str] = None, repetition_penalty: Optional[float] = None,
+                 min_pixels: int = QWEN_VL_UTILS_MIN_PIXELS, max_pixels: int = QWEN_VL_UTILS_MAX_PIXELS, **kwargs):
         assert model_name in QWEN2_VL_MODELS
+        self.min_pixels, self.max_pixels = int(min_pixels), int(max_pixels)
         # The reference's scores come out of `generate(..., output_scores=True)`, i.e. AFTER the logits processors the checkpoint's
         # generation_config.json configures (Qwen2.5-VL-Instruct ships repetition_penalty 1.05). None = read it from the
         # generation_config.json next to `checkpoint` when there is one, else 1.0 (off).
@@ -57,17 +63,12 @@ class Qwen2VLModel(VQAScoreModel):
         else:
             from transformers import AutoTokenizer
             self.tokenizer = AutoTokenizer.from_pretrained(spec["model"]["path"], cache_dir=self.cache_dir)
+        from ...checkpoint import load_state_dict, normalise_qwen_keys
         sd = self._state_dict
         if sd is None:
-            path = self._checkpoint or spec["model"]["path"]
-            import os
-            if not os.path.isfile(path):
-                raise FileNotFoundError(f"Qwen2.5-VL weights not found at {path!r}; pass `checkpoint=` or `state_dict=` (no network here)")
-            if path.endswith(".safetensors"):
-                from safetensors.torch import load_file
-                sd = load_file(path)
-            else:
-                sd = torch.load(path, map_location="cpu")
+            # a local file or a downloaded repository directory (index json + shards), as `from_pretrained(path)` takes (qwen2vl_model.py:116-130)
+            sd = load_state_dict(self._checkpoint or spec["model"]["path"])
+        sd = normalise_qwen_keys(sd)      # published checkpoints use `visual.*` / `model.layers.*`; transformers renames them while loading
         if self.repetition_penalty is None:
             self.repetition_penalty = _generation_config_penalty(self._checkpoint or spec["model"]["path"])
         dev = torch.device(self.device if self.device != "cuda" else "cuda:0")
@@ -82,15 +83,34 @@ class Qwen2VLModel(VQAScoreModel):
         # PIL decode on the host, everything else (smart_resize, PIL-exact bicubic, normalise, frame duplication, merge-order patch
         # rows) in ONE device kernel -- bit-identical to qwen_utils.qwen_image_to_patches, the CPU path the reference runs per image
         import numpy as np
+        from PIL import Image
         from ...engine import qwen_preprocess_u8
-        raw = [torch.from_numpy(np.ascontiguousarray(np.asarray(self.image_loader(p).convert("RGB"), dtype=np.uint8))) for p in image]
-        return qwen_preprocess_u8(raw, self.engine.device, self.cfg.patch_size, self.cfg.temporal_patch_size, self.cfg.spatial_merge_size)
+        raw = []
+        for p in image:
+            if p.lower().endswith(".npy"):
+                # the reference's Qwen path takes the array as RGB, no channel flip (qwen2vl_model.py:146-153); 4-D arrays are frame stacks
+                arr = np.load(p)
+                if arr.ndim == 4:
+                    raise NotImplementedError("4-D .npy frame stacks are video inputs: outside the B200 engine's hot-path scope")
+                if arr.ndim != 3:
+                    raise ValueError(f"Unexpected shape for NumPy array in {p}")
+                arr = np.asarray(Image.fromarray(arr.astype("uint8"), "RGB"), dtype=np.uint8)
+            else:
+                with Image.open(p) as im:
+                    arr = np.asarray(im.convert("RGB"), dtype=np.uint8)
+            raw.append(torch.from_numpy(np.ascontiguousarray(arr)))
+        return qwen_preprocess_u8(raw, self.engine.device, self.cfg.patch_size, self.cfg.temporal_patch_size, self.cfg.spatial_merge_size,
+                                  min_pixels=self.min_pixels, max_pixels=self.max_pixels)
 
     @torch.no_grad()
     def forward(self, images: List[str], texts: List[str], fps=None, question_template: str = default_question_template,
                 answer_template: str = default_answer_template, max_new_tokens: int = 1, temperature: float = 1.0,
                 debug: bool = False, repetition_penalty: Optional[float] = None) -> torch.Tensor:
         assert len(images) == len(texts), "Number of images/videos and texts must match"
+        if max_new_tokens != 1:
+            # With max_new_tokens = k > 1 the reference scores answer token i on the logits of generation step len(scores) - n + i, i.e.
+            # conditioned on its own GREEDY continuation (qwen2vl_model.py:259-289) -- a decode loop, not the single prefill this engine runs.
+            raise NotImplementedError("the B200 engine scores the first generated position only (max_new_tokens=1, the reference default)")
         questions = [question_template.format(t) for t in texts]
         answers = [answer_template.format(t) for t in texts]
         uniq: Dict[str, int] = {}
@@ -109,7 +129,9 @@ class Qwen2VLModel(VQAScoreModel):
                 ids = cache[("answer", a)] = tuple(self.tokenizer.encode(a, add_special_tokens=False))
             if not ids:
                 raise ValueError("empty answer")
-            answer_ids.append(ids[0])      # max_new_tokens=1: only the first answer token is ever scored (qwen2vl_model.py:259-263)
+            # one generated position => the reference truncates a multi-token answer to its first token ("Generated 1 tokens but need n,
+            # adjusting", qwen2vl_model.py:259-263) and the geometric mean over one token is that token's probability
+            answer_ids.append(ids[0])
         probs = self.engine.score_prompts(patches, grids, prompts, answer_ids, image_of_sample=index, temperature=temperature,
                                           repetition_penalty=self.repetition_penalty if repetition_penalty is None else repetition_penalty)
         return probs.float().cpu()

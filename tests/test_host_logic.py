@@ -166,3 +166,92 @@ def test_image_loader_cases(tmp_path):
     assert (np.asarray(image_loader(str(tmp_path / "x.npy"))) == a[:, :, ::-1]).all()
     assert (np.asarray(image_loader(str(tmp_path / "x.png"))) == a).all()
     assert np.asarray(image_loader(str(tmp_path / "g.png"))).shape == (4, 5, 3)
+
+
+def test_checkpoint_directory_shards_and_key_names(tmp_path):
+    """mm_utils.py:182-241 / qwen2vl_model.py:110-133 load HF repository directories: index json + shards, on-disk tensor names. The
+    loader returns the in-memory HF names the engine converters consume, for either naming."""
+    import json
+    from safetensors.torch import save_file
+    from oracle import qwen25vl_oracle as qo
+    from t2v_metrics_b200 import checkpoint as ck
+    cfg = qo.Qwen25VLConfig.tiny()
+    sd = qo.make_synthetic_state_dict(cfg)
+    disk = {}
+    for k, v in sd.items():           # the names published Qwen2.5-VL checkpoints carry on disk
+        if k.startswith("model.visual."):
+            disk[k[len("model."):]] = v
+        elif k.startswith("model.language_model."):
+            disk["model." + k[len("model.language_model."):]] = v
+        else:
+            disk[k] = v
+    keys = sorted(disk)
+    wm = {}
+    for i, part in enumerate((keys[: len(keys) // 2], keys[len(keys) // 2:])):
+        name = f"model-0000{i + 1}-of-00002.safetensors"
+        save_file({k: disk[k].contiguous() for k in part}, str(tmp_path / name))
+        wm.update({k: name for k in part})
+    (tmp_path / "model.safetensors.index.json").write_text(json.dumps(dict(metadata={}, weight_map=wm)))
+    (tmp_path / "generation_config.json").write_text(json.dumps(dict(repetition_penalty=1.05)))
+    back = ck.normalise_qwen_keys(ck.load_state_dict(str(tmp_path)))
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert set(ck.normalise_qwen_keys(sd)) == set(sd)                                  # already in-memory names: unchanged
+    assert ck.generation_config_value(str(tmp_path), "repetition_penalty", 1.0) == 1.05
+    assert ck.generation_config_value(str(tmp_path / "model-00001-of-00002.safetensors"), "repetition_penalty", 1.0) == 1.05
+    with pytest.raises(FileNotFoundError, match="no network"):
+        ck.load_state_dict(str(tmp_path / "absent"))
+    # CLIP-FlanT5: LLaVA-style nesting, vision tower inside the checkpoint or loaded separately (mm_utils.py:226-227)
+    c = orc.ClipT5Config.tiny()
+    s = orc.make_synthetic_state_dict(c)
+    llava, vis = {}, {}
+    for k, v in s.items():
+        if k.startswith("vision_tower."):
+            vis[k[len("vision_tower."):]] = v
+        elif k.startswith("mm_projector."):
+            llava["model." + k] = v
+        else:
+            llava[k] = v
+    assert set(ck.normalise_clipt5_keys(llava, vis)) == set(s)
+    nested = dict(llava, **{"model.vision_tower.vision_tower." + k: v for k, v in vis.items()})
+    assert set(ck.normalise_clipt5_keys(nested)) == set(s)
+    with pytest.raises(KeyError, match="vision_tower_checkpoint"):
+        ck.normalise_clipt5_keys(llava)
+
+
+def test_qwen_resize_bounds_follow_qwen_vl_utils_not_the_hf_processor():
+    """The reference resizes in qwen_vl_utils.process_vision_info (MIN_PIXELS = 4*28*28, MAX_PIXELS = 16384*28*28) and calls the HF
+    processor with do_resize=False (reference qwen2vl_model.py:201-216): the processor's 14*14*4*1280 ceiling must not apply. The
+    reference's own images/0.png (1920 x 1280) is above that ceiling."""
+    from t2v_metrics_b200.engine import qwen_preprocess_plan
+    from t2v_metrics_b200.models.vqascore_models import qwen2vl_model as qm
+    from t2v_metrics_b200.models.vqascore_models.qwen_utils import smart_resize
+    assert (qm.QWEN_VL_UTILS_MIN_PIXELS, qm.QWEN_VL_UTILS_MAX_PIXELS) == (3136, 12845056)
+    ref_like = smart_resize(1280, 1920, 28, qm.QWEN_VL_UTILS_MIN_PIXELS, qm.QWEN_VL_UTILS_MAX_PIXELS)
+    assert ref_like == (1288, 1932)                                       # round to multiples of 28, no down-scaling
+    hf_default = smart_resize(1280, 1920)                                 # the processor's own bound: scaled down to <= 1 003 520 pixels
+    assert hf_default[0] * hf_default[1] <= 14 * 14 * 4 * 1280 < ref_like[0] * ref_like[1]
+    assert smart_resize(1024, 1024, 28, qm.QWEN_VL_UTILS_MIN_PIXELS, qm.QWEN_VL_UTILS_MAX_PIXELS) == (1036, 1036)   # ADVICE r1: 1369 tokens, not 1225
+    for bounds in ((qm.QWEN_VL_UTILS_MIN_PIXELS, qm.QWEN_VL_UTILS_MAX_PIXELS), (56 * 56, 14 * 14 * 4 * 1280)):
+        sizes = [(1280, 1920), (1275, 1920), (1024, 1024), (20, 30), (5000, 4000)]
+        grids, _, _ = qwen_preprocess_plan(sizes, min_pixels=bounds[0], max_pixels=bounds[1])   # the C++ plan the device kernel uses
+        assert [(g[1] * 14, g[2] * 14) for g in grids] == [smart_resize(h, w, 28, *bounds) for h, w in sizes]
+    import inspect
+    sig = inspect.signature(qm.Qwen2VLModel.__init__)
+    assert sig.parameters["max_pixels"].default == qm.QWEN_VL_UTILS_MAX_PIXELS and sig.parameters["min_pixels"].default == qm.QWEN_VL_UTILS_MIN_PIXELS
+
+
+def test_plugins_refuse_inputs_the_kernels_cannot_take():
+    """a caption containing '<image>' adds a second image slot (the splice kernel handles exactly one); Qwen max_new_tokens > 1
+    needs the reference's greedy decode loop. Both must fail loudly on the host, before anything is launched."""
+    from t2v_metrics_b200.models.vqascore_models import qwen2vl_model as qm
+    fake = types.SimpleNamespace(tokenizer=FakeTok(), context_len=2048, cfg=types.SimpleNamespace(vocab=32128))
+    q = format_question('Does this figure show "{}"? Please answer yes or no.'.format("a dog"))
+    ids, lens, labels = CLIPT5Model._tokenize(fake, [q], ["Yes"])
+    assert int((ids == -200).sum()) == 1 and int(lens[0]) == ids.shape[1]
+    bad = format_question('Does this figure show "{}"? Please answer yes or no.'.format("a dog <image> and a cat"))
+    with pytest.raises(ValueError, match="exactly one"):
+        CLIPT5Model._tokenize(fake, [bad], ["Yes"])
+    with pytest.raises(ValueError, match="answer"):
+        CLIPT5Model._tokenize(fake, [q], ["<image>"])
+    with pytest.raises(NotImplementedError, match="max_new_tokens=1"):
+        qm.Qwen2VLModel.forward(types.SimpleNamespace(), ["a.png"], ["a dog"], max_new_tokens=2)
