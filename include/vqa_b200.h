@@ -186,7 +186,7 @@ int vqa_profile_read(vqa_handle* h, float* ms, double* flops, double* bytes, int
 /* Parity investigation aids: byte offsets, inside the caller-owned workspace of a call with the same sizes, of intermediate tensors
  * that the reference exposes too (encoder_last_hidden_state, decoder_hidden_states[-1], ...). Valid after the stream has passed
  * the scoring call. CLIP-FlanT5 (n >= 6): {encoder output, decoder output (both after the final T5LayerNorm), projector output,
- * encoder / decoder residual streams, last vision-tower hidden state}. Qwen2.5-VL (n >= 4): {last-position hidden state after the
+ * encoder / decoder residual streams, last vision-tower hidden state (fp32)}. Qwen2.5-VL (n >= 4): {last-position hidden state after the
  * final norm, merged vision features, residual stream, last-position residual}. */
 int vqa_clipt5_debug_layout(vqa_handle* h, int32_t batch, int32_t n_images, int32_t text_len, int32_t label_len, size_t* offsets,
                             int32_t n);
@@ -251,9 +251,17 @@ int vqa_op_lmhead_logprob(const void* H, int32_t ldh, const void* W, int32_t ldw
 /* Bidirectional attention, head_dim 64, packed qkv [B*S, 3*H*64] -> out [B*S, H*64].
  * bias_table: DEVICE float [H, 2S-1] (index key - query + S - 1) or NULL; seq_lens DEVICE int32 [B] or NULL.
  * bias_const_from > 0: the caller guarantees bias_table[h][.] is constant for |key - query| >= bias_const_from on each side (T5's
- * relative_attention_max_distance, modeling_t5.py:189-234), which lets far key tiles fold the bias into one FFMA; 0: no assumption. */
+ * relative_attention_max_distance, modeling_t5.py:189-234), which lets far key tiles fold the bias into one FFMA; 0: no assumption.
+ * round_scores != 0: reproduce the bf16 tensors the reference's eager attention forms before its fp32 softmax (q.k^T as bf16, then the
+ * bf16 `scores += position_bias`, modeling_t5.py:308-331); 0: scores and bias stay fp32. */
 int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                         const float* bias_table, float scale, int32_t bias_const_from, void* stream);
+                         const float* bias_table, float scale, int32_t bias_const_from, int32_t round_scores, void* stream);
+
+/* Instrumented run of the T5-encoder attention kernel (bias table, score rounding on): counters = DEVICE uint64[9], zeroed by the
+ * caller; afterwards cycles summed over one softmax warp per CTA in {wait S, TMEM load, max + vote, wait O / rescale, exp2 + P store,
+ * store wait + arrive, epilogue, total} and [8] = key tiles those warps went through (tools/bench_kernels.py attn-phases). */
+int vqa_debug_attention_d64_phases(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
+                                   const float* bias_table, int32_t bias_const_from, uint64_t* counters, void* stream);
 
 /* T5LayerNorm / nn.LayerNorm on [rows, D] bf16. beta == NULL selects T5 RMS norm. */
 int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,

@@ -31,7 +31,7 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
-constexpr int ATTN_POLY_DEFAULT = 2;   // score pairs of every 8 whose exp2 runs on the FMA pipe (0, 2 or 3)
+constexpr int ATTN_POLY_DEFAULT = 0;   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
 
 inline size_t attn_tc_smem_bytes(int S) {
     return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
@@ -432,11 +432,13 @@ struct AttnTc2Params {
     int S, H, q_col0, k_col0, v_col0;
     float scale_log2e;
     int near_tiles;     // key tiles with |kt - qt| <= near_tiles read the bias table; beyond, the table's end values (constant there)
+    float scale;        // ROUND kernels: softmax scale applied after the bf16 rounding of the scores (1 for T5, 1/8 for CLIP)
+    unsigned long long* prof;   // PROF kernels only: 8 cycle counters summed over the quad-0 softmax warps of all CTAs (tools/bench_kernels.py)
 };
 
-inline size_t attn_tc2_smem_bytes(int near_tiles, bool has_bias) {
+inline size_t attn_tc2_smem_bytes(int near_tiles, bool has_bias, bool round_scores) {
     const size_t nq = has_bias ? (size_t)(2 * (128 * near_tiles + 127) + 1) : 0;
-    return 1024 + 6 * AT_TILE_BYTES + nq * 16 + 32 /*reduction scratch*/ + 14 * 8 + 16;
+    return 1024 + 6 * AT_TILE_BYTES + ((nq * (round_scores ? 8 : 16) + 15) & ~size_t(15)) + 32 /*reduction scratch*/ + 14 * 8 + 16;
 }
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -480,24 +482,52 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(y1) << 23));
 }
 
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 // One 32-key chunk of the exponential pass: sv = raw scores (fp32 bits) of this thread's row, out = 16 packed bf16 pairs of P.
-//   NEAR:  t = s * c + bias[j] - m      (bias from the sliding-window table)
-//   !NEAR: t = s * c + addc             (addc = constant bias - m)
-template <bool NEAR, int POLY>
+//   !ROUND:  NEAR   t = s * c + bias_log2[j] - m           (fp32 log2-domain bias from the sliding-window table, LDS.128 per 4 keys)
+//            !NEAR  t = s * c + addc                       (addc = constant bias (log2 domain) - m)
+//   ROUND :  the reference's eager attention produces bf16 tensors before its fp32 softmax (modeling_t5.py:308-331: `scores = matmul(q, k^T)`
+//            is a bf16 tensor, `scores += position_bias` a bf16 add; modeling_clip.py: bf16 matmul * 2^-3). With |score| ~ 10 that rounding
+//            moves the exponent's argument by up to 0.04, far more than any other rounding on the path, so parity needs the same values:
+//            x = bf16(s);  NEAR: x = bf16(x + bias[j]) (HADD2.BF16, bias in natural units from a bf16 sliding-window table, LDS.64 per 4 keys);
+//            !NEAR with bias: x = bf16(x + bconst);  t = x * c - m with c = scale * log2(e).
+template <bool NEAR, int POLY, bool ROUND>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t (&pk)[16], uint32_t bq /*shared-space byte address*/,
-                                              uint64_t cc, uint64_t addc, uint64_t& acc0, uint64_t& acc1) {
+                                              uint64_t cc, uint64_t addc, uint32_t bconst2 /*ROUND: far bias as bf16x2*/, bool far_bias,
+                                              uint64_t& acc0, uint64_t& acc1) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        uint64_t t0 = pack2(__uint_as_float(sv[4 * q]), __uint_as_float(sv[4 * q + 1]));
-        uint64_t t1 = pack2(__uint_as_float(sv[4 * q + 2]), __uint_as_float(sv[4 * q + 3]));
-        if (NEAR) {
-            uint64_t b01, b23;   // four consecutive biases of this row: one conflict-free LDS.128 (see the kernel's header comment)
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bq + q * 64));
-            t0 = fadd2(ffma2(t0, cc, b01), addc);
-            t1 = fadd2(ffma2(t1, cc, b23), addc);
+        uint64_t t0, t1;
+        if constexpr (ROUND) {
+            uint32_t x01 = pack_bf16x2(__uint_as_float(sv[4 * q]), __uint_as_float(sv[4 * q + 1]));
+            uint32_t x23 = pack_bf16x2(__uint_as_float(sv[4 * q + 2]), __uint_as_float(sv[4 * q + 3]));
+            if (NEAR) {
+                uint32_t b01, b23;
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b01), "=r"(b23) : "r"(bq + q * 32));
+                x01 = hadd2_bf16(x01, b01);
+                x23 = hadd2_bf16(x23, b23);
+            } else if (far_bias) {
+                x01 = hadd2_bf16(x01, bconst2);
+                x23 = hadd2_bf16(x23, bconst2);
+            }
+            t0 = ffma2(pack2(__uint_as_float(x01 << 16), __uint_as_float(x01 & 0xffff0000u)), cc, addc);
+            t1 = ffma2(pack2(__uint_as_float(x23 << 16), __uint_as_float(x23 & 0xffff0000u)), cc, addc);
         } else {
-            t0 = ffma2(t0, cc, addc);
-            t1 = ffma2(t1, cc, addc);
+            t0 = pack2(__uint_as_float(sv[4 * q]), __uint_as_float(sv[4 * q + 1]));
+            t1 = pack2(__uint_as_float(sv[4 * q + 2]), __uint_as_float(sv[4 * q + 3]));
+            if (NEAR) {
+                uint64_t b01, b23;   // four consecutive biases of this row: one conflict-free LDS.128 (see the kernel's header comment)
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bq + q * 64));
+                t0 = fadd2(ffma2(t0, cc, b01), addc);
+                t1 = fadd2(ffma2(t1, cc, b23), addc);
+            } else {
+                t0 = ffma2(t0, cc, addc);
+                t1 = ffma2(t1, cc, addc);
+            }
         }
         float e0, e1, e2, e3;
         // pairs 2q and 2q+1 of this chunk's 16: POLY of every 8 pairs go to the FMA pipe, spread so MUFU and FMA work interleave
@@ -512,7 +542,8 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t
     }
 }
 
-template <bool HAS_BIAS, int POLY>
+// PROF: clock64() stamps around the phases of the softmax loop (one warp per CTA reports), for the phase table in profiles/.
+template <bool HAS_BIAS, int POLY, bool ROUND, bool PROF = false>
 __global__ void __launch_bounds__(192, 2)
 attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
     const int h = blockIdx.y, b = blockIdx.z;
@@ -534,10 +565,12 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
     uint8_t* sQ = smem;                          // [2]
     uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
     uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
-    float4* sBiasQ = reinterpret_cast<float4*>(smem + 6 * AT_TILE_BYTES);   // Q[x] = log2e * (b[x-W], .., b[x-W+3]), x in [0, 2W]
+    // sliding-window bias table, entry x <-> rel = x - W: !ROUND: float4 log2e * (b[rel], .., b[rel+3]); ROUND: the same four as bf16 (8 bytes)
+    uint8_t* sBiasQ = smem + 6 * AT_TILE_BYTES;
+    constexpr uint32_t BQ_ENTRY = ROUND ? 8u : 16u;
     const int Wn = 128 * p.near_tiles + 127;
     const int nQ = HAS_BIAS ? 2 * Wn + 1 : 0;
-    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (size_t)nQ * 16);   // [8]
+    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (((size_t)nQ * BQ_ENTRY + 15) & ~size_t(15)));   // [8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8);
     uint64_t* q_full = bars;          // [2]
     uint64_t* q_empty = bars + 2;     // [2]
@@ -575,21 +608,23 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
         tmem_relinquish<1>();
     }
     const float LOG2E = 1.4426950408889634f;
-    float b_left = 0.f, b_right = 0.f;      // constant bias (log2 domain) of far tiles to the left / right of the diagonal
+    const float BSC = ROUND ? 1.0f : LOG2E;   // domain the table / constants are kept in
+    float b_left = 0.f, b_right = 0.f;      // constant bias of far tiles to the left / right of the diagonal
     if (HAS_BIAS) {
         const int width = 2 * p.S - 1;
         const float* src = p.bias_table + (size_t)h * width;
-        b_left = __ldg(src) * LOG2E;
-        b_right = __ldg(src + width - 1) * LOG2E;
+        b_left = __ldg(src) * BSC;
+        b_right = __ldg(src + width - 1) * BSC;
         float lmax = -INFINITY;
         for (int x = threadIdx.x; x < nQ; x += blockDim.x) {
             float v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int idx = min(max(x + k - Wn + (p.S - 1), 0), width - 1);   // rel = x + k - W, clamped to the table
-                v[k] = __ldg(src + idx) * LOG2E;
+                v[k] = __ldg(src + idx) * BSC;
             }
-            sBiasQ[x] = make_float4(v[0], v[1], v[2], v[3]);
+            if constexpr (ROUND) reinterpret_cast<uint2*>(sBiasQ)[x] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            else                 reinterpret_cast<float4*>(sBiasQ)[x] = make_float4(v[0], v[1], v[2], v[3]);
             lmax = fmaxf(lmax, v[0]);
         }
 #pragma unroll
@@ -675,6 +710,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
             for (int i = 1; i < 6; ++i) bmax_near = fmaxf(bmax_near, sRed[i]);
         }
         const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
+        const uint32_t bl2 = pack_bf16x2(b_left, b_left), br2 = pack_bf16x2(b_right, b_right);   // ROUND: far-tile bias as bf16 pairs
         int g = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int q0 = qi * AT_BQ;
@@ -700,18 +736,24 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                 continue;
             }
             float m_run = -INFINITY, l_run = 0.f;
+            long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = 0;
+            if constexpr (PROF) tq0 = clock64();
             for (int j = 0; j < nkt; ++j, ++g) {
                 const int k0 = j * AT_BK;
                 const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
                 const int dt = j - qi;
                 const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
+                long long t0 = 0, t1 = 0;
+                if constexpr (PROF) t0 = clock64();
                 mbar_wait(s_full, (uint32_t)g & 1u);
                 tcgen05_fence_after();
+                if constexpr (PROF) { t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
                 uint32_t sv[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if (c < nch) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
                 tmem_ld_wait();
+                if constexpr (PROF) { t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
                 // S is in registers: hand the TMEM columns back so the next QK^T can start
                 tcgen05_fence_before();
                 __syncwarp();
@@ -737,7 +779,10 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                     }
                 }
                 const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
-                const float tile_max = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), p.scale_log2e, bias_ub);
+                const float raw_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // upper bound of this tile's exponent arguments (log2 domain); ROUND: the bf16 roundings move a value by < 2^-7 relative,
+                // well inside the 2^8 headroom of the lazy rescale
+                const float tile_max = ROUND ? (raw_max + bias_ub) * p.scale_log2e : fmaf(raw_max, p.scale_log2e, bias_ub);
                 // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
                 float corr = 1.f;
                 bool rescale = false;
@@ -752,6 +797,7 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                         m_run = m_new;
                     }
                 }
+                if constexpr (PROF) { t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
                 if (j > 0) {
                     mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
                     tcgen05_fence_after();
@@ -767,15 +813,16 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                         }
                     }
                 }
+                if constexpr (PROF) { t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
                 // ---- pass 2: exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
                 uint64_t acc0 = 0ull, acc1 = 0ull;
                 if (near) {
                     const uint64_t negm = pack2(-m_run, -m_run);
-                    const uint32_t bq = smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * 16u;
+                    const uint32_t bq = smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * BQ_ENTRY;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t pk[16];
-                        if (c < nch) softmax_chunk<true, POLY>(sv[c], pk, bq + c * 512, cc, negm, acc0, acc1);
+                        if (c < nch) softmax_chunk<true, POLY, ROUND>(sv[c], pk, bq + c * 32 * BQ_ENTRY, cc, negm, 0u, false, acc0, acc1);
                         else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -783,12 +830,12 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                         tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
                     }
                 } else {
-                    const float a = (dt < 0 ? b_left : b_right) - m_run;
+                    const float a = ROUND ? -m_run : (dt < 0 ? b_left : b_right) - m_run;
                     const uint64_t addc = pack2(a, a);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t pk[16];
-                        if (c < nch) softmax_chunk<false, POLY>(sv[c], pk, 0u, cc, addc, acc0, acc1);
+                        if (c < nch) softmax_chunk<false, POLY, ROUND>(sv[c], pk, 0u, cc, addc, dt < 0 ? bl2 : br2, HAS_BIAS, acc0, acc1);
                         else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) pk[i] = 0u;
@@ -844,9 +891,9 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
 // qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
 // bias_const_from: the bias table is constant (per head and side) for |key - query| >= bias_const_from (T5: relative_attention_max_distance);
 // <= 0 or >= S: no such guarantee, every tile reads the table.
-template <bool HAS_BIAS, int POLY>
+template <bool HAS_BIAS, int POLY, bool ROUND>
 inline cudaError_t launch_attn_tc2_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
-    auto kernel = attn_tc_d64_kernel<HAS_BIAS, POLY>;
+    auto kernel = attn_tc_d64_kernel<HAS_BIAS, POLY, ROUND>;
     static std::atomic<size_t> max_set[64];   // per device: largest dynamic smem size opted into so far
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -861,9 +908,10 @@ inline cudaError_t launch_attn_tc2_t(const CUtensorMap& tm, const AttnTc2Params&
     return cudaGetLastError();
 }
 
+// round_scores: reproduce the bf16 tensors of the reference's eager attention (scores, scores + bias) before the fp32 softmax.
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
                                   int B, int S, int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
-                                  cudaStream_t stream) {
+                                  bool round_scores, cudaStream_t stream, unsigned long long* prof = nullptr) {
     CUtensorMap tm;
     if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
     static const int variant = [] { const char* v = getenv("VQA_ATTN_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();
@@ -881,24 +929,29 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         else            attn_tc_d64_v1_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
         return cudaGetLastError();
     }
+    if (variant == 20) round_scores = false;      // A/B: v2 without the score rounding
+    if (variant == 21) round_scores = true;
     AttnTc2Params p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
+    p.scale = scale;
     const int n_tiles = (S + 127) / 128;
     int near = n_tiles;                                  // every tile reads the table
     if (bias_table && bias_const_from > 0 && bias_const_from < S) near = min(n_tiles, (bias_const_from - 1 + 127) / 128);
     p.near_tiles = bias_table ? near : 0;
-    const size_t smem = attn_tc2_smem_bytes(p.near_tiles, bias_table != nullptr);
-    const int poly = variant >= 10 ? variant - 10 : ATTN_POLY_DEFAULT;   // VQA_ATTN_VARIANT=10/12/13: POLY 0/2/3
-    if (bias_table) {
-        if (poly == 0) return launch_attn_tc2_t<true, 0>(tm, p, B, smem, stream);
-        if (poly == 2) return launch_attn_tc2_t<true, 2>(tm, p, B, smem, stream);
-        return launch_attn_tc2_t<true, 3>(tm, p, B, smem, stream);
+    p.prof = prof;
+    const size_t smem = attn_tc2_smem_bytes(p.near_tiles, bias_table != nullptr, round_scores);
+    if (prof) {   // instrumented build of the T5 variant (bias + rounding) only
+        if (!bias_table || !round_scores) return cudaErrorInvalidValue;
+        auto kernel = attn_tc_d64_kernel<true, 0, true, true>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<dim3(1, H, B), 192, smem, stream>>>(tm, p);
+        return cudaGetLastError();
     }
-    if (poly == 0) return launch_attn_tc2_t<false, 0>(tm, p, B, smem, stream);
-    if (poly == 2) return launch_attn_tc2_t<false, 2>(tm, p, B, smem, stream);
-    return launch_attn_tc2_t<false, 3>(tm, p, B, smem, stream);
+    if (bias_table) return round_scores ? launch_attn_tc2_t<true, 0, true>(tm, p, B, smem, stream) : launch_attn_tc2_t<true, 0, false>(tm, p, B, smem, stream);
+    return round_scores ? launch_attn_tc2_t<false, 0, true>(tm, p, B, smem, stream) : launch_attn_tc2_t<false, 0, false>(tm, p, B, smem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -920,7 +973,9 @@ constexpr int A8_BLOCK = 128 * 64 * 2;       // 16 KB
 constexpr int A8_TMEM_COLS = 512;            // S [0,128)  O [128,256)  P [256,320)
 inline size_t attn_tc128_smem_bytes() { return 1024 + 5 * A8_TILE + 128; }
 
-template <bool CAUSAL>
+// POLY >= 0: the v2 softmax stage of the d64 kernel above (raw-score FMNMX3 maximum, packed FFMA2 scale/reference, POLY of every 8 score
+// pairs exponentiated on the FMA pipe, one TMEM wait per tile); POLY = -1: the round-1 stage (A/B reference).
+template <bool CAUSAL, int POLY>
 __global__ void __launch_bounds__(192, 1)
 attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc128Params p) {
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -1039,6 +1094,89 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
         const int qrow = q0 + row;
         const uint32_t lane_off = (quad * 32u) << 16;
         float m_run = -INFINITY, l_run = 0.f;
+        if constexpr (POLY >= 0) {
+            const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
+            for (int j = 0; j < nkt; ++j) {
+                const int k0 = j * 128;
+                mbar_wait(s_full, (uint32_t)j & 1u);
+                tcgen05_fence_after();
+                uint32_t sv[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
+
+                const bool edge = (k0 + 128 > len) || (CAUSAL && j == qt);
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (edge) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kcol = k0 + c * 32 + i;
+                            if (kcol >= len || (CAUSAL && kcol > qrow)) sv[c][i] = 0xff800000u;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        mx0 = fmax3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+                        mx1 = fmax3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+                        mx2 = fmax3(mx2, __uint_as_float(sv[c][i + 4]), __uint_as_float(sv[c][i + 5]));
+                        mx3 = fmax3(mx3, __uint_as_float(sv[c][i + 6]), __uint_as_float(sv[c][i + 7]));
+                    }
+                }
+                float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2e;
+                if (!(tile_max > -1e30f)) tile_max = -1e30f;   // a padded query row may see no key at all in this tile (-inf * scale)
+                float corr = 1.f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_run = tile_max;
+                } else {
+                    const bool need = tile_max > m_run + 8.f;
+                    rescale = __any_sync(0xffffffffu, need);
+                    if (rescale) {
+                        const float m_new = fmaxf(m_run, tile_max);
+                        corr = fast_exp2(m_run - m_new);
+                        m_run = m_new;
+                    }
+                }
+                if (j > 0) {
+                    mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
+                    tcgen05_fence_after();
+                    if (rescale) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                        }
+                    }
+                }
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                const uint64_t addc = pack2(-m_run, -m_run);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+                    softmax_chunk<false, POLY, false>(sv[c], pk, 0u, cc, addc, 0u, false, acc0, acc1);
+                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                }
+                {
+                    float a0, a1, a2, a3;
+                    unpack2(acc0, a0, a1);
+                    unpack2(acc1, a2, a3);
+                    l_run = l_run * corr + ((a0 + a1) + (a2 + a3));
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+        } else {
         for (int j = 0; j < nkt; ++j) {
             const int k0 = j * 128;
             mbar_wait(s_full, (uint32_t)j & 1u);
@@ -1123,6 +1261,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
+        }
         mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
         tcgen05_fence_after();
         const float inv = (qrow < len && l_run > 0.f) ? 1.f / l_run : 0.f;
@@ -1155,23 +1294,32 @@ inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long
                                      __nv_bfloat16* o, int ldo, int n_seq, int max_len, int S, int Hq, int kv_group,
                                      const int* cu_seqlens, const int* seq_lens, float scale, bool causal, cudaStream_t stream) {
     CUtensorMap tm;
-    if (!make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
     AttnTc128Params p;
     p.o = o; p.ldo = ldo; p.cu_seqlens = cu_seqlens; p.seq_lens = seq_lens; p.S = S;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.kv_group = kv_group;
     p.scale_log2e = scale * 1.4426950408889634f;
     const size_t smem = attn_tc128_smem_bytes();
-    static bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_d128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_d128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static const int variant = [] { const char* v = getenv("VQA_ATTN128_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();   // 1: round-1 stage; 10/12/13: POLY 0/2/3
+    const int poly = variant == 1 ? -1 : (variant >= 10 ? variant - 10 : ATTN_POLY_DEFAULT);
     dim3 grid((max_len + 127) / 128, Hq, n_seq);
-    if (causal) attn_tc_d128_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
-    else        attn_tc_d128_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
-    return cudaGetLastError();
+    auto go = [&](auto kernel, PerDeviceOnce& once) -> cudaError_t {
+        cudaError_t e = once.ensure([&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, 192, smem, stream>>>(tm, p);
+        return cudaGetLastError();
+    };
+    static PerDeviceOnce once[8];
+    if (causal) {
+        if (poly < 0) return go(attn_tc_d128_kernel<true, -1>, once[0]);
+        if (poly == 0) return go(attn_tc_d128_kernel<true, 0>, once[1]);
+        if (poly == 2) return go(attn_tc_d128_kernel<true, 2>, once[2]);
+        return go(attn_tc_d128_kernel<true, 3>, once[3]);
+    }
+    if (poly < 0) return go(attn_tc_d128_kernel<false, -1>, once[4]);
+    if (poly == 0) return go(attn_tc_d128_kernel<false, 0>, once[5]);
+    if (poly == 2) return go(attn_tc_d128_kernel<false, 2>, once[6]);
+    return go(attn_tc_d128_kernel<false, 3>, once[7]);
 }
 
 }  // namespace vqa

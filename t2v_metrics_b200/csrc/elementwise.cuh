@@ -127,28 +127,40 @@ __global__ void __launch_bounds__(256) t5_rmsnorm_kernel(const __nv_bfloat16* __
 
 // nn.LayerNorm with affine, fp32 statistics (autocast runs layer_norm in fp32), bf16 out.
 // One warp per row, D == 1024 (CLIP ViT-L hidden) or any D % 256 == 0 up to 2048.
-template <int D>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x,
+// TIn = __nv_bfloat16 or float (the CLIP tower's fp32 residual stream); the output is always the bf16 tensor the next Linear consumes.
+template <int D, typename TIn = __nv_bfloat16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x,
                                                        const __nv_bfloat16* __restrict__ gamma,
                                                        const __nv_bfloat16* __restrict__ beta,
                                                        __nv_bfloat16* __restrict__ y, int rows, float eps) {
-    constexpr int VPL = D / 256;  // uint4 per lane
+    constexpr int VPL = D / 256;  // groups of 8 elements per lane
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     float f[VPL * 8];
     float s = 0.f;
+    if constexpr (sizeof(TIn) == 4) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        uint4 v = xr[lane + i * 32];
-        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+        for (int i = 0; i < VPL; ++i) {
+            const float4 a = xr[(lane + i * 32) * 2], b = xr[(lane + i * 32) * 2 + 1];
+            f[i * 8] = a.x; f[i * 8 + 1] = a.y; f[i * 8 + 2] = a.z; f[i * 8 + 3] = a.w;
+            f[i * 8 + 4] = b.x; f[i * 8 + 5] = b.y; f[i * 8 + 6] = b.z; f[i * 8 + 7] = b.w;
+            s += (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+        }
+    } else {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float2 t = unpack_bf16x2(u[e]);
-            f[i * 8 + 2 * e] = t.x;
-            f[i * 8 + 2 * e + 1] = t.y;
-            s += t.x + t.y;
+        for (int i = 0; i < VPL; ++i) {
+            uint4 v = xr[lane + i * 32];
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 t = unpack_bf16x2(u[e]);
+                f[i * 8 + 2 * e] = t.x;
+                f[i * 8 + 2 * e + 1] = t.y;
+                s += t.x + t.y;
+            }
         }
     }
     s = warp_sum(s);
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(256) clip_embed_ln_kernel(const __nv_bfloat16*
                                                            const __nv_bfloat16* __restrict__ pos,    // [P+1, D]
                                                            const __nv_bfloat16* __restrict__ gamma,
                                                            const __nv_bfloat16* __restrict__ beta,
-                                                           __nv_bfloat16* __restrict__ y,  // [B*(P+1), D]
+                                                           float* __restrict__ y,  // [B*(P+1), D] fp32: pre_layrnorm's output under autocast
                                                            int B, int P, float eps) {
     constexpr int VPL = D / 256;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -250,22 +262,23 @@ __global__ void __launch_bounds__(256) clip_embed_ln_kernel(const __nv_bfloat16*
     }
     var = warp_sum(var) / (float)D;
     const float rstd = rsqrtf(var + eps);
-    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * D);
+    float4* yr = reinterpret_cast<float4*>(y + (size_t)row * D);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + lane + i * 32);
         const uint4 bb4 = __ldg(reinterpret_cast<const uint4*>(beta) + lane + i * 32);
         const uint32_t* gu = reinterpret_cast<const uint32_t*>(&g);
         const uint32_t* bu = reinterpret_cast<const uint32_t*>(&bb4);
-        uint32_t o[4];
+        float o[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 gg = unpack_bf16x2(gu[e]);
             float2 bb = unpack_bf16x2(bu[e]);
-            o[e] = pack_bf16x2((f[i * 8 + 2 * e] - mean) * rstd * gg.x + bb.x,
-                               (f[i * 8 + 2 * e + 1] - mean) * rstd * gg.y + bb.y);
+            o[2 * e] = (f[i * 8 + 2 * e] - mean) * rstd * gg.x + bb.x;
+            o[2 * e + 1] = (f[i * 8 + 2 * e + 1] - mean) * rstd * gg.y + bb.y;
         }
-        yr[lane + i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
+        yr[(lane + i * 32) * 2] = make_float4(o[0], o[1], o[2], o[3]);
+        yr[(lane + i * 32) * 2 + 1] = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
 

@@ -38,6 +38,8 @@ struct GemmParams {
     const __nv_bfloat16* bias;      // [N] or nullptr
     const __nv_bfloat16* residual;  // [M, ldr] or nullptr
     int ldr;
+    int c_f32;                // EPI_STORE only: C and residual are fp32 buffers (ldc / ldr in floats): C = residual + bf16(acc + bias), unrounded
+                              // (the CLIP tower's residual stream stays fp32 under the reference's autocast: LayerNorm is on autocast's fp32 list)
     int gate_up_offset;       // GATED: row offset of the "up" weight block inside W (= d_ff)
     // EPI_LSE
     float* lse_max;           // [M, num_n_tiles]
@@ -90,12 +92,24 @@ __device__ __forceinline__ float act_quick_gelu(float x) { return __fdividef(x, 
 __device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float act_gelu_new(float x) {
-    // 0.5 * x * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- transformers/activations.py NewGELUActivation
+    // 0.5 * x * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  -- transformers/activations.py NewGELUActivation, evaluated in fp32 like the
+    // reference does under CUDA autocast (torch.pow is on autocast's fp32 list, so everything downstream of it is fp32).
+    // tanh(u) = 1 - 2 / (exp(2u) + 1) with ex2.approx + rcp.approx: relative error ~1e-6. (tanh.approx.f32 is 2^-11 absolute, i.e. a
+    // SYSTEMATIC 5e-4 error in 48 FFNs -- too coarse for parity with the fp32-evaluated reference.)
     const float k = 0.7978845608028654f;
     const float inner = k * (x + 0.044715f * x * x * x);
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));   // MUFU.TANH, |err| ~ 2^-11: below the bf16 rounding that follows
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(inner * 2.8853900817779268f));   // exp(2u) = 2^(2u log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float th = 1.0f - 2.0f * r;
     return 0.5f * x * (1.0f + th);
+}
+// CLIP's quick_gelu as eager bf16 tensor ops run it (`input * torch.sigmoid(1.702 * input)`, transformers/activations.py:117-123; none of
+// the three ops is on an autocast list, so each produces a bf16 tensor): y bf16 -> bf16(1.702 y) -> bf16(sigmoid) -> product (rounded by caller)
+__device__ __forceinline__ float act_quick_gelu_bf16_ops(float y) {
+    const float a = bf16_round(1.702f * y);
+    const float sg = bf16_round(__fdividef(1.0f, 1.0f + __expf(-a)));
+    return y * sg;
 }
 
 template <int BLOCK_N, int CG, int EPI>
@@ -296,8 +310,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                 g0 = bf16_round(g0); g1 = bf16_round(g1); u0 = bf16_round(u0); u1 = bf16_round(u1);
                                 float h0, h1;
                                 if constexpr (EPI == EPI_GATED_GELU) {
-                                    h0 = bf16_round(act_gelu_new(g0)) * u0;
-                                    h1 = bf16_round(act_gelu_new(g1)) * u1;
+                                    // T5DenseGatedActDense under CUDA autocast: act(wi_0 x) comes out in fp32 (pow -> fp32), the product
+                                    // with the bf16 wi_1 x is fp32, and the single rounding is the cast in front of `wo` (modeling_t5.py:115-131)
+                                    h0 = act_gelu_new(g0) * u0;
+                                    h1 = act_gelu_new(g1) * u1;
                                 } else {
                                     h0 = bf16_round(act_silu(g0)) * u0;
                                     h1 = bf16_round(act_silu(g1)) * u1;
@@ -349,6 +365,40 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     p.lse_max[slot] = run_max;
                     p.lse_sum[slot] = run_sum;
                 }
+            } else if (EPI == EPI_STORE && p.c_f32) {
+                const int n0 = n_blk * BLOCK_N;
+                float* Cf = reinterpret_cast<float*>(p.C);
+                const float* Rf = reinterpret_cast<const float*>(p.residual);
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int nc = n0 + c * 32;
+                    if (row_ok && nc < p.N) {
+                        float* crow = Cf + c_off + (size_t)m * p.ldc + nc;
+                        const float* rrow = Rf ? Rf + c_off + (size_t)m * p.ldr + nc : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (nc + j * 4 < p.N) {
+                                float4 r = rrow ? *reinterpret_cast<const float4*>(rrow + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                float b[4] = {0.f, 0.f, 0.f, 0.f};
+                                if (p.bias) {
+                                    const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + nc + j * 4));
+                                    const float2 b0 = unpack_bf16x2(bb.x), b1 = unpack_bf16x2(bb.y);
+                                    b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+                                }
+                                r.x += bf16_round(__uint_as_float(v[j * 4]) + b[0]);
+                                r.y += bf16_round(__uint_as_float(v[j * 4 + 1]) + b[1]);
+                                r.z += bf16_round(__uint_as_float(v[j * 4 + 2]) + b[2]);
+                                r.w += bf16_round(__uint_as_float(v[j * 4 + 3]) + b[3]);
+                                *reinterpret_cast<float4*>(crow + j * 4) = r;
+                            }
+                        }
+                    }
+                }
             } else {
                 const int n0 = n_blk * BLOCK_N;
                 // Bias and residual for the FIRST chunk are requested before waiting for the accumulator, and the next
@@ -395,7 +445,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     float y = bf16_round(f[e]);   // the Linear's bf16 output in the reference
-                                    if constexpr (EPI == EPI_QUICK_GELU) y = act_quick_gelu(y);
+                                    if constexpr (EPI == EPI_QUICK_GELU) y = act_quick_gelu_bf16_ops(y);
                                     if constexpr (EPI == EPI_GELU_ERF) y = act_gelu_erf(y);
                                     if constexpr (EPI == EPI_RELU) y = fmaxf(y, 0.f);
                                     f[e] = y;
@@ -541,31 +591,37 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
     p.num_m_tiles = (p.M + rows_per_tile - 1) / rows_per_tile;
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     // Tile order = L2 blocking (see tile_coords). Either the W chunk or the A row group is the L2-resident operand:
-    //   * W-stationary: W cut into chunks of <= ~L2_RESIDENT bytes, small A groups stream past each chunk; DRAM reads ~ A * n_chunks + W
-    //   * A-stationary: one chunk (all of W streams), A groups of ~L2_RESIDENT bytes;                      DRAM reads ~ W * n_groups + A
-    // and the cheaper of the two by that model is taken. Measured DRAM bytes per launch for the encoder shapes are in
-    // profiles/r02_gemm_raster.md. vqa_set_gemm_schedule() / VQA_GEMM_GROUP_ROWS / VQA_GEMM_CHUNK_ROWS override (tuning).
+    //   * W-stationary: W cut into chunks of <= ~36 MB, small A groups stream past each chunk;
+    //   * A-stationary: one chunk (all of W streams), A groups of ~32 MB.
+    // The choice per shape follows the sweep in profiles/r02_gemm_raster.md (DRAM bytes from ncu, isolated CUDA-event times).
+    // vqa_set_gemm_schedule() / VQA_GEMM_GROUP_ROWS / VQA_GEMM_CHUNK_ROWS override (tuning); VQA_GEMM_SCHEDULE=r1 selects round 1's order.
     static const int env_rows = [] { const char* v = getenv("VQA_GEMM_GROUP_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
     static const int env_chunk = [] { const char* v = getenv("VQA_GEMM_CHUNK_ROWS"); return (v && v[0]) ? atoi(v) : 0; }();
     const int ov_rows = g_gemm_group_rows_override > 0 ? g_gemm_group_rows_override : env_rows;
     const int ov_chunk = g_gemm_chunk_rows_override != 0 ? g_gemm_chunk_rows_override : env_chunk;
-    const long long w_bytes = (long long)g.w_rows * p.K * 2, a_bytes = (long long)p.M * p.K * 2;
+    const long long w_bytes = (long long)g.w_rows * p.K * 2;
     const long long resident = 36ll << 20;
+    static const int policy = [] { const char* v = getenv("VQA_GEMM_SCHEDULE"); return (v && v[0] == 'r' && v[1] == '1') ? 1 : 2; }();
     int group_rows, chunk_rows;   // chunk_rows < 0: no chunking (all N tiles in one chunk)
-    if (w_bytes <= resident) {
-        group_rows = 1024; chunk_rows = -1;
+    if (policy == 1) {
+        // round-1 order (A/B reference): no W chunks; A groups of ~32 MB when W is larger than ~L2, else 1024 rows
+        chunk_rows = -1;
+        if (w_bytes <= (96ll << 20)) group_rows = 1024;
+        else group_rows = max(512, min(8192, (int)((32ll << 20) / ((long long)p.K * 2)) / 256 * 256));
+    } else if (w_bytes <= resident) {
+        group_rows = 1024; chunk_rows = -1;                       // W stays in L2 as a whole, A streams once
     } else {
         const long long n_chunks = (w_bytes + resident - 1) / resident;
-        const long long n_groups = (a_bytes + resident - 1) / resident;
-        const long long cost_w = a_bytes * n_chunks + w_bytes, cost_a = w_bytes * n_groups + a_bytes;
-        if (cost_w <= cost_a) {
+        if (n_chunks <= 3) {
+            // W-stationary: up to three L2-resident chunks, A streams once per chunk. Measured on B200 (profiles/r02_gemm_raster.md):
+            // encoder qkv 7.7 -> 1.8 GB of DRAM reads, wo 7.6 -> 6.1 GB and 2.74 -> 2.40 ms in isolation
             const long long rows = ((long long)g.w_rows + n_chunks - 1) / n_chunks;
             chunk_rows = (int)((rows + BLOCK_N - 1) / BLOCK_N * BLOCK_N);
             group_rows = 1024;
         } else {
+            // W much larger than L2 (FFN wi, 168 MB): A-stationary groups of ~32 MB are faster than many small W chunks (5.22 vs 5.38 ms)
             chunk_rows = -1;
-            group_rows = (int)((32ll << 20) / ((long long)p.K * 2));
-            group_rows = max(512, min(8192, group_rows / 256 * 256));
+            group_rows = max(512, min(8192, (int)((32ll << 20) / ((long long)p.K * 2)) / 256 * 256));
         }
     }
     if (ov_rows > 0) group_rows = ov_rows;

@@ -151,12 +151,14 @@ static int pick_variant(int M, int N, int epi) {
 // Launch C = epi(A W^T). Returns cudaError_t. `launch_counter` is incremented per kernel.
 static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M, int N,
                             int K, const bf16* bias, const bf16* residual, int ldr, int epi, int gate_up_offset,
-                            int variant, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+                            int variant, int num_sms, cudaStream_t st, int64_t* launch_counter, bool c_f32 = false) {
     GemmLaunch g;
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = w_rows;
     memset(&g.p, 0, sizeof(g.p));
     g.p.M = M; g.p.N = N; g.p.K = K; g.p.C = C; g.p.ldc = ldc; g.p.bias = bias; g.p.residual = residual;
     g.p.ldr = ldr; g.p.gate_up_offset = gate_up_offset;
+    if (c_f32 && epi != EPI_STORE) return cudaErrorInvalidValue;
+    g.p.c_f32 = c_f32 ? 1 : 0;
     if (launch_counter) ++*launch_counter;
     if (variant == 0) variant = pick_variant(M, N, epi);
     switch (epi) {
@@ -227,6 +229,18 @@ static cudaError_t run_rmsnorm(const bf16* x, const bf16* w, bf16* y, int rows, 
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
+// LayerNorm of an fp32 stream (the CLIP residual under autocast) -> bf16
+static cudaError_t run_layernorm_f32(const float* x, const bf16* g, const bf16* b, bf16* y, int rows, int D, float eps,
+                                     cudaStream_t st, int64_t* lc) {
+    if (lc) ++*lc;
+    const int blocks = (rows + 7) / 8;
+    if (D == 1024)      layernorm_kernel<1024, float><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 256)  layernorm_kernel<256, float><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 512)  layernorm_kernel<512, float><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else if (D == 768)  layernorm_kernel<768, float><<<blocks, 256, 0, st>>>(x, g, b, y, rows, eps);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 static cudaError_t run_layernorm(const bf16* x, const bf16* g, const bf16* b, bf16* y, int rows, int D, float eps,
                                  cudaStream_t st, int64_t* lc) {
     if (lc) ++*lc;
@@ -241,11 +255,11 @@ static cudaError_t run_layernorm(const bf16* x, const bf16* g, const bf16* b, bf
 }
 // q, k, v are column slices of one packed buffer (they always are on this path). bias_const_from: see launch_attn_tc.
 static cudaError_t run_flash(const bf16* q, const bf16* k, const bf16* v, int ldqkv, bf16* o, int ldo, int B, int S,
-                             int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
+                             int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from, bool round_scores,
                              cudaStream_t st, int64_t* lc) {
     if (lc) ++*lc;
     const int q_col0 = 0, k_col0 = (int)(k - q), v_col0 = (int)(v - q);
-    return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, bias_const_from, st);
+    return launch_attn_tc(q, ldqkv, q_col0, k_col0, v_col0, o, ldo, B, S, H, seq_lens, bias_table, scale, bias_const_from, round_scores, st);
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI: lifecycle
@@ -447,7 +461,7 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     ClipT5Workspace w;
     w.patches = pl.take(Mp * h->kpad * 2);
     w.patch_out = pl.take(Mp * c.vit_hidden * 2);
-    w.hv = pl.take(Mv * c.vit_hidden * 2);
+    w.hv = pl.take(Mv * c.vit_hidden * 4);      // fp32: the vision tower's residual stream (see the vision loop)
     w.vn = pl.take(Mv * c.vit_hidden * 2);
     w.vqkv = pl.take(Mv * 3 * c.vit_hidden * 2);
     w.vattn = pl.take(Mv * c.vit_hidden * 2);
@@ -556,10 +570,23 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         ProfScope ps(h, CAT_NORM, 0, st);
         return cuda_ok(run_rmsnorm(x, wgt, y, rows, Dm, c.t5_ln_eps, st, lc), "rmsnorm");
     };
-    auto lnorm = [&](const bf16* x, const bf16* g, const bf16* b_, bf16* y, int rows) -> int {
+    auto lnorm = [&](const float* x, const bf16* g, const bf16* b_, bf16* y, int rows) -> int {
         ProfScope ps(h, CAT_NORM, 0, st);
-        return cuda_ok(run_layernorm(x, g, b_, y, rows, Dv, c.vit_ln_eps, st, lc), "layernorm");
+        return cuda_ok(run_layernorm_f32(x, g, b_, y, rows, Dv, c.vit_ln_eps, st, lc), "layernorm");
     };
+    auto gemm_f32res = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, float* C, int M_, int N_, int K_, const bf16* bias) -> int {
+        // C (fp32) = C + bf16(A W^T + bias): the residual stream is read and written in fp32
+        const double bytes = 2.0 * ((double)M_ * K_ + (double)N_ * K_) + 8.0 * (double)M_ * N_;
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st, bytes);
+        return cuda_ok(run_gemm(A, lda, W, ldw, w_rows, reinterpret_cast<bf16*>(C), N_, M_, N_, K_, bias, reinterpret_cast<const bf16*>(C), N_,
+                                EPI_STORE, 0, 0, nsm, st, lc, true), "gemm (fp32 residual)");
+    };
+    // Precision of the vision tower's residual stream: the reference runs CLIPVisionModel under torch.autocast(bf16). nn.LayerNorm is on
+    // autocast's fp32 list, so pre_layrnorm hands the encoder an fp32 tensor, every `residual + hidden_states` (modeling_clip.py:371,
+    // :376) promotes to fp32, and only the Linear inputs are cast to bf16. hidden_states[-2] is therefore an fp32 tensor, rounded to
+    // bf16 once where the projector's first Linear consumes it. The engine keeps the same: hv is fp32, the out_proj / fc2 epilogues add
+    // the bf16 Linear output into it unrounded, the LayerNorms read fp32 and write the bf16 GEMM operand.
+    float* hv = reinterpret_cast<float*>(ws + w.hv);
 
     // ---------------- vision tower (CLIP ViT, layers 0 .. vit_layers_run-1; hidden_states[-2]) ----------------
     {
@@ -580,32 +607,38 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         ++*lc;
         if (Dv == 1024)
             clip_embed_ln_kernel<1024><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w,
-                                                                     h->pre_ln_b, P_(w.hv), n_images, P, c.vit_ln_eps);
+                                                                     h->pre_ln_b, hv, n_images, P, c.vit_ln_eps);
         else if (Dv == 256)
             clip_embed_ln_kernel<256><<<(Mv + 7) / 8, 256, 0, st>>>(P_(w.patch_out), h->cls, h->pos, h->pre_ln_w,
-                                                                    h->pre_ln_b, P_(w.hv), n_images, P, c.vit_ln_eps);
+                                                                    h->pre_ln_b, hv, n_images, P, c.vit_ln_eps);
         else
             return fail(h, VQA_ERR_UNSUPPORTED, "vit_hidden must be 1024 or 256");
         TRY(cuda_ok(cudaSuccess, "clip_embed_ln"));
     }
     for (int l = 0; l < c.vit_layers_run; ++l) {
         const VitLayerW& Lw = h->vit[l];
-        TRY(lnorm(P_(w.hv), Lw.ln1_w, Lw.ln1_b, P_(w.vn), Mv));
+        TRY(lnorm(hv, Lw.ln1_w, Lw.ln1_b, P_(w.vn), Mv));
         TRY(gemm(P_(w.vn), Dv, Lw.qkv_w, Dv, 3 * Dv, P_(w.vqkv), 3 * Dv, Mv, 3 * Dv, Dv, Lw.qkv_b, nullptr, 0, EPI_STORE, 0));
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * n_images * (double)Hv * (P + 1) * (P + 1) * 64, st);
             TRY(cuda_ok(run_flash(P_(w.vqkv), P_(w.vqkv) + Dv, P_(w.vqkv) + 2 * Dv, 3 * Dv, P_(w.vattn), Dv, n_images, P + 1,
-                                  Hv, nullptr, nullptr, 0.125f, 0, st, lc), "vit attention"));
+                                  Hv, nullptr, nullptr, 0.125f, 0, rnd != 0, st, lc), "vit attention"));
         }
-        TRY(gemm(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, P_(w.hv), Dv, Mv, Dv, Dv, Lw.out_b, P_(w.hv), Dv, EPI_STORE, 0));
-        TRY(lnorm(P_(w.hv), Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv));
+        TRY(gemm_f32res(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, hv, Mv, Dv, Dv, Lw.out_b));
+        TRY(lnorm(hv, Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv));
         TRY(gemm(P_(w.vn), Dv, Lw.fc1_w, Dv, c.vit_mlp, P_(w.vmlp), c.vit_mlp, Mv, c.vit_mlp, Dv, Lw.fc1_b, nullptr, 0,
                  EPI_QUICK_GELU, 0));
-        TRY(gemm(P_(w.vmlp), c.vit_mlp, Lw.fc2_w, c.vit_mlp, Dv, P_(w.hv), Dv, Mv, Dv, c.vit_mlp, Lw.fc2_b, P_(w.hv), Dv,
-                 EPI_STORE, 0));
+        TRY(gemm_f32res(P_(w.vmlp), c.vit_mlp, Lw.fc2_w, c.vit_mlp, Dv, hv, Mv, Dv, c.vit_mlp, Lw.fc2_b));
+    }
+    {   // hidden_states[-2] -> bf16 (`.to(images.dtype)` / the projector Linear's autocast cast): the single rounding of the tower's output
+        ProfScope ps(h, CAT_OTHER, 0, st);
+        ++*lc;
+        const size_t n = (size_t)Mv * Dv;
+        cast_f32_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(hv, P_(w.vn), n);
+        TRY(cuda_ok(cudaSuccess, "vision output cast"));
     }
     // mlp2x_gelu projector (Linear -> GELU(erf) -> Linear), applied to every row; the CLS rows are simply not spliced
-    TRY(gemm(P_(w.hv), Dv, h->proj0_w, Dv, Dm, P_(w.proj1), Dm, Mv, Dm, Dv, h->proj0_b, nullptr, 0, EPI_GELU_ERF, 0));
+    TRY(gemm(P_(w.vn), Dv, h->proj0_w, Dv, Dm, P_(w.proj1), Dm, Mv, Dm, Dv, h->proj0_b, nullptr, 0, EPI_GELU_ERF, 0));
     TRY(gemm(P_(w.proj1), Dm, h->proj2_w, Dm, Dm, P_(w.proj2), Dm, Mv, Dm, Dm, h->proj2_b, nullptr, 0, EPI_STORE, 0));
 
     // ---------------- multimodal splice -> T5 encoder input ----------------
@@ -630,7 +663,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * S * S * 64, st);
             TRY(cuda_ok(run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
-                                  seq_lens, bias_table, 1.0f, c.rel_max_distance, st, lc), "t5 encoder attention"));
+                                  seq_lens, bias_table, 1.0f, c.rel_max_distance, rnd != 0, st, lc), "t5 encoder attention"));
         }
         TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
         TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
@@ -747,7 +780,7 @@ extern "C" int vqa_clipt5_debug_layout(vqa_handle* h, int32_t batch, int32_t n_i
     offsets[2] = w.proj2;   // projector output                            [NI*(P+1), d_model] bf16 (row 0 of each image = CLS)
     offsets[3] = w.x;       // encoder residual stream before the final norm
     offsets[4] = w.y;       // decoder residual stream before the final norm
-    offsets[5] = w.hv;      // vision tower hidden states of the last executed layer [NI*(P+1), vit_hidden]
+    offsets[5] = w.hv;      // vision tower hidden states of the last executed layer [NI*(P+1), vit_hidden] FP32
     return VQA_OK;
 }
 
@@ -925,12 +958,25 @@ extern "C" int vqa_op_lmhead_logprob(const void* Hs, int32_t ldh, const void* W,
 }
 
 extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                                    const float* bias_table, float scale, int32_t bias_const_from, void* stream) {
+                                    const float* bias_table, float scale, int32_t bias_const_from, int32_t round_scores, void* stream) {
     if (!qkv || !out || B <= 0 || S <= 0 || H <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
     const bf16* q = (const bf16*)qkv;
     cudaError_t e = run_flash(q, q + H * 64, q + 2 * H * 64, 3 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table,
-                              scale, bias_const_from, (cudaStream_t)stream, nullptr);
+                              scale, bias_const_from, round_scores != 0, (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// Instrumented run of the T5-encoder attention kernel (bias table + score rounding): `counters` = DEVICE uint64[9], zeroed by the caller;
+// after the stream has passed: cycles summed over one softmax warp per CTA in {wait S, TMEM load, max + vote, wait O / rescale, exp2 + P store,
+// store wait + arrive, epilogue, total}, and [8] = key tiles those warps processed.
+extern "C" int vqa_debug_attention_d64_phases(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
+                                              const float* bias_table, int32_t bias_const_from, uint64_t* counters, void* stream) {
+    if (!qkv || !out || !bias_table || !counters || B <= 0 || S <= 0 || H <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
+    const bf16* q = (const bf16*)qkv;
+    cudaError_t e = launch_attn_tc(q, 3 * H * 64, 0, H * 64, 2 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table, 1.0f, bias_const_from,
+                                   true, (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(counters));
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention (phases) launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }
 

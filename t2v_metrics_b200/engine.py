@@ -225,7 +225,8 @@ class ClipT5Engine:
         return dict(enc_out=view(off[0], batch * S, cfg.d_model).view(batch, S, cfg.d_model),
                     dec_out=view(off[1], batch * label_len, cfg.d_model).view(batch, label_len, cfg.d_model),
                     proj=view(off[2], n_images * (cfg.num_patches + 1), cfg.d_model).view(n_images, cfg.num_patches + 1, cfg.d_model),
-                    vit_hidden=view(off[5], n_images * (cfg.num_patches + 1), cfg.vit_hidden).view(n_images, cfg.num_patches + 1, cfg.vit_hidden))
+                    vit_hidden=ws[off[5]:off[5] + n_images * (cfg.num_patches + 1) * cfg.vit_hidden * 4].view(torch.float32)
+                    .view(n_images, cfg.num_patches + 1, cfg.vit_hidden))
 
     def set_profile(self, enable: bool):
         _check(self.lib.vqa_set_profile(self._h, 1 if enable else 0), self._h, "vqa_set_profile")
@@ -278,13 +279,13 @@ class ops:
 
     @staticmethod
     def attention(qkv: torch.Tensor, B: int, S: int, H: int, seq_lens=None, bias_table=None, scale=1.0,
-                  bias_const_from: int = 0):
+                  bias_const_from: int = 0, round_scores: bool = False):
         """bias_const_from > 0 promises that bias_table[h] is constant for |key - query| >= bias_const_from on either side (T5:
-        relative_attention_max_distance); 0 makes no assumption."""
+        relative_attention_max_distance); 0 makes no assumption. round_scores: form the reference's bf16 score tensors before the softmax."""
         lib = _lib.load()
         out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device=qkv.device)
         rc = lib.vqa_op_attention_d64(_ptr(qkv), _ptr(out), B, S, H, _ptr(seq_lens), _ptr(bias_table), float(scale),
-                                      int(bias_const_from), _stream_ptr(qkv.device))
+                                      int(bias_const_from), 1 if round_scores else 0, _stream_ptr(qkv.device))
         _check(rc, None, "vqa_op_attention_d64")
         return out
 

@@ -69,6 +69,16 @@ def run_clipt5_case(cfg, dev, B, L, lens, label_ids=(2163, 1), with_fp32=True, t
         lm.data[tok] = row.to(lm.device)
         sd["lm_head.weight"][tok] = row.to(sd["lm_head.weight"].device)
     ref = fwd(mods, True)
+    # ---- how well-conditioned is the fixture, and how much does the REFERENCE move when only its batch composition changes?
+    hd = ref["dec_hidden"]                                                  # [B, T, d]
+    hn = torch.nn.functional.normalize(hd[:, 0].float(), dim=-1)
+    cos = (hn @ hn.t())[~torch.eye(B, dtype=torch.bool, device=hn.device)]
+    one = torch.stack([hf.hf_clipt5_forward(cfg, mods, inp["pixels"][b:b + 1], inp["input_ids"][b:b + 1], inp["text_lens"][b:b + 1],
+                                            inp["labels"][b:b + 1], autocast_bf16=True)[0] for b in range(B)])
+    self_noise = float((one - ref["scores"]).abs().max())
+    print(f"\n[{tag}] fixture: cos(final decoder states of different pairs) min {float(cos.min()):.4f} max {float(cos.max()):.4f}; "
+          f"|lm_head answer row| * |h| = {float(lm[label_ids[0]].float().norm() * hd[:, 0].float().norm(dim=-1).mean()):.1f}"
+          f"\n[{tag}] reference self-noise: HF bf16 scored pair-by-pair (batch 1) vs in one batch of {B}: max|dscore| {self_noise:.3e}  {one.tolist()}")
     # ---- engine
     eng = ClipT5Engine(ClipT5Config(**dataclasses.asdict(cfg)), dev)
     eng.load_state_dict(sd)
@@ -86,7 +96,7 @@ def run_clipt5_case(cfg, dev, B, L, lens, label_ids=(2163, 1), with_fp32=True, t
           f"\n[{tag}] max|dscore| {err:.3e}   max|dlogp| {float((lp - ref['logprobs']).abs().max()):.3e}"
           f"\n[{tag}] rel.err (max abs): projector {proj_rel[0]:.2e} ({proj_rel[1]:.2e}) | encoder out {enc_rel[0]:.2e} ({enc_rel[1]:.2e}) | "
           f"decoder out {dec_rel[0]:.2e} ({dec_rel[1]:.2e}) | launches {eng.last_launch_count()}")
-    out = dict(engine=s, ref=ref["scores"], err=err)
+    out = dict(engine=s, ref=ref["scores"], err=err, self_noise=self_noise)
     if with_fp32:
         try:
             del mods, eng, dbg

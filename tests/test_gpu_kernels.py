@@ -139,6 +139,40 @@ def test_attention_saturating_t5_bias(ops, S, dist, ragged):
     assert float((generic[qmask].float() - ref[qmask]).abs().max()) < 0.02
 
 
+@pytest.mark.parametrize("S,use_bias,scale", [(672, True, 1.0), (577, False, 0.125), (200, True, 1.0)])
+def test_attention_reference_rounding_points(ops, S, use_bias, scale):
+    """round_scores=True forms the bf16 tensors of the reference's eager attention before the fp32 softmax (modeling_t5.py:308-331:
+    `scores = matmul(q, k^T)` is bf16, `scores += position_bias` is a bf16 add; modeling_clip.py:271: bf16 matmul * 2^-3). Large
+    scores (|s| ~ 20) so that the rounding is visible: the kernel must follow the rounded reference more closely than the fp32-score one."""
+    torch.manual_seed(3)
+    B, H = 2, 4
+    qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 1.5).bfloat16()
+    table = None
+    if use_bias:
+        rel = torch.arange(-(S - 1), S, device="cuda").clamp(-128, 128) + 128
+        table = (torch.randn(H, 257, device="cuda") * 2.0).bfloat16().float()[:, rel].contiguous()
+    got = ops.attention(qkv, B, S, H, bias_table=table, scale=scale, bias_const_from=128 if use_bias else 0, round_scores=True).float()
+    plain = ops.attention(qkv, B, S, H, bias_table=table, scale=scale, bias_const_from=128 if use_bias else 0, round_scores=False).float()
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    raw = torch.matmul(q, k.transpose(-1, -2))
+    idx = (torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None]) + S - 1
+    sc = raw.bfloat16()                                                   # bf16 matmul output
+    if use_bias:
+        sc = (sc + table[:, idx][None].bfloat16())                        # bf16 + bf16 -> bf16
+    sc = (sc * scale).float()                                             # * 2^-3 is exact in bf16
+    p = torch.softmax(sc, -1).bfloat16().float()
+    ref_rounded = torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    exact = raw * scale + (table[:, idx][None] if use_bias else 0.0)
+    ref_exact = torch.matmul(torch.softmax(exact, -1), v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    e_round = float((got - ref_rounded).abs().mean())
+    e_cross = float((got - ref_exact).abs().mean())
+    e_plain = float((plain - ref_exact).abs().mean())
+    print(f"\n[S={S} bias={use_bias}] round_scores kernel vs rounded reference {e_round:.2e}, vs exact-score reference {e_cross:.2e}; "
+          f"fp32-score kernel vs exact reference {e_plain:.2e}")
+    assert e_round < 0.6 * e_cross          # it follows the reference's rounding, not the exact scores
+    assert float((got - ref_rounded).abs().max()) < 0.05 and float((plain - ref_exact).abs().max()) < 0.05
+
+
 def test_norms(ops):
     torch.manual_seed(6)
     for D in (4096, 3584, 2048, 1280, 256, 128, 5120):   # warp-per-row (D % 256 == 0, <= 4096) and the generic block-per-row path

@@ -40,13 +40,80 @@ def attn():
             rel = torch.arange(-(S - 1), S, device="cuda").clamp(-128, 128) + 128
             table = (torch.randn(H, 257, device="cuda")).bfloat16().float()[:, rel].contiguous()
         lens = torch.randint(639, 673, (B,), device="cuda", dtype=torch.int32) if "ragged" in name else None
-        fn = lambda: ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=scale, bias_const_from=128 if bias else 0)
+        rnd = os.environ.get("ATTN_ROUND", "1") == "1"
+        fn = lambda: ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=scale, bias_const_from=128 if bias else 0, round_scores=rnd)
         ms = time_ms(fn)
         o = fn()
         torch.cuda.synchronize()
         flops = 4.0 * B * H * S * S * 64
         out[name] = dict(ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), checksum=float(o.float().abs().sum()))
     print(json.dumps(dict(variant=os.environ.get("VQA_ATTN_VARIANT", "default"), **out)))
+
+
+def _t5_attn_inputs(B=64, S=672, H=64):
+    torch.manual_seed(0)
+    qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 0.5).bfloat16()
+    rel = torch.arange(-(S - 1), S, device="cuda").clamp(-128, 128) + 128
+    table = (torch.randn(H, 257, device="cuda")).bfloat16().float()[:, rel].contiguous()
+    return qkv, table
+
+
+def attn_phases():
+    """clock64() phase table of the T5-encoder attention kernel (instrumented build, one softmax warp per CTA reports)."""
+    import ctypes as C
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    B, S, H = 64, 672, 64
+    qkv, table = _t5_attn_inputs(B, S, H)
+    out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device="cuda")
+    cnt = torch.zeros(9, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        cnt.zero_()
+        _check(lib.vqa_debug_attention_d64_phases(_ptr(qkv), _ptr(out), B, S, H, None, _ptr(table), 128, _ptr(cnt), _stream_ptr(qkv.device)), None, "phases")
+        torch.cuda.synchronize()
+    c = cnt.tolist()
+    names = ["wait_S", "tmem_load", "max+vote", "wait_O/rescale", "exp2+P_store", "st_wait+arrive", "epilogue", "total"]
+    tiles = max(c[8], 1)
+    print(json.dumps(dict(tiles=c[8], cycles_per_key_tile={n: round(v / tiles, 1) for n, v in zip(names, c[:8])})))
+
+
+def attn_one():
+    """one launch of the production attention kernel at the T5-encoder shape (target of `ncu --set full`)."""
+    from t2v_metrics_b200.engine import ops
+    qkv, table = _t5_attn_inputs()
+    for _ in range(3):
+        ops.attention(qkv, 64, 672, 64, bias_table=table, scale=1.0, bias_const_from=128, round_scores=True)
+    torch.cuda.synchronize()
+
+
+def attn128():
+    """head_dim-128 attention at the Qwen2.5-VL-7B shapes: causal GQA prefill (B=32, S=320, 28/4 heads), vision windows (64 tokens) and whole frames."""
+    import ctypes as C
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    torch.manual_seed(0)
+    res = {}
+
+    def run(qkv, out_cols, n_seq, max_len, S, Hq, group, cu, scale, causal, q0, k0, v0):
+        out = torch.empty(qkv.shape[0], out_cols, dtype=torch.bfloat16, device="cuda")
+        fn = lambda: _check(lib.vqa_op_attention_d128(_ptr(qkv), qkv.shape[1], qkv.shape[0], q0, k0, v0, _ptr(out), out_cols, n_seq, max_len, S, Hq,
+                                                       group, _ptr(cu), None, float(scale), 1 if causal else 0, _stream_ptr(qkv.device)), None, "d128")
+        return time_ms(fn), float(out.float().abs().sum())
+    B, S, Hq, Hkv = 32, 320, 28, 4
+    qkv = (torch.randn(B * S, (Hq + 2 * Hkv) * 128, device="cuda") * 0.5).bfloat16()
+    ms, cs = run(qkv, Hq * 128, B, S, S, Hq, Hq // Hkv, None, 128 ** -0.5, True, 0, Hq * 128, (Hq + Hkv) * 128)
+    res["llm_causal"] = dict(ms=round(ms, 4), tflops=round(2.0 * B * Hq * S * S * 128 / ms / 1e9, 1), checksum=cs)
+    L, Hv = 32 * 1024, 16
+    x = torch.zeros(L, 3, Hv, 128, device="cuda")
+    x[..., :80] = torch.randn(L, 3, Hv, 80, device="cuda") * 0.5
+    vq = x.reshape(L, 3 * Hv * 128).bfloat16()
+    for name, wlen in (("vis_window64", 64), ("vis_frame1024", 1024)):
+        cu = torch.arange(0, L + 1, wlen, dtype=torch.int32, device="cuda")
+        ms, cs = run(vq, Hv * 128, L // wlen, wlen, 0, Hv, 1, cu, 80 ** -0.5, False, 0, Hv * 128, 2 * Hv * 128)
+        res[name] = dict(ms=round(ms, 4), tflops_padded=round(4.0 * L * wlen * Hv * 128 / ms / 1e9, 1), checksum=cs)
+    print(json.dumps(dict(variant=os.environ.get("VQA_ATTN128_VARIANT", "default"), **res)))
 
 
 SHAPES = dict(   # name: (M, N, K, epilogue, residual)   clip-flant5-xxl encoder layer at B=64, S=672
@@ -94,6 +161,12 @@ if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "attn":
         attn()
+    elif cmd == "attn-phases":
+        attn_phases()
+    elif cmd == "attn-one":
+        attn_one()
+    elif cmd == "attn128":
+        attn128()
     elif cmd == "gemm-time":
         gemm("time")
     elif cmd == "gemm-ncu":
