@@ -172,6 +172,16 @@ int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int32_t pixel_d
                        int32_t seq_len, float temperature, float repetition_penalty, float* out_probs, float* out_logprobs,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Trace output (reference forward_with_trace, qwen2vl_model.py:303-493, top-5 at :439-447): the k <= 8 most probable next tokens of every
+ * prompt of the LAST vqa_qwen25vl_score call on this handle with the same (batch, seq_len, n_patches) and the same workspace (its final
+ * hidden states are still there), under the same processing as the score: bf16 logits -> fp32 -> repetition penalty -> 1/T -> softmax over
+ * the whole vocabulary. out_ids / out_probs: DEVICE [batch, k], most probable first; out_ids[b][0] is the token generate(max_new_tokens=1,
+ * do_sample=False) would emit. This call materialises [batch, vocab] bf16 logits of that one position in the workspace -- a debugging aid;
+ * the scoring path never stores logits. input_ids / seq_lens (as given to the score call) are only read when repetition_penalty != 1. */
+int vqa_qwen25vl_topk(vqa_handle* h, const int32_t* input_ids, const int32_t* seq_lens, int32_t batch, int32_t seq_len, int32_t n_patches,
+                      int32_t k, float temperature, float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last vqa_clipt5_score call launched (for bench.py's gpu_launches). */
 int64_t vqa_last_launch_count(vqa_handle* h);
 

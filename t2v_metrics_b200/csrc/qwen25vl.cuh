@@ -25,7 +25,7 @@ static inline int qwen_mlp_pad(int mlp) { return (mlp + 127) / 128 * 128; }
 
 struct QwenWorkspace {
     size_t patches, vx, vxn, vqkv, vattn, vff, vmerge_in, vfc1, vfeat, vfeat_orig, vcos, vsin;
-    size_t x, xn, qkv, attn, ff, cos, sin, last, lastn, lse_max, lse_sum, label_logit, logprob, pen_bitmap;
+    size_t x, xn, qkv, attn, ff, cos, sin, last, lastn, lse_max, lse_sum, label_logit, logprob, pen_bitmap, trace_logits;
     size_t total;
 };
 static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n_patches) {
@@ -63,6 +63,7 @@ static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n
     w.label_logit = pl.take((size_t)B * 4);
     w.logprob = pl.take((size_t)B * 4);
     w.pen_bitmap = pl.take((size_t)B * ((c.vocab + 31) / 32) * 4);
+    w.trace_logits = pl.take((size_t)B * c.vocab * 2);      // only written by vqa_qwen25vl_topk (trace output); the scoring path never stores logits
     w.total = pl.off;
     return w;
 }
@@ -269,5 +270,31 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         TRY(cuda_ok(cudaSuccess, "lse finalize"));
     }
 #undef TRY
+    return VQA_OK;
+}
+
+// forward_with_trace support: top-k of the last-position distribution of the LAST scoring call (its final hidden states are still in the
+// workspace). Materialises the [B, vocab] bf16 logits of that one position -- trace mode only.
+static int qwen_topk(vqa_handle* h, QwenState& q, const int* input_ids, const int* seq_lens, int B, int S, int n_patches, int K, float temperature,
+                     float repetition_penalty, int* out_ids, float* out_probs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const vqa_qwen25vl_config& c = q.cfg;
+    const QwenWorkspace w = qwen_plan(c, B, S, n_patches);
+    if (workspace_bytes < w.total) return fail(h, VQA_ERR_WORKSPACE, "workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    bf16* lastn = reinterpret_cast<bf16*>(ws + w.lastn);
+    bf16* logits = reinterpret_cast<bf16*>(ws + w.trace_logits);
+    const int pen_words = (c.vocab + 31) / 32;
+    const bool penalise = repetition_penalty != 1.0f;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + w.pen_bitmap);
+    if (penalise) {
+        CUDA_TRY(h, cudaMemsetAsync(bitmap, 0, (size_t)B * pen_words * 4, st));
+        token_bitmap_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(input_ids, seq_lens, B, S, c.vocab, bitmap, pen_words);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, run_gemm(lastn, c.hidden, q.lm_head, c.hidden, c.vocab, logits, c.vocab, B, c.vocab, c.hidden, nullptr, nullptr, 0, EPI_STORE, 0, 0,
+                         h->num_sms, st, nullptr));
+    topk_softmax_kernel<<<B, 256, 0, st>>>(logits, (long long)c.vocab, c.vocab, 1.0f / temperature, penalise ? bitmap : nullptr, pen_words,
+                                           repetition_penalty, K, out_ids, out_probs);
+    CUDA_TRY(h, cudaGetLastError());
     return VQA_OK;
 }

@@ -143,4 +143,77 @@ __global__ void exp_kernel(const float* __restrict__ lp, float* __restrict__ out
     if (i < n) out[i] = expf(lp[i]);
 }
 
+// Trace output (reference forward_with_trace, qwen2vl_model.py:439-447: torch.topk(softmax(scores / T), 5)): the k most probable tokens of
+// one row of materialised last-position logits, with their probabilities under the same processing as the scoring path (bf16 logits ->
+// fp32 -> repetition penalty -> 1/T -> full-vocabulary softmax). One block per row; a debugging aid, not on the scoring path.
+constexpr int TOPK_MAX = 8;
+__global__ void __launch_bounds__(256) topk_softmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, float inv_temp,
+                                                           const uint32_t* __restrict__ pen_bitmap, int pen_words, float penalty, int K,
+                                                           int* __restrict__ out_ids, float* __restrict__ out_probs) {
+    __shared__ float s_val[256 * TOPK_MAX];
+    __shared__ int s_idx[256 * TOPK_MAX];
+    __shared__ float s_red[2][8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const __nv_bfloat16* lr = logits + (size_t)row * ldl;
+    const uint32_t* pb = pen_bitmap ? pen_bitmap + (size_t)row * pen_words : nullptr;
+    float tv[TOPK_MAX];
+    int ti[TOPK_MAX];
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
+    float mx = -INFINITY, sm = 0.f;
+    for (int n = tid; n < V; n += 256) {
+        float x = __bfloat162float(lr[n]);
+        if (pb && ((pb[n >> 5] >> (n & 31)) & 1u)) x = x < 0.f ? x * penalty : __fdiv_rn(x, penalty);
+        x *= inv_temp;
+        if (x > mx) { sm = sm * __expf(mx - x) + 1.f; mx = x; } else { sm += __expf(x - mx); }
+        if (x > tv[TOPK_MAX - 1]) {          // insert into the sorted local list (ties keep the lower id first, like torch.topk on a scan)
+            int pos = TOPK_MAX - 1;
+#pragma unroll
+            for (int i = TOPK_MAX - 2; i >= 0; --i)
+                if (x > tv[i]) { tv[i + 1] = tv[i]; ti[i + 1] = ti[i]; pos = i; }
+            tv[pos] = x; ti[pos] = n;
+        }
+    }
+    // block-wide log-sum-exp
+    float bm = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    if ((tid & 31) == 0) s_red[0][tid >> 5] = bm;
+    __syncthreads();
+    bm = s_red[0][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) bm = fmaxf(bm, s_red[0][i]);
+    float bs = (mx == -INFINITY) ? 0.f : sm * __expf(mx - bm);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
+    if ((tid & 31) == 0) s_red[1][tid >> 5] = bs;
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; ++i) { s_val[tid * TOPK_MAX + i] = tv[i]; s_idx[tid * TOPK_MAX + i] = ti[i]; }
+    __syncthreads();
+    if (tid < 32) {
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) total += s_red[1][i];
+        for (int k = 0; k < K; ++k) {
+            float best = -INFINITY; int bpos = -1, bid = 0x7fffffff;
+            for (int j = tid; j < 256 * TOPK_MAX; j += 32) {
+                const float v = s_val[j]; const int id = s_idx[j];
+                if (id >= 0 && (v > best || (v == best && id < bid))) { best = v; bpos = j; bid = id; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (ov > best || (ov == best && oid < bid)) { best = ov; bpos = op; bid = oid; }
+            }
+            if (tid == 0) {
+                out_ids[row * K + k] = bpos >= 0 ? bid : -1;
+                out_probs[row * K + k] = bpos >= 0 ? __expf(best - bm) / total : 0.f;
+                if (bpos >= 0) s_idx[bpos] = -1;      // remove the winner
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace vqa

@@ -914,6 +914,18 @@ extern "C" int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int3
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vqa_qwen25vl_topk(vqa_handle* h, const int32_t* input_ids, const int32_t* seq_lens, int32_t batch, int32_t seq_len, int32_t n_patches,
+                                 int32_t k, float temperature, float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!h || h->kind != 1) return fail(h, VQA_ERR_INVALID_ARG, "not a Qwen2.5-VL handle");
+    if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
+    if (!out_ids || !out_probs || !workspace || batch <= 0 || seq_len <= 0 || n_patches <= 0 || k <= 0 || k > TOPK_MAX || !(temperature > 0.f) ||
+        !(repetition_penalty > 0.f) || (repetition_penalty != 1.0f && (!input_ids || !seq_lens)))
+        return fail(h, VQA_ERR_INVALID_ARG, "bad top-k argument (1 <= k <= 8; the prompt ids are needed when a repetition penalty applies)");
+    return qwen_topk(h, *h->qwen, input_ids, seq_lens, batch, seq_len, n_patches, k, temperature, repetition_penalty, out_ids, out_probs, workspace,
+                     workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ kernel-level ABI
 static int device_sms() {
     static int sms = 0;

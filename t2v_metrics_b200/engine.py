@@ -591,7 +591,25 @@ class QwenVLEngine:
                                              float(temperature), float(repetition_penalty), _ptr(out), _ptr(logp), _ptr(self._workspace),
                                              self._workspace.numel(), _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_score")
+        self._last_call = (B, S, vi["n_patches"], input_ids, seq_lens)       # what topk_last() needs to find the final hidden states again
         return (out, logp) if return_logprobs else out
+
+    def topk_last(self, k: int = 5, temperature: float = 1.0, repetition_penalty: float = 1.0):
+        """Top-k next tokens (ids [B, k] int32, probabilities [B, k] fp32, most probable first) of the prompts of the LAST score_tensors /
+        score_prompts call, under the same logit processing as the scores -- the reference's forward_with_trace output
+        (qwen2vl_model.py:439-447). Trace mode only: materialises the last position's [B, vocab] logits in the workspace."""
+        if getattr(self, "_last_call", None) is None:
+            raise RuntimeError("topk_last() follows a scoring call")
+        B, S, n_patches, input_ids, seq_lens = self._last_call
+        dev = self.device
+        ids = torch.empty(B, k, dtype=torch.int32, device=dev)
+        probs = torch.empty(B, k, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.vqa_qwen25vl_topk(self._h, _ptr(input_ids), _ptr(seq_lens), B, S, n_patches, k, float(temperature),
+                                            float(repetition_penalty), _ptr(ids), _ptr(probs), _ptr(self._workspace), self._workspace.numel(),
+                                            _stream_ptr(dev))
+        _check(rc, self._h, "vqa_qwen25vl_topk")
+        return ids, probs
 
     def debug_tensors(self, batch: int, seq_len: int, n_patches: int) -> Dict[str, torch.Tensor]:
         """Views into the workspace of the LAST call with these sizes (synchronise first). Parity investigations only."""

@@ -39,7 +39,7 @@ def _generation_config_penalty(checkpoint_path: str) -> float:
 class Qwen2VLModel(VQAScoreModel):
     video_mode = "direct"
     allows_image = True
-    supports_trace = False
+    supports_trace = True
 
     def __init__(self, model_name="qwen2.5-vl-7b", device="cuda", cache_dir=HF_CACHE_DIR, tokenizer=None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, config: Optional[Qwen25VLConfig] = None,
@@ -103,6 +103,37 @@ class Qwen2VLModel(VQAScoreModel):
                                   min_pixels=self.min_pixels, max_pixels=self.max_pixels)
 
     @torch.no_grad()
+    def forward_with_trace(self, images: List[str], texts: List[str], fps=None, question_template: str = default_question_template,
+                           answer_template: str = default_answer_template, max_new_tokens: int = 1, temperature: float = 1.0,
+                           score_position: str = "end", debug: bool = False, repetition_penalty: Optional[float] = None):
+        """Scores plus the per-sample trace dictionaries of the reference's forward_with_trace (qwen2vl_model.py:303-493; schema at
+        :469-487): the greedy token, the answer token's probability and the five most probable alternatives. With one generated position
+        `score_position` "start" and "end" coincide. The alternatives come from a top-k pass over the last position's logits
+        (engine.topk_last) under the same temperature / repetition penalty as the score."""
+        assert score_position in ("start", "end"), f"score_position must be 'start' or 'end', got '{score_position}'"
+        probs = self.forward(images, texts, fps=fps, question_template=question_template, answer_template=answer_template,
+                             max_new_tokens=max_new_tokens, temperature=temperature, debug=False, repetition_penalty=repetition_penalty)
+        pen = self.repetition_penalty if repetition_penalty is None else repetition_penalty
+        ids, top_p = self.engine.topk_last(5, temperature=temperature, repetition_penalty=pen)
+        ids, top_p = ids.cpu().tolist(), top_p.cpu().tolist()
+        dec = lambda t: self.tokenizer.decode([t]) if hasattr(self.tokenizer, "decode") else str(t)
+        special = {getattr(self.tokenizer, n, None) for n in ("eos_token_id", "bos_token_id", "pad_token_id")} - {None}
+        traces = []
+        for b, (p, answer_id) in enumerate(zip(probs.tolist(), self._last_answer_ids)):
+            generated = ids[b][0]                                   # generate(max_new_tokens=1, do_sample=False) emits the arg-max
+            if generated in special:
+                # the reference drops a trailing special token and then has nothing left to score (qwen2vl_model.py:395-419)
+                raise ValueError("No tokens available to score at the specified position")
+            alternatives = [dict(token_id=t, token_text=dec(t), probability=q) for t, q in zip(ids[b], top_p[b])]
+            detail = dict(position=0, expected_token_id=answer_id, expected_token_text=dec(answer_id), probability=p, top_alternatives=alternatives)
+            traces.append(dict(generated_text=dec(generated), generated_length=1, score_position=score_position, score_start_idx=0,
+                               scored_indices=[0], scored_tokens_text=dec(generated), probability=p, token_details=[detail]))
+            if debug:
+                print(f"sample {b}: generated {dec(generated)!r}; P(answer {dec(answer_id)!r}) = {p:.6f}; top-5 "
+                      f"{[(a['token_text'], round(a['probability'], 6)) for a in alternatives]}")
+        return probs, traces
+
+    @torch.no_grad()
     def forward(self, images: List[str], texts: List[str], fps=None, question_template: str = default_question_template,
                 answer_template: str = default_answer_template, max_new_tokens: int = 1, temperature: float = 1.0,
                 debug: bool = False, repetition_penalty: Optional[float] = None) -> torch.Tensor:
@@ -132,6 +163,7 @@ class Qwen2VLModel(VQAScoreModel):
             # one generated position => the reference truncates a multi-token answer to its first token ("Generated 1 tokens but need n,
             # adjusting", qwen2vl_model.py:259-263) and the geometric mean over one token is that token's probability
             answer_ids.append(ids[0])
+        self._last_answer_ids = list(answer_ids)
         probs = self.engine.score_prompts(patches, grids, prompts, answer_ids, image_of_sample=index, temperature=temperature,
                                           repetition_penalty=self.repetition_penalty if repetition_penalty is None else repetition_penalty)
         return probs.float().cpu()

@@ -198,3 +198,31 @@ def test_qwen_engine_matches_committed_hf_golden(golden_dir, dev, case):
           f"oracle bf16-vs-HF fp32 {gap:.3e}")
     assert e <= 2.0 * gap + 2e-2
     assert ep <= 2.0 * gap / 0.5 + 4e-2      # temperature 0.5 doubles every logit error (measured on B200: 3.2e-2 / 1.5e-2)
+
+
+def test_qwen_trace_topk(dev):
+    """forward_with_trace's top-5 alternatives (reference qwen2vl_model.py:439-447 torch.topk(softmax(scores / T), 5)): the engine's top-k pass
+    over the last position against the oracle's fp32 logits, with and without temperature / repetition penalty; the answer probability
+    of the scoring path must equal the probability the top-k pass assigns to the same token."""
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=4)
+    inp = qo.make_synthetic_inputs(cfg, 3, (84, 56), 12, ragged=True)
+    prompts = [x.tolist() for x in inp["input_ids"]]
+    o32 = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], mode="fp32", return_all=True)
+    eng = make_engine(cfg, sd, dev)
+    for T, pen in ((1.0, 1.0), (0.5, 1.3)):
+        p = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, inp["answer_ids"], temperature=T, repetition_penalty=pen).cpu()
+        ids, probs = eng.topk_last(5, temperature=T, repetition_penalty=pen)
+        ids, probs = ids.cpu(), probs.cpu()
+        assert bool((probs[:, :-1] >= probs[:, 1:]).all()) and bool((ids >= 0).all())
+        for b in range(3):
+            full = torch.stack([qo.answer_probability(o32["logits"][b], int(t), T, inp["input_ids"][b], pen) for t in ids[b]])
+            assert float((torch.log(probs[b]) - torch.log(full)).abs().max()) < 6e-2 / min(T, 1.0), (probs[b], full)
+            ref_top = torch.topk(torch.softmax(o32["logits"][b].float(), -1), 1).indices[0] if (T, pen) == (1.0, 1.0) else None
+            if ref_top is not None and float(torch.topk(torch.softmax(o32["logits"][b].float(), -1), 2).values.diff().abs()) > 2e-2:
+                assert int(ids[b, 0]) == int(ref_top)
+        # an answer token that is itself in the top-k list carries exactly the score's probability
+        top1 = [int(ids[b, 0]) for b in range(3)]
+        p_top = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, top1, temperature=T, repetition_penalty=pen).cpu()
+        ids2, probs2 = eng.topk_last(5, temperature=T, repetition_penalty=pen)
+        assert torch.equal(ids2.cpu(), ids) and float((probs2.cpu()[:, 0] - p_top).abs().max()) < 1e-5
