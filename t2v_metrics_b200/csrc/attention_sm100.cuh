@@ -1,6 +1,6 @@
 // tcgen05 flash attention for head_dim 64 (T5 encoder self-attention with relative-position bias + key padding mask,
-// CLIP ViT self-attention with 1/sqrt(d) scale). One CTA = one (sample, head, 128-query tile); the score tile never
-// leaves the SM:
+// CLIP ViT self-attention with 1/sqrt(d) scale). One CTA = one (sample, head), looping over its 128-query tiles (TMEM allocation,
+// barrier set-up and the bias table are paid once, the TMA producer runs ahead across query tiles); the score tile never leaves the SM:
 //
 //   warp 0   TMA producer : Q tile once, then K/V tiles (128 keys x 64) through a 2-stage smem ring
 //   warp 1   MMA issuer   : S = Q K^T   (UMMA 128x128x16, SS: both operands in 128B-swizzled smem, D in TMEM)
@@ -17,25 +17,14 @@
 
 namespace vqa {
 
-struct AttnTcParams {
-    __nv_bfloat16* o;         // [B*S, ldo], column h*64 + d
-    int ldo;
-    const int* seq_lens;      // [B] or nullptr
-    const float* bias_table;  // [H, 2S-1] or nullptr; index = key - query + S - 1
-    int S, H;
-    int q_col0, k_col0, v_col0;  // column of head 0 inside the packed [B*S, ld] buffer
-    float scale_log2e;        // (softmax scale) * log2(e)
-};
 
 constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
+constexpr bool ATTN_STREAM_DEFAULT = false;   // true: attn_tc_d64_stream_kernel is the production softmax stage
 constexpr int ATTN_POLY_DEFAULT = 0;   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
 
-inline size_t attn_tc_smem_bytes(int S) {
-    return 1024 + 6 * AT_TILE_BYTES + (size_t)(2 * S - 1 + 2 * AT_BIAS_PAD) * 4 + 8 + 160;
-}
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -96,326 +85,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-// One CTA owns one (sample, head) and walks its 128-row query tiles back to back: TMEM allocation, barrier set-up and the
-// bias table are paid once, and the TMA producer keeps running ahead across query-tile boundaries (Q is double buffered),
-// so only the very first tile of a CTA sees the full HBM/L2 latency.
-template <bool HAS_BIAS>
-__global__ void __launch_bounds__(192, 2)
-attn_tc_d64_v1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
-    const int h = blockIdx.y, b = blockIdx.z;
-    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const size_t row_base = (size_t)b * p.S;
-    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
-    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
-
-    // rows past the last valid query tile: deterministic zeros
-    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
-        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
-        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
-    }
-    if (nq == 0) return;
-
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                          // [2]
-    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
-    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
-    float* sBias = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES);   // entry i <-> rel = i - AT_BIAS_PAD, rel = key - query + S - 1
-    const int bias_n = 2 * p.S - 1 + 2 * AT_BIAS_PAD;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AT_TILE_BYTES + ((size_t)bias_n * 4 + 7) / 8 * 8);
-    uint64_t* q_full = bars;          // [2]
-    uint64_t* q_empty = bars + 2;     // [2]
-    uint64_t* kv_full = bars + 4;     // [2]
-    uint64_t* kv_empty = bars + 6;    // [2]
-    uint64_t* s_full = bars + 8;
-    uint64_t* s_empty = bars + 9;
-    uint64_t* p_full = bars + 10;
-    uint64_t* o_done = bars + 11;
-    uint64_t* o_free = bars + 12;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_qkv);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-        }
-        mbar_init(s_full, 1);
-        mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);
-        mbar_init(o_done, 1);
-        mbar_init(o_free, 4);
-        fence_barrier_init();
-        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
-        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
-        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
-        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
-        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
-        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
-    }
-    if (warp == 1) {
-        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
-        tmem_relinquish<1>();
-    }
-    if (HAS_BIAS) {
-        const float LOG2E = 1.4426950408889634f;
-        const int width = 2 * p.S - 1;
-        const float* src = p.bias_table + (size_t)h * width;
-        for (int i0 = threadIdx.x; i0 < bias_n; i0 += 4 * blockDim.x) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                const int r = i - AT_BIAS_PAD;
-                v[u] = (i < bias_n && r >= 0 && r < width) ? __ldg(src + r) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < bias_n) sBias[i] = v[u] * LOG2E;
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
-    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int qi = 0; qi < nq; ++qi) {
-                const int qb = qi & 1;
-                if (qi > 0) {   // (tile 0 was issued during set-up)
-                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
-                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
-                }
-                for (int j = 0; j < nkt; ++j) {
-                    const int g = qi * nkt + j;
-                    if (g == 0) continue;
-                    const int st = g & 1;
-                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
-                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
-                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
-            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
-            auto issue_pv = [&](int g) {
-                const int j = g % nkt, qi = g / nkt;
-                mbar_wait(p_full, (uint32_t)g & 1u);
-                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
-                tcgen05_fence_after();
-                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < AT_BK / 16; ++ks)
-                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
-                                (j > 0 || ks > 0) ? 1u : 0u);
-                umma_commit<1>(&kv_empty[g & 1]);
-                umma_commit<1>(o_done);
-            };
-            for (int qi = 0; qi < nq; ++qi) {
-                const int qb = qi & 1;
-                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
-                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
-                for (int j = 0; j < nkt; ++j) {
-                    const int g = qi * nkt + j;
-                    const int st = g & 1;
-                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
-                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
-                    tcgen05_fence_after();
-                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
-#pragma unroll
-                    for (int k = 0; k < AT_D / 16; ++k)
-                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                    umma_commit<1>(s_full);
-                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
-                    if (g > 0) issue_pv(g - 1);
-                }
-            }
-            issue_pv(total_tiles - 1);
-        }
-    } else {
-        // ===================== softmax / correction / epilogue: one thread per query row =====================
-        const uint32_t quad = warp & 3u;
-        const int row = quad * 32 + lane;
-        const uint32_t lane_off = (quad * 32u) << 16;
-        int g = 0;
-        for (int qi = 0; qi < nq; ++qi) {
-            const int q0 = qi * AT_BQ;
-            const int qrow = q0 + row;
-            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
-            if (q0 + (int)quad * 32 >= len) {
-                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
-                for (int j = 0; j < nkt; ++j, ++g) {
-                    mbar_wait(s_full, (uint32_t)g & 1u);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(s_empty);
-                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(p_full);
-                }
-                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(o_free);
-                if (qrow < p.S) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
-                }
-                continue;
-            }
-            float m_run = -INFINITY, l_run = 0.f;
-            const int bias_base = AT_BIAS_PAD + (p.S - 1) - qrow;   // + kcol
-            for (int j = 0; j < nkt; ++j, ++g) {
-                const int k0 = j * AT_BK;
-                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
-                mbar_wait(s_full, (uint32_t)g & 1u);
-                tcgen05_fence_after();
-                float t[4][32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < nch) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]);
-                    }
-                }
-                // S is in registers: hand the TMEM columns back so the next QK^T can start
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_empty);
-
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < nch) {
-                        if (HAS_BIAS) {
-                            const float* bp = sBias + bias_base + k0 + c * 32;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) t[c][i] = fmaf(t[c][i], p.scale_log2e, bp[i]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) t[c][i] *= p.scale_log2e;
-                        }
-                        if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (k0 + c * 32 + i >= len) t[c][i] = -INFINITY;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
-                            mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
-                        }
-                    }
-                }
-                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
-                float corr = 1.f;
-                bool rescale = false;
-                if (j == 0) {
-                    m_run = tile_max;
-                } else {
-                    const bool need = tile_max > m_run + 8.f;
-                    rescale = __any_sync(0xffffffffu, need);
-                    if (rescale) {
-                        const float m_new = fmaxf(m_run, tile_max);
-                        corr = fast_exp2(m_run - m_new);
-                        m_run = m_new;
-                    }
-                }
-                if (j > 0) {
-                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
-                    tcgen05_fence_after();
-                    if (rescale) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {   // 16 columns at a time keeps the score registers resident
-                            uint32_t ov[16];
-                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                        }
-                    }
-                }
-                // exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
-                float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[16];
-                    if (c < nch) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
-                            const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
-                            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-                            pk[i] = pack_bf16x2(e0, e1);
-                            pk[i + 1] = pack_bf16x2(e2, e3);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-                    }
-                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-                }
-                l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
-                tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full);
-            }
-            // ---- epilogue of this query tile: O / l
-            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
-            tcgen05_fence_after();
-            const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-                tmem_ld_wait();
-                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(o_free);
-                }
-                if (qrow < p.S) {
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-        }
-        tcgen05_fence_before();
-    }
-
-    __syncthreads();
-    tcgen05_fence_after();
-    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
-// v2 softmax stage. Same CTA skeleton and barrier protocol as v1 above (TMA warp, MMA warp, four softmax warps, two CTAs per SM);
-// what changes is the work per score, which is what bounds this kernel (head_dim 64: 512 tensor-core cycles per 128x128 tile against
-// >= 1024 MUFU cycles for its 16384 exponentials):
+// Softmax stage (round 2; round 1's kernel kept all 128 scores of a row in registers with scalar fp32 math, profiles/r01_ncu_kernels.md).
+// The work per score bounds this kernel (head_dim 64: 512 tensor-core cycles per 128x128 tile against >= 1024 MUFU cycles for its
+// 16384 exponentials and 64 KB of S through the TMEM read port):
 //   * the row maximum is taken over the RAW scores (FMNMX3, two scores per instruction); the reference point of the exponentials is
 //     the upper bound  scale * max_j s_ij + max(bias window)  -- softmax is invariant to it, P just carries a common factor <= 1;
 //   * scale, bias and reference are applied with packed fp32x2 FFMA2 / FADD2 (two scores per instruction);
@@ -849,12 +522,379 @@ attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Pa
                     unpack2(acc1, a2, a3);
                     l_run = l_run * corr + ((a0 + a1) + (a2 + a3));
                 }
+                if constexpr (PROF) { t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
+                if constexpr (PROF) { t1 = clock64(); pc[5] += t1 - t0; }
             }
             // ---- epilogue of this query tile: O / l
+            long long te0 = 0;
+            if constexpr (PROF) te0 = clock64();
+            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+            tcgen05_fence_after();
+            const float inv = (qrow < len) ? 1.f / l_run : 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_wait();
+                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_free);
+                }
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            if constexpr (PROF) {
+                const long long te1 = clock64();
+                pc[6] += te1 - te0;
+                pc[7] += te1 - tq0;
+                if (quad == 0 && lane == 0 && p.prof) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) atomicAdd(p.prof + i, (unsigned long long)pc[i]);
+                    atomicAdd(p.prof + 8, (unsigned long long)nkt);     // key tiles this warp went through
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
+}
+
+// Streaming variant of the softmax stage: the same CTA skeleton, barriers and MMA schedule, but a softmax thread never holds more than
+// two 32-key chunks of its row. The 128 scores of a tile are exponentiated against a reference fixed BEFORE the tile starts (the running
+// bound of the previous tiles; for the first key tile of a query tile a max-only pre-pass over S), so each chunk goes TMEM -> registers ->
+// exp2 -> P in one pass while the next chunk's tcgen05.ld is in flight; the tile's own maximum is collected on the way and, if it
+// exceeds the reference by more than 2^8, O and l are rescaled before the NEXT tile (P may exceed 1 inside a tile -- harmless in
+// bf16 / fp32, the normaliser l carries the same factor). Why: profiles/r02_attention.md -- the 128-register score array of the
+// two-pass stage costs spills at the 168-register cap of two CTAs per SM and unrolls to 67 KB of SASS (instruction-fetch stalls 11 %,
+// branch-resolve stalls 16 % of the samples); this loop is ~10 KB and needs ~110 registers.
+template <bool HAS_BIAS, bool ROUND>
+__global__ void __launch_bounds__(192, 2)
+attn_tc_d64_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
+    constexpr int POLY = 0;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const size_t row_base = (size_t)b * p.S;
+    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
+    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
+
+    // rows past the last valid query tile: deterministic zeros
+    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
+        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
+        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (nq == 0) return;
+
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
+    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
+    // sliding-window bias table, entry x <-> rel = x - W: !ROUND: float4 log2e * (b[rel], .., b[rel+3]); ROUND: the same four as bf16 (8 bytes)
+    uint8_t* sBiasQ = smem + 6 * AT_TILE_BYTES;
+    constexpr uint32_t BQ_ENTRY = ROUND ? 8u : 16u;
+    const int Wn = 128 * p.near_tiles + 127;
+    const int nQ = HAS_BIAS ? 2 * Wn + 1 : 0;
+    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (((size_t)nQ * BQ_ENTRY + 15) & ~size_t(15)));   // [8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8);
+    uint64_t* q_full = bars;          // [2]
+    uint64_t* q_empty = bars + 2;     // [2]
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        mbar_init(o_free, 4);
+        fence_barrier_init();
+        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
+        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
+        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
+        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
+        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    const float LOG2E = 1.4426950408889634f;
+    const float BSC = ROUND ? 1.0f : LOG2E;   // domain the table / constants are kept in
+    float b_left = 0.f, b_right = 0.f;      // constant bias of far tiles to the left / right of the diagonal
+    if (HAS_BIAS) {
+        const int width = 2 * p.S - 1;
+        const float* src = p.bias_table + (size_t)h * width;
+        b_left = __ldg(src) * BSC;
+        b_right = __ldg(src + width - 1) * BSC;
+        float lmax = -INFINITY;
+        for (int x = threadIdx.x; x < nQ; x += blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = min(max(x + k - Wn + (p.S - 1), 0), width - 1);   // rel = x + k - W, clamped to the table
+                v[k] = __ldg(src + idx) * BSC;
+            }
+            if constexpr (ROUND) reinterpret_cast<uint2*>(sBiasQ)[x] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            else                 reinterpret_cast<float4*>(sBiasQ)[x] = make_float4(v[0], v[1], v[2], v[3]);
+            lmax = fmaxf(lmax, v[0]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) sRed[warp] = lmax;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                if (qi > 0) {   // (tile 0 was issued during set-up)
+                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+                }
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    if (g == 0) continue;
+                    const int st = g & 1;
+                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
+            auto issue_pv = [&](int g) {
+                const int j = g % nkt, qi = g / nkt;
+                mbar_wait(p_full, (uint32_t)g & 1u);
+                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
+                tcgen05_fence_after();
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < AT_BK / 16; ++ks)
+                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
+                                (j > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[g & 1]);
+                umma_commit<1>(o_done);
+            };
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
+                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    const int st = g & 1;
+                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
+                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit<1>(s_full);
+                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
+                    if (g > 0) issue_pv(g - 1);
+                }
+            }
+            issue_pv(total_tiles - 1);
+        }
+    } else {
+        // ===================== softmax / correction / epilogue: one thread per query row, one 32-key chunk at a time =====================
+        const uint32_t quad = warp & 3u;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (quad * 32u) << 16;
+        float bmax_near = 0.f;
+        if (HAS_BIAS) {
+            bmax_near = sRed[0];
+#pragma unroll
+            for (int i = 1; i < 6; ++i) bmax_near = fmaxf(bmax_near, sRed[i]);
+        }
+        const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
+        const uint32_t bl2 = pack_bf16x2(b_left, b_left), br2 = pack_bf16x2(b_right, b_right);   // ROUND: far-tile bias as bf16 pairs
+        auto chunk_max = [](const uint32_t (&v)[32], float& m0, float& m1, float& m2, float& m3) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            }
+        };
+        int g = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q0 = qi * AT_BQ;
+            const int qrow = q0 + row;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
+            if (q0 + (int)quad * 32 >= len) {
+                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
+                for (int j = 0; j < nkt; ++j, ++g) {
+                    mbar_wait(s_full, (uint32_t)g & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full);
+                }
+                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            float m_run = 0.f, l_run = 0.f, corr_pend = 1.f;
+            bool pend = false;                 // O and l still have to be multiplied by corr_pend (decided at the end of the previous tile)
+            for (int j = 0; j < nkt; ++j, ++g) {
+                const int k0 = j * AT_BK;
+                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
+                const int dt = j - qi;
+                const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
+                const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
+                const uint32_t s_addr = tmem_S + lane_off;
+                mbar_wait(s_full, (uint32_t)g & 1u);
+                tcgen05_fence_after();
+                if (j == 0) {
+                    // first key tile of this query tile: no reference yet -> max-only pre-pass over S (S stays in TMEM for the real pass)
+                    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(s_addr + c * 32, v);
+                        tmem_ld_wait();
+                        if (k0 + c * 32 + 32 > len) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (k0 + c * 32 + i >= len) v[i] = 0xff800000u;
+                        }
+                        chunk_max(v, a0, a1, a2, a3);
+                    }
+                    const float raw = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                    m_run = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
+                } else {
+                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                    tcgen05_fence_after();
+                    if (pend) {
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr_pend);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
+                        }
+                        l_run *= corr_pend;
+                        pend = false;
+                    }
+                }
+                // ---- the tile: chunk c is exponentiated while chunk c + 1 is on its way from TMEM (ping-pong register buffers)
+                const float a_add = near ? -m_run : (ROUND ? -m_run : bias_ub - m_run);
+                const uint64_t addc = pack2(a_add, a_add);
+                const uint32_t bq = near ? smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * BQ_ENTRY : 0u;
+                const uint32_t bfar = dt < 0 ? bl2 : br2;
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                uint32_t bufA[32], bufB[32];
+                auto process = [&](uint32_t (&v)[32], int c) {
+                    if (c == nch - 1) {      // every chunk of S has left TMEM: the next QK^T may overwrite it
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_empty);
+                    }
+                    if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (k0 + c * 32 + i >= len) v[i] = 0xff800000u;
+                    }
+                    chunk_max(v, t0, t1, t2, t3);
+                    uint32_t pk[16];
+                    if (near) softmax_chunk<true, POLY, ROUND>(v, pk, bq + c * 32 * BQ_ENTRY, cc, addc, 0u, false, acc0, acc1);
+                    else      softmax_chunk<false, POLY, ROUND>(v, pk, 0u, cc, addc, bfar, HAS_BIAS, acc0, acc1);
+                    tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
+                };
+                tmem_ld_32x32b_x32(s_addr, bufA);
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 2) {
+                    tmem_ld_wait();                                              // bufA = chunk c
+                    if (c + 1 < nch) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, bufB);
+                    process(bufA, c);
+                    if (c + 1 < nch) {
+                        tmem_ld_wait();                                          // bufB = chunk c + 1
+                        if (c + 2 < nch) tmem_ld_32x32b_x32(s_addr + (c + 2) * 32, bufA);
+                        process(bufB, c + 1);
+                    }
+                }
+                if (nch < 4) {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll 1
+                    for (int c = nch; c < 4; ++c) tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, z);
+                }
+                {
+                    float a0, a1, a2, a3;
+                    unpack2(acc0, a0, a1);
+                    unpack2(acc1, a2, a3);
+                    l_run += (a0 + a1) + (a2 + a3);
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                // ---- did this tile outgrow the reference? then the NEXT tile starts by rescaling O and l (after P.V of this one retired)
+                const float raw = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                const float bound = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
+                if (__any_sync(0xffffffffu, bound > m_run + 8.f)) {
+                    const float m_new = fmaxf(m_run, bound);
+                    corr_pend = fast_exp2(m_run - m_new);
+                    m_run = m_new;
+                    pend = true;
+                }
+            }
+            // ---- epilogue of this query tile: O / l (a pending rescale would multiply both by the same factor: skipped)
             mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
             tcgen05_fence_after();
             const float inv = (qrow < len) ? 1.f / l_run : 0.f;
@@ -908,29 +948,32 @@ inline cudaError_t launch_attn_tc2_t(const CUtensorMap& tm, const AttnTc2Params&
     return cudaGetLastError();
 }
 
+template <bool HAS_BIAS, bool ROUND>
+inline cudaError_t launch_attn_stream_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
+    auto kernel = attn_tc_d64_stream_kernel<HAS_BIAS, ROUND>;
+    static std::atomic<size_t> max_set[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > max_set[dev & 63].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[dev & 63].store(smem, std::memory_order_release);
+    }
+    kernel<<<dim3(1, p.H, B), 192, smem, stream>>>(tm, p);
+    return cudaGetLastError();
+}
+
 // round_scores: reproduce the bf16 tensors of the reference's eager attention (scores, scores + bias) before the fp32 softmax.
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
                                   int B, int S, int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
-                                  bool round_scores, cudaStream_t stream, unsigned long long* prof = nullptr) {
+                                  bool round_scores, cudaStream_t stream_, unsigned long long* prof = nullptr) {
     CUtensorMap tm;
     if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
     static const int variant = [] { const char* v = getenv("VQA_ATTN_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();
-    if (variant == 1) {   // A/B: the round-1 kernel
-        AttnTcParams p;
-        p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
-        p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
-        p.scale_log2e = scale * 1.4426950408889634f;
-        const size_t smem = attn_tc_smem_bytes(S);
-        cudaError_t e = bias_table ? cudaFuncSetAttribute(attn_tc_d64_v1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                   : cudaFuncSetAttribute(attn_tc_d64_v1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        dim3 grid(1, H, B);
-        if (bias_table) attn_tc_d64_v1_kernel<true><<<grid, 192, smem, stream>>>(tm, p);
-        else            attn_tc_d64_v1_kernel<false><<<grid, 192, smem, stream>>>(tm, p);
-        return cudaGetLastError();
-    }
-    if (variant == 20) round_scores = false;      // A/B: v2 without the score rounding
-    if (variant == 21) round_scores = true;
+    if (variant == 20 || variant == 30) round_scores = false;      // A/B: without the score rounding
+    if (variant == 21 || variant == 31) round_scores = true;
+    const bool stream = variant >= 30 ? true : (variant >= 20 ? false : ATTN_STREAM_DEFAULT);
     AttnTc2Params p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -947,11 +990,15 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         auto kernel = attn_tc_d64_kernel<true, 0, true, true>;
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<dim3(1, H, B), 192, smem, stream>>>(tm, p);
+        kernel<<<dim3(1, H, B), 192, smem, stream_>>>(tm, p);
         return cudaGetLastError();
     }
-    if (bias_table) return round_scores ? launch_attn_tc2_t<true, 0, true>(tm, p, B, smem, stream) : launch_attn_tc2_t<true, 0, false>(tm, p, B, smem, stream);
-    return round_scores ? launch_attn_tc2_t<false, 0, true>(tm, p, B, smem, stream) : launch_attn_tc2_t<false, 0, false>(tm, p, B, smem, stream);
+    if (stream) {
+        if (bias_table) return round_scores ? launch_attn_stream_t<true, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<true, false>(tm, p, B, smem, stream_);
+        return round_scores ? launch_attn_stream_t<false, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<false, false>(tm, p, B, smem, stream_);
+    }
+    if (bias_table) return round_scores ? launch_attn_tc2_t<true, 0, true>(tm, p, B, smem, stream_) : launch_attn_tc2_t<true, 0, false>(tm, p, B, smem, stream_);
+    return round_scores ? launch_attn_tc2_t<false, 0, true>(tm, p, B, smem, stream_) : launch_attn_tc2_t<false, 0, false>(tm, p, B, smem, stream_);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

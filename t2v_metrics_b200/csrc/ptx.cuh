@@ -44,17 +44,20 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase flips (or the hint expires) instead of
+// re-issuing try_wait + branch in a tight loop. Measured on the attention kernel (profiles/r02_attention.md): without the hint the
+// producer / MMA warps' polling was 39 % of all issued instructions and shared its SMSPs with two of the four softmax warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

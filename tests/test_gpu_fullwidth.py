@@ -97,6 +97,31 @@ def run_clipt5_case(cfg, dev, B, L, lens, label_ids=(2163, 1), with_fp32=True, t
           f"\n[{tag}] rel.err (max abs): projector {proj_rel[0]:.2e} ({proj_rel[1]:.2e}) | encoder out {enc_rel[0]:.2e} ({enc_rel[1]:.2e}) | "
           f"decoder out {dec_rel[0]:.2e} ({dec_rel[1]:.2e}) | launches {eng.last_launch_count()}")
     out = dict(engine=s, ref=ref["scores"], err=err, self_noise=self_noise)
+    # ---- information: (a) the engine with the reference's cross-attention association (K/V projected for all encoder rows) instead of the
+    # absorbed one; (b) the REFERENCE with its vision tower on transformers' default attention (sdpa) instead of eager -- an equally
+    # legitimate run of the same model at the same precision
+    try:
+        eng_ref = ClipT5Engine(ClipT5Config(**dataclasses.asdict(cfg)), dev, cross_attention_mode="reference")
+        eng_ref.bind_engine_tensors({k: v for k, v in eng._weights.items()})
+        s2 = eng_ref.score_tensors(inp["pixels"].to(dev), i32(inp["input_ids"]), i32(inp["text_lens"]), i32(inp["labels"]))
+        torch.cuda.synchronize()
+        d2 = eng_ref.debug_tensors(B, B, L, len(label_ids))
+        print(f"[{tag}] engine, reference cross-attention association: max|dscore| {float((s2.cpu() - ref['scores']).abs().max()):.3e}  "
+              f"decoder out rel.err {_rel(d2['dec_out'].cpu(), ref['dec_hidden'].cpu())[0]:.2e}")
+        del eng_ref, d2
+    except Exception as e:  # noqa
+        print(f"[{tag}] reference-association run failed: {e!r}")
+    try:
+        mods[0].config._attn_implementation = "sdpa"
+        for m_ in mods[0].modules():
+            if hasattr(m_, "config") and hasattr(m_.config, "_attn_implementation"):
+                m_.config._attn_implementation = "sdpa"
+        r_sdpa = fwd(mods, True)
+        out["ref_impl_noise"] = float((r_sdpa["scores"] - ref["scores"]).abs().max())
+        print(f"[{tag}] reference with its CLIP tower on sdpa (transformers' default) instead of eager: max|dscore| vs the eager reference "
+              f"{out['ref_impl_noise']:.3e}   {[round(float(x), 5) for x in r_sdpa['scores']]}")
+    except Exception as e:  # noqa
+        print(f"[{tag}] sdpa reference run failed: {e!r}")
     if with_fp32:
         try:
             del mods, eng, dbg
