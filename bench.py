@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--video", action="store_true", help="qwen: SURVEY 8(d) config 5 shape (grid 8x16x16, S=576, batch 8)")
     ap.add_argument("--pairs", type=int, default=0, help="clip-flant5: SURVEY 8(d) config 4 -- a JOB of this many pairs sharded "
                     "contiguously over the ranks in batches of --batch (+ tail), one all-gather; a step = the whole job; strong scaling")
+    ap.add_argument("--fuse-norms", type=int, default=-1, help="1/0: fold the encoder's T5LayerNorms into the GEMMs (default: the engine's default)")
+    ap.add_argument("--round-scores", type=int, default=-1, help="1/0: bf16 score tensors in the attention like the reference's eager path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-eager-bf16-on-this-GPU comparison point (hf_gpu_baseline)")
     ap.add_argument("--config1", action="store_true", help="--impl reference: BASELINE config 1 only (clip-flant5-xl, the reference's 4 PNGs x 4 prompts, batch 1, CPU)")
@@ -430,7 +432,12 @@ def run_engine(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = CLIPT5_MODELS[args.model]["config"]()
-    eng = ClipT5Engine(cfg, dev)
+    ekw = {}
+    if args.fuse_norms >= 0:
+        ekw["fuse_norms"] = bool(args.fuse_norms)
+    if args.round_scores >= 0:
+        ekw["round_attention_scores"] = bool(args.round_scores)
+    eng = ClipT5Engine(cfg, dev, **ekw)
     eng.bind_engine_tensors(synthetic_engine_weights(cfg, dev, seed=0))
     B, L = args.batch, args.text_len
     if args.pairs:

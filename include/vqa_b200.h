@@ -63,7 +63,11 @@ typedef struct {
     int32_t image_token_id;   /* -200, t2v_metrics/constants.py:7 */
     int32_t pad_token_id;     /* 0 */
     int32_t decoder_start_id; /* 0 */
-    int32_t emulate_bf16_rounding; /* 1: round scores/bias adds to bf16 where the reference's eager path does */
+    int32_t emulate_bf16_rounding; /* bit flags. 1: the small decoder kernels round scores / bias adds to bf16 where the reference's eager path
+                                      does. 2: the tcgen05 attention forms the reference's bf16 score tensors before the softmax (off: fp32
+                                      scores). 4: fuse the encoder's T5LayerNorms into the GEMMs around them -- needs t5.enc.{i}.qkv_g / wi_g
+                                      (= qkv . diag(ln0), wi . diag(ln1)); the o / wo epilogues emit row sums of squares, the qkv / wi
+                                      epilogues apply rsqrt(mean(x^2) + eps) to their accumulator rows */
     int32_t cross_attention_mode;  /* 0: absorbed (q.(Wk x) = (Wk^T q).x, needs t5.dec.{i}.ckT); 1: project K/V of all
                                       encoder rows in every decoder layer, as modeling_t5.py:297-299 does */
 } vqa_clipt5_config;
@@ -252,6 +256,15 @@ int32_t vqa_resample_table(int32_t in_size, int32_t out_size, int32_t first, int
 int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc,
                      int32_t M, int32_t N, int32_t K, const void* bias, const void* residual, int32_t ldr,
                      int32_t epilogue, int32_t gate_up_offset, int32_t variant, void* stream);
+
+/* vqa_op_gemm_bf16 with the fused-RMSNorm hooks the encoder uses when emulate_bf16_rounding & 4 (T5LayerNorm, modeling_t5.py:55-68, folded
+ * into the GEMMs around it). ssq_in DEVICE float [M, stride] or NULL: partial sums of squares of the rows of A; the epilogue multiplies
+ * accumulator row m by rsqrt(sum_i ssq_in[m][i] / norm_dim + eps) before the Linear's bf16 rounding (W must carry the norm's gain:
+ * W . diag(gamma)). ssq_out DEVICE float [M, stride] or NULL (epilogue 0 only): receives the partial sums of squares of the bf16 rows this
+ * launch stores, slots [0, *parts_out); the caller zeroes the buffer first. stride % 4 == 0. No bias. */
+int vqa_op_gemm_bf16_normfuse(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M, int32_t N,
+                              int32_t K, const void* residual, int32_t ldr, int32_t epilogue, int32_t gate_up_offset, const float* ssq_in,
+                              float* ssq_out, int32_t stride, int32_t norm_dim, float eps, int32_t* parts_out, void* stream);
 
 /* Fused lm_head + log-softmax gather: logprob[m] = (h[m].W[label[m]]) - logsumexp_n(h[m].W[n]); logits never stored.
  * scratch: DEVICE float, >= 4*M*ceil(N/128) + M floats. */

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "vqa_create_qwen25vl", "vqa_qwen25vl_set_rope", "vqa_qwen25vl_workspace_bytes", "vqa_qwen25vl_score",
     "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess", "vqa_resample_table", "vqa_qwen_preprocess_plan",
     "vqa_qwen_preprocess", "vqa_clipt5_debug_layout", "vqa_qwen25vl_debug_layout", "vqa_set_gemm_schedule",
-    "vqa_debug_attention_d64_phases", "vqa_qwen25vl_topk",
+    "vqa_debug_attention_d64_phases", "vqa_qwen25vl_topk", "vqa_op_gemm_bf16_normfuse",
 ]
 
 VQA_DTYPE_BF16, VQA_DTYPE_F32, VQA_DTYPE_I32 = 0, 1, 2
@@ -92,6 +92,9 @@ def load() -> C.CDLL:
     lib.vqa_destroy.restype = None
     lib.vqa_op_gemm_bf16.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.vqa_op_gemm_bf16.restype = C.c_int
+    lib.vqa_op_gemm_bf16_normfuse.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, i32, f32,
+                                              C.POINTER(i32), vp]
+    lib.vqa_op_gemm_bf16_normfuse.restype = C.c_int
     lib.vqa_op_lmhead_logprob.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.vqa_op_lmhead_logprob.restype = C.c_int
     lib.vqa_op_attention_d64.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, i32, i32, vp]

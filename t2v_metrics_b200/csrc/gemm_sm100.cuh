@@ -52,6 +52,16 @@ struct GemmParams {
     const uint32_t* penalty_bitmap;   // [M, penalty_words] or nullptr
     int penalty_words;
     float penalty;
+    // RMSNorm folded into the GEMMs around it (T5LayerNorm modeling_t5.py:55-68 / Qwen2RMSNorm): the GEMM that WRITES the residual stream
+    // (EPI_STORE with a residual) also emits, per row, the sum of squares of the bf16 values it stores for its slice of columns
+    // (ssq_out[m * ssq_out_parts + n_tile * parts_per_tile + column_half]); the GEMM that CONSUMES the stream takes the un-normalised rows
+    // as its A operand with gamma folded into W, sums the partials and multiplies its fp32 accumulator row by rsqrt(sum / dim + eps)
+    // before the bf16 rounding of the Linear's output (EPI_STORE, EPI_GATED_*). No normalised copy of the stream is ever written.
+    float* ssq_out;
+    int ssq_out_parts;
+    const float* ssq_in;
+    int ssq_in_parts;
+    float ssq_inv_dim, ssq_eps;
     // batching: `num_batches` independent GEMMs of the same M,N,K share one launch; batch b reads A at
     // (row + b*a_row_off, k + b*a_k_off), W at (row + b*w_row_off, k + b*w_k_off) and writes C + b*c_batch_stride.
     int num_batches;
@@ -279,6 +289,16 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const int m = (m_blk * CG + (int)cta_rank) * BLOCK_M + row_in_tile;
             const bool row_ok = m < p.M;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+            float row_scale = 1.0f;     // fused RMSNorm of the A rows (consumer side)
+            if (p.ssq_in && row_ok) {
+                const float* sp = p.ssq_in + (size_t)m * p.ssq_in_parts;
+                float ssum = 0.f;
+                for (int i = 0; i < p.ssq_in_parts; i += 4) {
+                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(sp + i));
+                    ssum += (v4.x + v4.y) + (v4.z + v4.w);
+                }
+                row_scale = rsqrtf(ssum * p.ssq_inv_dim + p.ssq_eps);
+            }
 
             if constexpr (epi_is_gated(EPI)) {
                 const int n_out0 = n_blk * OUT_TILE_COLS;
@@ -297,8 +317,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             uint32_t w[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                float g0 = __uint_as_float(g[j * 8 + 2 * e]), g1 = __uint_as_float(g[j * 8 + 2 * e + 1]);
-                                float u0 = __uint_as_float(u[j * 8 + 2 * e]), u1 = __uint_as_float(u[j * 8 + 2 * e + 1]);
+                                float g0 = __uint_as_float(g[j * 8 + 2 * e]) * row_scale, g1 = __uint_as_float(g[j * 8 + 2 * e + 1]) * row_scale;
+                                float u0 = __uint_as_float(u[j * 8 + 2 * e]) * row_scale, u1 = __uint_as_float(u[j * 8 + 2 * e + 1]) * row_scale;
                                 if (p.bias) {   // [gate bias | up bias], `gate_up_offset` apart like the weight rows
                                     const int n = n_out0 + c * 32 + j * 8 + 2 * e;
                                     if (n < p.N / 2) {
@@ -416,6 +436,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 };
                 prefetch(c_begin);
+                float ssq_acc = 0.f;        // producer side of the fused RMSNorm: sum of squares of the bf16 values this thread stores
                 mbar_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
 #pragma unroll 1
@@ -435,7 +456,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             if (nc + j * 8 < p.N) {
                                 float f[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) * row_scale;
                                 {
                                     float2 b0 = unpack_bf16x2(bcur[j].x), b1 = unpack_bf16x2(bcur[j].y);
                                     float2 b2 = unpack_bf16x2(bcur[j].z), b3 = unpack_bf16x2(bcur[j].w);
@@ -459,10 +480,17 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                 uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                                 *reinterpret_cast<uint4*>(crow + j * 8) = o;
+                                if (p.ssq_out) {
+                                    const float2 s0 = unpack_bf16x2(o.x), s1 = unpack_bf16x2(o.y), s2 = unpack_bf16x2(o.z), s3 = unpack_bf16x2(o.w);
+                                    ssq_acc += (s0.x * s0.x + s0.y * s0.y) + (s1.x * s1.x + s1.y * s1.y) + (s2.x * s2.x + s2.y * s2.y) +
+                                               (s3.x * s3.x + s3.y * s3.y);
+                                }
                             }
                         }
                     }
                 }
+                if (p.ssq_out && row_ok)
+                    p.ssq_out[(size_t)m * p.ssq_out_parts + n_blk * Cfg::LSE_PARTS + (SPLIT ? half : 0)] = ssq_acc;
             }
             // release this accumulator stage back to the MMA warp
             tcgen05_fence_before();
@@ -560,6 +588,10 @@ struct PerDeviceOnce {
         return e;
     }
 };
+
+// number of (row) partial sums a residual-writing GEMM of N columns emits with this tile shape (GemmParams::ssq_out_parts)
+template <int BLOCK_N, int CG>
+inline int gemm_ssq_parts(int N) { return ((N + BLOCK_N - 1) / BLOCK_N) * GemmConfig<BLOCK_N, CG>::LSE_PARTS; }
 
 struct GemmLaunch {
     const __nv_bfloat16* A; int lda;   // [a_rows, a_cols] visible to TMA (defaults: M x K)

@@ -21,6 +21,9 @@
 using namespace vqa;
 typedef __nv_bfloat16 bf16;
 
+// bits of vqa_clipt5_config::emulate_bf16_rounding (see include/vqa_b200.h)
+constexpr int VQA_FLAG_ROUND_DECODER = 1, VQA_FLAG_ROUND_ATTN_SCORES = 2, VQA_FLAG_FUSE_NORMS = 4;
+
 // ------------------------------------------------------------------------------------------------ handle
 struct BoundTensor {
     const void* data = nullptr;
@@ -34,6 +37,7 @@ struct VitLayerW {
 };
 struct T5EncLayerW {
     const bf16 *ln0, *qkv, *o, *ln1, *wi, *wo;
+    const bf16 *qkv_g = nullptr, *wi_g = nullptr;   // fused-norm mode: qkv . diag(ln0), wi . diag(ln1) (gamma folded into the weight's K axis)
 };
 struct T5DecLayerW {
     const bf16 *ln0, *qkv, *o, *ln1, *cq, *ckv, *co, *ln2, *wi, *wo;
@@ -148,10 +152,51 @@ static int pick_variant(int M, int N, int epi) {
     return 2562;
 }
 
+// partial sums per row that a residual-writing GEMM with this tile variant emits for N output columns (GemmParams::ssq_out)
+static int ssq_parts_for(int variant, int N) {
+    switch (variant) {
+        case 2562: return gemm_ssq_parts<256, 2>(N);
+        case 2561: return gemm_ssq_parts<256, 1>(N);
+        case 1282: return gemm_ssq_parts<128, 2>(N);
+        case 1281: return gemm_ssq_parts<128, 1>(N);
+        case 641:  return gemm_ssq_parts<64, 1>(N);
+        default:   return gemm_ssq_parts<32, 1>(N);
+    }
+}
+
+// Sum of squares of every row of x (bf16 [rows, D]) into slot 0 of its partial-sum row (the other slots are zero): seeds the fused
+// RMSNorm chain for the encoder's input embeddings. One warp per row.
+__global__ void __launch_bounds__(256) row_ssq_kernel(const bf16* __restrict__ x, float* __restrict__ ssq, int rows, int D, int stride) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+    float ss = 0.f;
+    for (int i = lane; i < D / 8; i += 32) {
+        const uint4 v = xr[i];
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(u[e]);
+            ss = fmaf(f.x, f.x, ss);
+            ss = fmaf(f.y, f.y, ss);
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) ssq[(size_t)row * stride] = ss;
+}
+
 // Launch C = epi(A W^T). Returns cudaError_t. `launch_counter` is incremented per kernel.
+struct NormFuse {            // fused RMSNorm hooks of one GEMM launch (see GemmParams::ssq_*)
+    float* ssq_out = nullptr;       // producer: partial sums of squares of the rows this GEMM writes ([M, ssq_stride])
+    const float* ssq_in = nullptr;  // consumer: partial sums of the rows of A
+    int stride = 0;                 // floats per row in both buffers (multiple of 4; unused slots are zero)
+    float inv_dim = 0.f, eps = 0.f;
+};
 static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M, int N,
                             int K, const bf16* bias, const bf16* residual, int ldr, int epi, int gate_up_offset,
-                            int variant, int num_sms, cudaStream_t st, int64_t* launch_counter, bool c_f32 = false) {
+                            int variant, int num_sms, cudaStream_t st, int64_t* launch_counter, bool c_f32 = false,
+                            const NormFuse* nf = nullptr) {
     GemmLaunch g;
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = w_rows;
     memset(&g.p, 0, sizeof(g.p));
@@ -159,6 +204,11 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
     g.p.ldr = ldr; g.p.gate_up_offset = gate_up_offset;
     if (c_f32 && epi != EPI_STORE) return cudaErrorInvalidValue;
     g.p.c_f32 = c_f32 ? 1 : 0;
+    if (nf) {
+        g.p.ssq_out = nf->ssq_out; g.p.ssq_in = nf->ssq_in; g.p.ssq_out_parts = g.p.ssq_in_parts = nf->stride;
+        g.p.ssq_inv_dim = nf->inv_dim; g.p.ssq_eps = nf->eps;
+        if (nf->ssq_out && (epi != EPI_STORE || c_f32)) return cudaErrorInvalidValue;
+    }
     if (launch_counter) ++*launch_counter;
     if (variant == 0) variant = pick_variant(M, N, epi);
     switch (epi) {
@@ -413,6 +463,10 @@ extern "C" int vqa_finalize_weights(vqa_handle* h) {
         L.ln0 = need(h, p + "ln0", Dm, 1, ok); L.qkv = need(h, p + "qkv", 3 * inner, Dm, ok);
         L.o = need(h, p + "o", Dm, inner, ok); L.ln1 = need(h, p + "ln1", Dm, 1, ok);
         L.wi = need(h, p + "wi", 2 * c.d_ff, Dm, ok); L.wo = need(h, p + "wo", Dm, c.d_ff, ok);
+        if (c.emulate_bf16_rounding & VQA_FLAG_FUSE_NORMS) {
+            L.qkv_g = need(h, p + "qkv_g", 3 * inner, Dm, ok);
+            L.wi_g = need(h, p + "wi_g", 2 * c.d_ff, Dm, ok);
+        }
     }
     h->dec.resize(c.dec_layers);
     for (int i = 0; i < c.dec_layers; ++i) {
@@ -444,12 +498,13 @@ struct ClipT5Workspace {
     // vision
     size_t patches, patch_out, hv, vn, vqkv, vattn, vmlp, proj1, proj2;
     // t5
-    size_t x, xn, qkv, attn, ff, bias_table, seq_lens, ckv;
+    size_t x, xn, qkv, attn, ff, bias_table, seq_lens, ckv, ssq_a, ssq_b;
     size_t y, yn, dqkv, dattn, dq, dff;
     size_t xt, qt, csc, cctx;   // absorbed cross-attention: Xenc^T, q~ = Wk^T q, scores/probs, context sum p.h
     size_t lse_max, lse_sum, label_logit;
     size_t total;
 };
+static int ssq_stride(int d_model) { return (d_model / 32 + 3) / 4 * 4; }
 static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L, int T) {
     const vqa_clipt5_config& c = h->cfg;
     const int P = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
@@ -473,6 +528,10 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     w.qkv = pl.take(M * 3 * inner * 2);
     w.attn = pl.take(M * inner * 2);
     w.ff = pl.take(M * c.d_ff * 2);
+    // fused-norm mode: per-row partial sums of squares of the residual stream, two buffers (the stream is rewritten twice per layer);
+    // worst case one partial per 32 output columns
+    w.ssq_a = pl.take(M * (size_t)ssq_stride(c.d_model) * 4);
+    w.ssq_b = pl.take(M * (size_t)ssq_stride(c.d_model) * 4);
     w.bias_table = pl.take((size_t)c.n_heads * (2 * S - 1) * 4);
     w.seq_lens = pl.take((size_t)B * 4);
     const size_t Sp = (size_t)(S + 7) / 8 * 8;
@@ -541,7 +600,9 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     h->launches = 0;
     int64_t* lc = &h->launches;
     const int nsm = h->num_sms;
-    const int rnd = c.emulate_bf16_rounding;
+    const int rnd = c.emulate_bf16_rounding & VQA_FLAG_ROUND_DECODER;
+    const bool round_attn = (c.emulate_bf16_rounding & VQA_FLAG_ROUND_ATTN_SCORES) != 0;
+    const bool fuse_norms = (c.emulate_bf16_rounding & VQA_FLAG_FUSE_NORMS) != 0;
 
     const int grid_w = c.image_size / c.patch_size;
     const int P = grid_w * grid_w;
@@ -622,7 +683,7 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * n_images * (double)Hv * (P + 1) * (P + 1) * 64, st);
             TRY(cuda_ok(run_flash(P_(w.vqkv), P_(w.vqkv) + Dv, P_(w.vqkv) + 2 * Dv, 3 * Dv, P_(w.vattn), Dv, n_images, P + 1,
-                                  Hv, nullptr, nullptr, 0.125f, 0, rnd != 0, st, lc), "vit attention"));
+                                  Hv, nullptr, nullptr, 0.125f, 0, round_attn, st, lc), "vit attention"));
         }
         TRY(gemm_f32res(P_(w.vattn), Dv, Lw.out_w, Dv, Dv, hv, Mv, Dv, Dv, Lw.out_b));
         TRY(lnorm(hv, Lw.ln2_w, Lw.ln2_b, P_(w.vn), Mv));
@@ -656,20 +717,63 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
     }
 
     // ---------------- T5 encoder ----------------
+    // fuse_norms: the two T5LayerNorms of a layer never run as kernels. The GEMMs that write the residual stream (o, wo) leave per-row
+    // partial sums of squares of what they stored; the GEMMs that read it (qkv, wi) take x itself with gamma folded into their weights and
+    // scale their accumulator rows by rsqrt(mean(x^2) + eps) in the epilogue (gemm_sm100.cuh, GemmParams::ssq_*).
+    NormFuse nf_cons, nf_prod;
+    float* ssq_cur = reinterpret_cast<float*>(ws + w.ssq_a);
+    float* ssq_nxt = reinterpret_cast<float*>(ws + w.ssq_b);
+    if (fuse_norms) {
+        const int parts = ssq_parts_for(pick_variant(M, Dm, EPI_STORE), Dm);
+        const int stride = (parts + 3) / 4 * 4;
+        if (stride > ssq_stride(Dm)) return fail(h, VQA_ERR_UNSUPPORTED, "fused norms: partial-sum stride exceeds the workspace plan");
+        nf_cons.stride = nf_prod.stride = stride;
+        nf_cons.inv_dim = 1.0f / (float)Dm;
+        nf_cons.eps = c.t5_ln_eps;
+        ProfScope ps(h, CAT_NORM, 0, st);
+        *lc += 3;
+        TRY(cuda_ok(cudaMemsetAsync(ssq_cur, 0, (size_t)M * stride * 4, st), "ssq clear"));
+        TRY(cuda_ok(cudaMemsetAsync(ssq_nxt, 0, (size_t)M * stride * 4, st), "ssq clear"));
+        row_ssq_kernel<<<(M + 7) / 8, 256, 0, st>>>(P_(w.x), ssq_cur, M, Dm, stride);
+        TRY(cuda_ok(cudaSuccess, "row ssq"));
+    }
+    auto gemm_nf = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M_, int N_, int K_, const bf16* res, int ldr,
+                       int epi, int gate_off, const NormFuse& nf) -> int {
+        const double n_out = epi_is_gated(epi) ? N_ / 2 : N_;
+        const double bytes = 2.0 * ((double)M_ * K_ + (double)N_ * K_ + (double)M_ * n_out * (res ? 2 : 1));
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st, bytes);
+        return cuda_ok(run_gemm(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, nullptr, res, ldr, epi, gate_off, 0, nsm, st, lc, false, &nf), "gemm");
+    };
     for (int l = 0; l < c.enc_layers; ++l) {
         const T5EncLayerW& Lw = h->enc[l];
-        TRY(rms(P_(w.x), Lw.ln0, P_(w.xn), M));
-        TRY(gemm(P_(w.xn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        if (fuse_norms) {
+            nf_cons.ssq_in = ssq_cur;
+            TRY(gemm_nf(P_(w.x), Dm, Lw.qkv_g, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, 0, EPI_STORE, 0, nf_cons));
+        } else {
+            TRY(rms(P_(w.x), Lw.ln0, P_(w.xn), M));
+            TRY(gemm(P_(w.xn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.qkv), 3 * inner, M, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        }
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * S * S * 64, st);
             TRY(cuda_ok(run_flash(P_(w.qkv), P_(w.qkv) + inner, P_(w.qkv) + 2 * inner, 3 * inner, P_(w.attn), inner, B, S, H,
-                                  seq_lens, bias_table, 1.0f, c.rel_max_distance, rnd != 0, st, lc), "t5 encoder attention"));
+                                  seq_lens, bias_table, 1.0f, c.rel_max_distance, round_attn, st, lc), "t5 encoder attention"));
         }
-        TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
-        TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
-        TRY(gemm(P_(w.xn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, nullptr, 0, EPI_GATED_GELU,
-                 c.d_ff));
-        TRY(gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm, EPI_STORE, 0));
+        if (fuse_norms) {
+            nf_prod.ssq_out = ssq_nxt;
+            TRY(gemm_nf(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, P_(w.x), Dm, EPI_STORE, 0, nf_prod));
+            std::swap(ssq_cur, ssq_nxt);
+            nf_cons.ssq_in = ssq_cur;
+            TRY(gemm_nf(P_(w.x), Dm, Lw.wi_g, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, 0, EPI_GATED_GELU, c.d_ff, nf_cons));
+            nf_prod.ssq_out = ssq_nxt;
+            TRY(gemm_nf(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, P_(w.x), Dm, EPI_STORE, 0, nf_prod));
+            std::swap(ssq_cur, ssq_nxt);
+        } else {
+            TRY(gemm(P_(w.attn), inner, Lw.o, inner, Dm, P_(w.x), Dm, M, Dm, inner, nullptr, P_(w.x), Dm, EPI_STORE, 0));
+            TRY(rms(P_(w.x), Lw.ln1, P_(w.xn), M));
+            TRY(gemm(P_(w.xn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.ff), c.d_ff, M, 2 * c.d_ff, Dm, nullptr, nullptr, 0, EPI_GATED_GELU,
+                     c.d_ff));
+            TRY(gemm(P_(w.ff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.x), Dm, M, Dm, c.d_ff, nullptr, P_(w.x), Dm, EPI_STORE, 0));
+        }
     }
     TRY(rms(P_(w.x), h->enc_final_ln, P_(w.xn), M));  // encoder output lives in xn from here on
     const int Sp = (S + 7) / 8 * 8;
@@ -946,6 +1050,28 @@ extern "C" int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32
     cudaError_t e = run_gemm((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, (const bf16*)bias,
                              (const bf16*)residual, ldr, epilogue, gate_up_offset, variant, device_sms(),
                              (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// vqa_op_gemm_bf16 with the fused-RMSNorm hooks (GemmParams::ssq_*): ssq_in [M, stride] partial sums of squares of the rows of A (the
+// epilogue scales accumulator row m by rsqrt(sum / norm_dim + eps)), ssq_out [M, stride] receives this GEMM's partial sums of squares of the
+// rows it stores (epilogue 0 only); either may be NULL. *parts_out (HOST, optional) = number of slots of ssq_out this launch writes.
+extern "C" int vqa_op_gemm_bf16_normfuse(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M,
+                                         int32_t N, int32_t K, const void* residual, int32_t ldr, int32_t epilogue, int32_t gate_up_offset,
+                                         const float* ssq_in, float* ssq_out, int32_t stride, int32_t norm_dim, float eps, int32_t* parts_out,
+                                         void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || stride <= 0 || stride % 4 || norm_dim <= 0)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "bad gemm argument");
+    if (lda % 8 || ldw % 8 || ldc % 8 || N % 8 || K % 8) return fail(nullptr, VQA_ERR_INVALID_ARG, "gemm: ld/N/K must be multiples of 8");
+    const int variant = pick_variant(M, N, epilogue);
+    const int parts = ssq_parts_for(variant, epi_is_gated(epilogue) ? N / 2 : N);
+    if (parts_out) *parts_out = parts;
+    if (ssq_out && parts > stride) return fail(nullptr, VQA_ERR_INVALID_ARG, "ssq stride smaller than the partial sums this launch writes");
+    NormFuse nf;
+    nf.ssq_in = ssq_in; nf.ssq_out = ssq_out; nf.stride = stride; nf.inv_dim = 1.0f / (float)norm_dim; nf.eps = eps;
+    cudaError_t e = run_gemm((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, nullptr, (const bf16*)residual, ldr, epilogue,
+                             gate_up_offset, variant, device_sms(), (cudaStream_t)stream, nullptr, false, &nf);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -33,7 +33,12 @@ def _check(rc: int, handle=None, what: str = ""):
         raise RuntimeError(f"libvqa_b200 {what} failed (status {rc}): {_lib.last_error(handle)}")
 
 
-def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device) -> Dict[str, torch.Tensor]:
+def fold_norm_gain(weight: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """W . diag(gamma) in fp32, rounded to bf16 once: the weight the fused-norm GEMMs use (their epilogue supplies rsqrt(mean(x^2) + eps))."""
+    return (weight.float() * gamma.float()[None, :]).to(torch.bfloat16).contiguous()
+
+
+def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device, fuse_norms: bool = False) -> Dict[str, torch.Tensor]:
     """HF-named CLIP-FlanT5 weights (CLIPVisionModel under `vision_tower.`, `mm_projector.*`,
     T5ForConditionalGeneration names) -> the engine's fused bf16 layout:
       * q/k/v projections concatenated row-wise ([3*inner, d]) so one GEMM produces the packed QKV buffer;
@@ -83,6 +88,9 @@ def convert_state_dict(sd: Dict[str, torch.Tensor], cfg: ClipT5Config, device) -
         put(q + "ln1", sd[p + "1.layer_norm.weight"])
         put(q + "wi", torch.cat([sd[p + "1.DenseReluDense.wi_0.weight"], sd[p + "1.DenseReluDense.wi_1.weight"]], dim=0))
         put(q + "wo", sd[p + "1.DenseReluDense.wo.weight"])
+        if fuse_norms:
+            out[q + "qkv_g"] = fold_norm_gain(out[q + "qkv"], out[q + "ln0"])
+            out[q + "wi_g"] = fold_norm_gain(out[q + "wi"], out[q + "ln1"])
     for l in range(cfg.dec_layers):
         p, q = f"decoder.block.{l}.layer.", f"t5.dec.{l}."
         a, c = p + "0.SelfAttention.", p + "1.EncDecAttention."
@@ -104,7 +112,10 @@ class ClipT5Engine:
     """One engine = one model replica on one GPU (one process per GPU)."""
 
     def __init__(self, cfg: ClipT5Config, device="cuda:0", emulate_bf16_rounding: bool = True,
-                 cross_attention_mode: str = "absorbed"):
+                 cross_attention_mode: str = "absorbed", round_attention_scores: bool = False, fuse_norms: bool = False):
+        """round_attention_scores: form the bf16 score tensors of the reference's eager attention before the softmax (off: fp32 scores --
+        closer to the exact result, and measured no closer to the bf16 reference). fuse_norms: fold the encoder's
+        T5LayerNorms into the GEMMs around them (no normalised copy of the residual stream; a different, equally valid rounding point)."""
         if not torch.cuda.is_available():
             raise RuntimeError("ClipT5Engine needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -117,8 +128,9 @@ class ClipT5Engine:
             n_heads=cfg.n_heads, d_ff=cfg.d_ff, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, vocab=cfg.vocab,
             rel_buckets=cfg.rel_buckets, rel_max_distance=cfg.rel_max_distance, t5_ln_eps=cfg.t5_ln_eps,
             image_token_id=IMAGE_TOKEN_INDEX, pad_token_id=cfg.pad_token_id, decoder_start_id=cfg.decoder_start_id,
-            emulate_bf16_rounding=1 if emulate_bf16_rounding else 0,
+            emulate_bf16_rounding=(1 if emulate_bf16_rounding else 0) | (2 if round_attention_scores else 0) | (4 if fuse_norms else 0),
             cross_attention_mode={"absorbed": 0, "reference": 1}[cross_attention_mode])
+        self.fuse_norms = bool(fuse_norms)
         if cfg.d_kv != 64:
             raise ValueError("the engine's attention kernels are specialised for d_kv == 64")
         self._h = C.c_void_p()
@@ -135,6 +147,12 @@ class ClipT5Engine:
 
     # ---- weights
     def bind_engine_tensors(self, tensors: Dict[str, torch.Tensor]):
+        if getattr(self, "fuse_norms", False) and "t5.enc.0.qkv" in tensors and "t5.enc.0.qkv_g" not in tensors:
+            tensors = dict(tensors)       # engine-layout weights without the folded copies (synthetic / shared dicts): derive them
+            for l in range(self.cfg.enc_layers):
+                q = f"t5.enc.{l}."
+                tensors[q + "qkv_g"] = fold_norm_gain(tensors[q + "qkv"], tensors[q + "ln0"])
+                tensors[q + "wi_g"] = fold_norm_gain(tensors[q + "wi"], tensors[q + "ln1"])
         arr = (_lib.VqaTensor * len(tensors))()
         keep = []
         for i, (name, t) in enumerate(tensors.items()):
@@ -152,7 +170,7 @@ class ClipT5Engine:
         _check(self.lib.vqa_finalize_weights(self._h), self._h, "vqa_finalize_weights")
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
-        self.bind_engine_tensors(convert_state_dict(sd, self.cfg, self.device))
+        self.bind_engine_tensors(convert_state_dict(sd, self.cfg, self.device, fuse_norms=self.fuse_norms))
 
     # ---- forward
     def workspace_bytes(self, batch: int, n_images: int, text_len: int, label_len: int) -> int:
@@ -263,6 +281,27 @@ class ops:
                                   gate_up_offset if epi == 3 else 0, variant, _stream_ptr(a.device))
         _check(rc, None, "vqa_op_gemm_bf16")
         return out
+
+    @staticmethod
+    def gemm_normfuse(a: torch.Tensor, w: torch.Tensor, residual=None, epilogue="store", gate_up_offset=0, ssq_in=None, ssq_out=None,
+                      norm_dim: int = 0, eps: float = 1e-6, out=None):
+        """GEMM with the fused-RMSNorm hooks (see include/vqa_b200.h). ssq_in / ssq_out: fp32 [M, stride] cuda, stride % 4 == 0.
+        Returns (C, number of ssq_out slots written)."""
+        lib = _lib.load()
+        M, K = a.shape
+        n_rows = w.shape[0]
+        epi = ops.EPI[epilogue]
+        n_out = n_rows // 2 if epi == 3 else n_rows
+        if out is None:
+            out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
+        buf = ssq_in if ssq_in is not None else ssq_out
+        parts = C.c_int32(0)
+        rc = lib.vqa_op_gemm_bf16_normfuse(_ptr(a), a.stride(0), _ptr(w), w.stride(0), n_rows, _ptr(out), out.stride(0), M, n_rows, K,
+                                           _ptr(residual), residual.stride(0) if residual is not None else 0, epi,
+                                           gate_up_offset if epi == 3 else 0, _ptr(ssq_in), _ptr(ssq_out), buf.shape[1], norm_dim or K, float(eps),
+                                           C.byref(parts), _stream_ptr(a.device))
+        _check(rc, None, "vqa_op_gemm_bf16_normfuse")
+        return out, int(parts.value)
 
     @staticmethod
     def lmhead_logprob(h: torch.Tensor, w: torch.Tensor, labels: torch.Tensor):

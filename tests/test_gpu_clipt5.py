@@ -117,6 +117,24 @@ def test_engine_vs_transformers_on_the_same_gpu(golden_dir, dev):
     assert float((s - ref).abs().max()) <= 2.0 * gap + 1e-3
 
 
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_fused_norms_and_score_rounding_modes(name, golden_dir, dev):
+    """Engine modes: (a) fuse_norms -- the encoder's T5LayerNorms folded into the GEMMs around them (no normalised copy of the residual
+    stream); (b) round_attention_scores -- the reference's bf16 score tensors before the softmax. Both are different-but-valid rounding
+    points: each must stay as close to the goldens as the default mode (within the same tolerance) and close to the default mode."""
+    blob, cfg, sd = load_case(name, golden_dir)
+    inp = blob["inputs"]
+    g32, g16 = blob["hf_fp32"], blob["hf_bf16"]
+    ref_gap = float((g16["scores"] - g32["scores"]).abs().max())
+    base, _ = run_engine(make_engine(cfg, sd, dev), inp, dev)
+    for kw in (dict(fuse_norms=True), dict(round_attention_scores=True), dict(fuse_norms=True, round_attention_scores=True)):
+        s, lp = run_engine(make_engine(cfg, sd, dev, **kw), inp, dev)
+        e32, e16, eb = (float((s - g32["scores"]).abs().max()), float((s - g16["scores"]).abs().max()), float((s - base).abs().max()))
+        print(f"\n[{name} {kw}] vs HF fp32 golden {e32:.2e} | vs HF bf16 golden {e16:.2e} | vs default mode {eb:.2e}")
+        assert e32 <= 1e-3 + 2.0 * ref_gap and e16 <= 1e-3 + 2.0 * ref_gap and eb <= 1e-3 + 2.0 * ref_gap
+        assert bool(torch.isfinite(lp).all())
+
+
 def test_batch_padding_and_dedupe_invariance(golden_dir, dev):
     """Properties the domain offers: a pair's score does not depend on (a) what else is in the batch, (b) how much right
     padding its row carries, (c) whether its image is shared through image_index."""

@@ -173,6 +173,40 @@ def test_attention_reference_rounding_points(ops, S, use_bias, scale):
     assert float((got - ref_rounded).abs().max()) < 0.05 and float((plain - ref_exact).abs().max()) < 0.05
 
 
+@pytest.mark.parametrize("M,D,N", [(700, 4096, 4096), (300, 256, 256), (130, 2048, 512)])
+def test_gemm_fused_rmsnorm_hooks(ops, M, D, N):
+    """north_star: 'RMSNorm ... fused into the adjacent matmul epilogue'. Producer: a residual GEMM leaves per-row partial sums of squares of
+    the bf16 rows it stores. Consumer: GEMM on the UN-normalised rows with gamma folded into W, accumulator rows scaled by rsqrt(mean(x^2)+eps)
+    == the Linear applied to T5LayerNorm(x) (modeling_t5.py:55-68) up to where the bf16 roundings sit."""
+    from t2v_metrics_b200.engine import fold_norm_gain
+    torch.manual_seed(8)
+    a = (torch.randn(M, 512, device="cuda") * 0.5).bfloat16()
+    wo = (torch.randn(D, 512, device="cuda") * 512 ** -0.5).bfloat16()
+    res = (torch.randn(M, D, device="cuda") * 3.0).bfloat16()
+    stride = (D // 32 + 3) // 4 * 4
+    ssq = torch.zeros(M, stride, dtype=torch.float32, device="cuda")
+    x, parts = ops.gemm_normfuse(a, wo, residual=res, ssq_out=ssq, norm_dim=D)
+    ref_x = ((a.float() @ wo.float().t()).bfloat16().float() + res.float()).bfloat16()
+    assert float((x.float() - ref_x.float()).abs().max()) <= 0.07
+    assert 1 <= parts <= stride and bool((ssq[:, parts:] == 0).all())
+    tot = ssq.sum(-1)
+    assert float(((tot - x.float().pow(2).sum(-1)).abs() / tot).max()) < 1e-5          # exactly the rows that were stored
+    # consumer: plain and gated
+    gamma = (1 + 0.1 * torch.randn(D, device="cuda")).bfloat16()
+    w = (torch.randn(N, D, device="cuda") * D ** -0.5).bfloat16()
+    y, _ = ops.gemm_normfuse(x, fold_norm_gain(w, gamma), ssq_in=ssq, norm_dim=D, eps=1e-6)
+    var = x.float().pow(2).mean(-1, keepdim=True)
+    xn = (gamma.float() * (x.float() * torch.rsqrt(var + 1e-6)).bfloat16().float()).bfloat16()
+    ref_y = (xn.float() @ w.float().t())
+    err = (y.float() - ref_y).abs()
+    assert float(err.max()) <= 0.05 * float(ref_y.abs().max()) and float(err.mean()) <= 6e-3 * float(ref_y.abs().mean()) + 2e-3
+    wg = (torch.randn(2 * N, D, device="cuda") * D ** -0.5).bfloat16()
+    h, _ = ops.gemm_normfuse(x, fold_norm_gain(wg, gamma), epilogue="gated_gelu", gate_up_offset=N, ssq_in=ssq, norm_dim=D, eps=1e-6)
+    g_, u_ = (xn.float() @ wg[:N].float().t()).bfloat16().float(), (xn.float() @ wg[N:].float().t()).bfloat16().float()
+    ref_h = torch.nn.functional.gelu(g_, approximate="tanh") * u_
+    assert float((h.float() - ref_h).abs().mean()) <= 1e-2 * float(ref_h.abs().mean()) + 2e-3
+
+
 def test_norms(ops):
     torch.manual_seed(6)
     for D in (4096, 3584, 2048, 1280, 256, 128, 5120):   # warp-per-row (D % 256 == 0, <= 4096) and the generic block-per-row path
