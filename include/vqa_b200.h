@@ -177,14 +177,32 @@ int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int32_t pixel_d
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Trace output (reference forward_with_trace, qwen2vl_model.py:303-493, top-5 at :439-447): the k <= 8 most probable next tokens of every
- * prompt of the LAST vqa_qwen25vl_score call on this handle with the same (batch, seq_len, n_patches) and the same workspace (its final
- * hidden states are still there), under the same processing as the score: bf16 logits -> fp32 -> repetition penalty -> 1/T -> softmax over
- * the whole vocabulary. out_ids / out_probs: DEVICE [batch, k], most probable first; out_ids[b][0] is the token generate(max_new_tokens=1,
- * do_sample=False) would emit. This call materialises [batch, vocab] bf16 logits of that one position in the workspace -- a debugging aid;
- * the scoring path never stores logits. input_ids / seq_lens (as given to the score call) are only read when repetition_penalty != 1. */
-int vqa_qwen25vl_topk(vqa_handle* h, const int32_t* input_ids, const int32_t* seq_lens, int32_t batch, int32_t seq_len, int32_t n_patches,
-                      int32_t k, float temperature, float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace,
-                      size_t workspace_bytes, void* stream);
+ * prompt of the LAST scoring call on this handle (vqa_qwen25vl_score: total_rows = batch * seq_len; vqa_qwen25vl_score_packed: its
+ * total_rows) with the same n_patches and the same workspace -- its final hidden states and, when repetition_penalty != 1, its prompt-token
+ * bitmap are still there -- under the same processing as the score: bf16 logits -> fp32 -> repetition penalty -> 1/T -> softmax over the
+ * whole vocabulary. out_ids / out_probs: DEVICE [batch, k], most probable first; out_ids[b][0] is the token generate(max_new_tokens=1,
+ * do_sample=False) would emit. This call materialises [batch, vocab] bf16 logits of that one position in the workspace -- a debugging
+ * aid; the scoring path never stores logits. */
+int vqa_qwen25vl_topk(vqa_handle* h, int32_t batch, int64_t total_rows, int32_t n_patches, int32_t k, float temperature,
+                      float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace, size_t workspace_bytes, void* stream);
+
+/* KV-prefix sharing (reference score.py:104-106 repeats one image across N texts and qwen2vl_model.py:190 re-runs the whole
+ * prompt per text). The language-model tokens are given as PACKED rows: sequences stored back to back (cu_seqlens [n_seq + 1]); the
+ * [chat prefix + vision tokens] of an image is ONE sequence (kv_prefix = -1), each prompt's remaining tokens are a sequence of their own whose
+ * kv_prefix names the shared one: its rows attend to all prefix rows, then causally to themselves. Causality makes this exact (a prefix
+ * row never sees a suffix), and the prefix rows go through every layer once per image instead of once per prompt.
+ *   input_ids / feat_index [total_rows], position_ids [3, total_rows]: as in vqa_qwen25vl_score, in packed row order
+ *   pair_row [n_prompts]: packed row of each prompt's last token; pair_seq [n_prompts]: the sequence holding it
+ *   max_seq_len: longest sequence; max_prompt_len: longest prefix + suffix (repetition-penalty bitmap) */
+size_t vqa_qwen25vl_packed_workspace_bytes(vqa_handle* h, int32_t n_prompts, int64_t total_rows, int32_t n_patches);
+int vqa_qwen25vl_score_packed(vqa_handle* h, const void* pixel_patches, int32_t pixel_dtype, int32_t n_patches, const int32_t* vis_pos_hw,
+                              const int32_t* window_index, const int32_t* reverse_index, const int32_t* cu_window, int32_t n_windows,
+                              int32_t max_window_len, const int32_t* cu_frames, int32_t n_frames, int32_t max_frame_len,
+                              const int32_t* input_ids, const int32_t* feat_index, const int32_t* position_ids, int32_t total_rows,
+                              const int32_t* cu_seqlens, const int32_t* kv_prefix, int32_t n_seq, int32_t max_seq_len, const int32_t* pair_row,
+                              const int32_t* pair_seq, const int32_t* answer_ids, int32_t n_prompts, int32_t max_prompt_len, float temperature,
+                              float repetition_penalty, float* out_probs, float* out_logprobs, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* Number of kernels the last vqa_clipt5_score call launched (for bench.py's gpu_launches). */
 int64_t vqa_last_launch_count(vqa_handle* h);

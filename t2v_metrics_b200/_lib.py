@@ -20,6 +20,7 @@ ABI_SYMBOLS = [
     "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess", "vqa_resample_table", "vqa_qwen_preprocess_plan",
     "vqa_qwen_preprocess", "vqa_clipt5_debug_layout", "vqa_qwen25vl_debug_layout", "vqa_set_gemm_schedule",
     "vqa_debug_attention_d64_phases", "vqa_qwen25vl_topk", "vqa_op_gemm_bf16_normfuse",
+    "vqa_qwen25vl_packed_workspace_bytes", "vqa_qwen25vl_score_packed",
 ]
 
 VQA_DTYPE_BF16, VQA_DTYPE_F32, VQA_DTYPE_I32 = 0, 1, 2
@@ -114,7 +115,12 @@ def load() -> C.CDLL:
     lib.vqa_qwen25vl_score.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
                                        f32, vp, vp, vp, C.c_size_t, vp]
     lib.vqa_qwen25vl_score.restype = C.c_int
-    lib.vqa_qwen25vl_topk.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, C.c_size_t, vp]
+    lib.vqa_qwen25vl_topk.argtypes = [vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, C.c_size_t, vp]
+    lib.vqa_qwen25vl_packed_workspace_bytes.argtypes = [vp, i32, i64, i32]
+    lib.vqa_qwen25vl_packed_workspace_bytes.restype = C.c_size_t
+    lib.vqa_qwen25vl_score_packed.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp,
+                                              vp, i32, i32, f32, f32, vp, vp, vp, C.c_size_t, vp]
+    lib.vqa_qwen25vl_score_packed.restype = C.c_int
     lib.vqa_qwen25vl_topk.restype = C.c_int
     lib.vqa_clip_preprocess_workspace_bytes.argtypes = [C.POINTER(i32), C.POINTER(i32), i32, i32, i32]
     lib.vqa_clip_preprocess_workspace_bytes.restype = C.c_size_t

@@ -23,7 +23,8 @@ constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
 constexpr bool ATTN_STREAM_DEFAULT = false;   // true: attn_tc_d64_stream_kernel is the production softmax stage
-constexpr int ATTN_POLY_DEFAULT = 0;   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
+constexpr int ATTN_POLY_DEFAULT = 0;
+constexpr int ATTN128_POLY_DEFAULT = 2;   // d128 (1 CTA / SM): 2 of 8 pairs on the FMA pipe measured 1-3 % faster (profiles/r02_attention.md)   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
 
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -1013,6 +1014,9 @@ struct AttnTc128Params {
     int q_col0, k_col0, v_col0;
     int kv_group;              // query heads per key/value head (GQA); 1 for MHA
     float scale_log2e;
+    const int* kv_prefix;      // varlen mode, [n_seq] or nullptr: sequence b additionally attends to ALL rows of sequence kv_prefix[b] (>= 0),
+                               // placed in front of its own keys -- the shared [system + vision] prefix of several prompts over one image
+                               // (SURVEY 8(f)1): its K/V rows are computed once and read by every prompt's suffix
 };
 
 constexpr int A8_TILE = 128 * 128 * 2;       // 32 KB: 128 rows x 128 bf16 as two 64-column swizzle blocks
@@ -1020,8 +1024,8 @@ constexpr int A8_BLOCK = 128 * 64 * 2;       // 16 KB
 constexpr int A8_TMEM_COLS = 512;            // S [0,128)  O [128,256)  P [256,320)
 inline size_t attn_tc128_smem_bytes() { return 1024 + 5 * A8_TILE + 128; }
 
-// POLY >= 0: the v2 softmax stage of the d64 kernel above (raw-score FMNMX3 maximum, packed FFMA2 scale/reference, POLY of every 8 score
-// pairs exponentiated on the FMA pipe, one TMEM wait per tile); POLY = -1: the round-1 stage (A/B reference).
+// Softmax stage as in the d64 kernel above (raw-score FMNMX3 maximum, packed FFMA2 scale/reference, one TMEM wait per tile; POLY of every
+// 8 score pairs exponentiated on the FMA pipe).
 template <bool CAUSAL, int POLY>
 __global__ void __launch_bounds__(192, 1)
 attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc128Params p) {
@@ -1063,8 +1067,16 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
     uint64_t* o_done = bars + 8;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
 
-    int nkt = (len + 127) / 128;
-    if (CAUSAL) nkt = min(nkt, qt + 1);
+    // key tiles: first the nA tiles of the shared prefix sequence (all of it visible), then this sequence's own tiles (causal)
+    int pre_base = 0, pre_len = 0;
+    if (p.kv_prefix && p.cu_seqlens) {
+        const int ps = p.kv_prefix[b];
+        if (ps >= 0) { pre_base = p.cu_seqlens[ps]; pre_len = p.cu_seqlens[ps + 1] - pre_base; }
+    }
+    const int nA = (pre_len + 127) / 128;
+    int nkt_own = (len + 127) / 128;
+    if (CAUSAL) nkt_own = min(nkt_own, qt + 1);
+    const int nkt = nA + nkt_own;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -1096,7 +1108,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                 const int st = j & 1;
                 mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * A8_TILE);
-                const int r = row_base + j * 128;
+                const int r = j < nA ? pre_base + j * 128 : row_base + (j - nA) * 128;
                 tma_load_2d(sK + st * A8_TILE, &tmap_qkv, &kv_full[st], p.k_col0 + kvh * 128, r);
                 tma_load_2d(sK + st * A8_TILE + A8_BLOCK, &tmap_qkv, &kv_full[st], p.k_col0 + kvh * 128 + 64, r);
                 tma_load_2d(sV + st * A8_TILE, &tmap_qkv, &kv_full[st], p.v_col0 + kvh * 128, r);
@@ -1141,10 +1153,12 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
         const int qrow = q0 + row;
         const uint32_t lane_off = (quad * 32u) << 16;
         float m_run = -INFINITY, l_run = 0.f;
-        if constexpr (POLY >= 0) {
+        {
             const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
             for (int j = 0; j < nkt; ++j) {
-                const int k0 = j * 128;
+                const bool in_prefix = j < nA;
+                const int k0 = in_prefix ? j * 128 : (j - nA) * 128;
+                const int klen = in_prefix ? pre_len : len;
                 mbar_wait(s_full, (uint32_t)j & 1u);
                 tcgen05_fence_after();
                 uint32_t sv[4][32];
@@ -1155,7 +1169,8 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);
 
-                const bool edge = (k0 + 128 > len) || (CAUSAL && j == qt);
+                const bool diag = CAUSAL && !in_prefix && (j - nA) == qt;
+                const bool edge = (k0 + 128 > klen) || diag;
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -1163,7 +1178,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int kcol = k0 + c * 32 + i;
-                            if (kcol >= len || (CAUSAL && kcol > qrow)) sv[c][i] = 0xff800000u;
+                            if (kcol >= klen || (diag && kcol > qrow)) sv[c][i] = 0xff800000u;
                         }
                     }
 #pragma unroll
@@ -1223,91 +1238,6 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
-        } else {
-        for (int j = 0; j < nkt; ++j) {
-            const int k0 = j * 128;
-            mbar_wait(s_full, (uint32_t)j & 1u);
-            tcgen05_fence_after();
-            float t[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) t[c][i] = __uint_as_float(v[i]) * p.scale_log2e;
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
-
-            const bool edge = (k0 + 128 > len) || (CAUSAL && j == qt);
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (edge) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int kcol = k0 + c * 32 + i;
-                        if (kcol >= len || (CAUSAL && kcol > qrow)) t[c][i] = -INFINITY;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    mx0 = fmaxf(mx0, t[c][i]);     mx1 = fmaxf(mx1, t[c][i + 1]);
-                    mx2 = fmaxf(mx2, t[c][i + 2]); mx3 = fmaxf(mx3, t[c][i + 3]);
-                }
-            }
-            float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            if (tile_max == -INFINITY) tile_max = -1e30f;   // a padded query row may see no key at all in this tile
-            float corr = 1.f;
-            bool rescale = false;
-            if (j == 0) {
-                m_run = tile_max;
-            } else {
-                const bool need = tile_max > m_run + 8.f;
-                rescale = __any_sync(0xffffffffu, need);
-                if (rescale) {
-                    const float m_new = fmaxf(m_run, tile_max);
-                    corr = fast_exp2(m_run - m_new);
-                    m_run = m_new;
-                }
-            }
-            if (j > 0) {
-                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
-                tcgen05_fence_after();
-                if (rescale) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t ov[16];
-                        tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                        tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                    }
-                }
-            }
-            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float e0 = fast_exp2(t[c][2 * i] - m_run),     e1 = fast_exp2(t[c][2 * i + 1] - m_run);
-                    const float e2 = fast_exp2(t[c][2 * i + 2] - m_run), e3 = fast_exp2(t[c][2 * i + 3] - m_run);
-                    ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-                    pk[i] = pack_bf16x2(e0, e1);
-                    pk[i + 1] = pack_bf16x2(e2, e3);
-                }
-                tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-            }
-            l_run = l_run * corr + ((ps0 + ps1) + (ps2 + ps3));
-            tmem_st_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
         }
         mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
         tcgen05_fence_after();
@@ -1336,19 +1266,22 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
     if (warp == 1) tmem_dealloc<1>(tmem_base, A8_TMEM_COLS);
 }
 
-// rows: total rows of the packed buffer; max_len: longest sequence (grid sizing)
+// rows: total rows of the packed buffer; max_len: longest sequence (grid sizing); kv_prefix: see AttnTc128Params (varlen mode only)
 inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long rows, int q_col0, int k_col0, int v_col0,
                                      __nv_bfloat16* o, int ldo, int n_seq, int max_len, int S, int Hq, int kv_group,
-                                     const int* cu_seqlens, const int* seq_lens, float scale, bool causal, cudaStream_t stream) {
+                                     const int* cu_seqlens, const int* seq_lens, float scale, bool causal, cudaStream_t stream,
+                                     const int* kv_prefix = nullptr) {
     CUtensorMap tm;
     if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    if (kv_prefix && !cu_seqlens) return cudaErrorInvalidValue;
     AttnTc128Params p;
     p.o = o; p.ldo = ldo; p.cu_seqlens = cu_seqlens; p.seq_lens = seq_lens; p.S = S;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.kv_group = kv_group;
     p.scale_log2e = scale * 1.4426950408889634f;
+    p.kv_prefix = kv_prefix;
     const size_t smem = attn_tc128_smem_bytes();
-    static const int variant = [] { const char* v = getenv("VQA_ATTN128_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();   // 1: round-1 stage; 10/12/13: POLY 0/2/3
-    const int poly = variant == 1 ? -1 : (variant >= 10 ? variant - 10 : ATTN_POLY_DEFAULT);
+    static const int variant = [] { const char* v = getenv("VQA_ATTN128_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();   // 10 / 12: POLY 0 / 2
+    const int poly = variant >= 10 ? variant - 10 : ATTN128_POLY_DEFAULT;
     dim3 grid((max_len + 127) / 128, Hq, n_seq);
     auto go = [&](auto kernel, PerDeviceOnce& once) -> cudaError_t {
         cudaError_t e = once.ensure([&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
@@ -1356,17 +1289,9 @@ inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long
         kernel<<<grid, 192, smem, stream>>>(tm, p);
         return cudaGetLastError();
     };
-    static PerDeviceOnce once[8];
-    if (causal) {
-        if (poly < 0) return go(attn_tc_d128_kernel<true, -1>, once[0]);
-        if (poly == 0) return go(attn_tc_d128_kernel<true, 0>, once[1]);
-        if (poly == 2) return go(attn_tc_d128_kernel<true, 2>, once[2]);
-        return go(attn_tc_d128_kernel<true, 3>, once[3]);
-    }
-    if (poly < 0) return go(attn_tc_d128_kernel<false, -1>, once[4]);
-    if (poly == 0) return go(attn_tc_d128_kernel<false, 0>, once[5]);
-    if (poly == 2) return go(attn_tc_d128_kernel<false, 2>, once[6]);
-    return go(attn_tc_d128_kernel<false, 3>, once[7]);
+    static PerDeviceOnce once[4];
+    if (causal) return poly == 0 ? go(attn_tc_d128_kernel<true, 0>, once[0]) : go(attn_tc_d128_kernel<true, 2>, once[1]);
+    return poly == 0 ? go(attn_tc_d128_kernel<false, 0>, once[2]) : go(attn_tc_d128_kernel<false, 2>, once[3]);
 }
 
 }  // namespace vqa

@@ -28,10 +28,11 @@ struct QwenWorkspace {
     size_t x, xn, qkv, attn, ff, cos, sin, last, lastn, lse_max, lse_sum, label_logit, logprob, pen_bitmap, trace_logits;
     size_t total;
 };
-static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n_patches) {
+// B = prompts scored, M = token rows of the language model (B * S in the padded layout; fewer when prompts share a vision prefix)
+static QwenWorkspace qwen_plan_rows(const vqa_qwen25vl_config& c, int B, size_t M, int n_patches) {
     Plan pl;
     QwenWorkspace w;
-    const size_t L = n_patches, M = (size_t)B * S;
+    const size_t L = n_patches;
     const size_t unit = (size_t)c.spatial_merge * c.spatial_merge;
     const size_t Dv = c.vit_hidden, Hv = c.vit_heads;
     const size_t mlp_pad = qwen_mlp_pad(c.vit_mlp);
@@ -67,6 +68,19 @@ static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n
     w.total = pl.off;
     return w;
 }
+
+static QwenWorkspace qwen_plan(const vqa_qwen25vl_config& c, int B, int S, int n_patches) { return qwen_plan_rows(c, B, (size_t)B * S, n_patches); }
+
+// Packed-rows layout of the language-model tokens (KV-prefix sharing): sequences are stored back to back (cu_seqlens);
+// a prompt's [system + vision] prefix is ONE sequence shared by every prompt over that image, each prompt's remaining tokens are their own
+// sequence whose kv_prefix points at it. Causal attention makes this exact: a prefix row never sees a suffix.
+struct QwenPacked {
+    int total_rows, n_seq, max_seq_len, max_prompt_len;
+    const int* cu_seqlens;   // [n_seq + 1]
+    const int* kv_prefix;    // [n_seq], -1 = none
+    const int* pair_row;     // [B] packed row of each prompt's last token
+    const int* pair_seq;     // [B] sequence holding that row
+};
 
 static int qwen_finalize(vqa_handle* h, QwenState& q) {
     const vqa_qwen25vl_config& c = q.cfg;
@@ -111,9 +125,9 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
                       const int* input_ids, const int* seq_lens, const int* feat_index, const int* position_ids,
                       const int* answer_ids, int B, int S, float temperature, float repetition_penalty, float* out_probs,
                       float* out_logprobs,
-                      void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                      void* workspace, size_t workspace_bytes, cudaStream_t st, const QwenPacked* pk = nullptr) {
     const vqa_qwen25vl_config& c = q.cfg;
-    const QwenWorkspace w = qwen_plan(c, B, S, n_patches);
+    const QwenWorkspace w = pk ? qwen_plan_rows(c, B, (size_t)pk->total_rows, n_patches) : qwen_plan(c, B, S, n_patches);
     if (workspace_bytes < w.total) return fail(h, VQA_ERR_WORKSPACE, "workspace too small");
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     auto P_ = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
@@ -143,7 +157,7 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     };
     const int L = n_patches, Dv = c.vit_hidden, Hv = c.vit_heads, hdv = c.vit_head_dim;
     const int unit = c.spatial_merge * c.spatial_merge, mlp_pad = qwen_mlp_pad(c.vit_mlp);
-    const int D = c.hidden, M = B * S;
+    const int D = c.hidden, M = pk ? pk->total_rows : B * S;
 
     // ---------------- vision tower ----------------
     {
@@ -204,7 +218,9 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         *lc += 3;
         gather_rows_kernel<<<L / unit, 128, 0, st>>>(P_(w.vfeat), P_(w.vfeat_orig), reverse_index, 1, c.out_hidden);
         // ---------------- language model input ----------------
-        qwen_embed_kernel<<<M, 128, 0, st>>>(input_ids, feat_index, seq_lens, q.embed, P_(w.vfeat_orig), P_(w.x), S, D);
+        // packed rows: one "sample" of M rows, all valid (its length is the last entry of cu_seqlens)
+        qwen_embed_kernel<<<M, 128, 0, st>>>(input_ids, feat_index, pk ? pk->cu_seqlens + pk->n_seq : seq_lens, q.embed, P_(w.vfeat_orig), P_(w.x),
+                                             pk ? M : S, D);
         rope_table_kernel<<<(M * 64 + 255) / 256, 256, 0, st>>>(position_ids, M, q.text_axis, q.text_inv_freq, 64, F_(w.cos), F_(w.sin), 1);
         TRY(cuda_ok(cudaSuccess, "llm prologue"));
     }
@@ -226,8 +242,12 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         {
             ProfScope ps(h, CAT_ATTENTION, 2.0 * B * (double)Hq * S * S * 128, st);
             ++*lc;
-            TRY(cuda_ok(launch_attn_tc128(P_(w.qkv), qkv_cols, M, 0, Hq * 128, (Hq + Hkv) * 128, P_(w.attn), Hq * 128, B, S, S, Hq, Hq / Hkv, nullptr,
-                                          seq_lens, tscale, true, st), "llm attention"));
+            if (pk)
+                TRY(cuda_ok(launch_attn_tc128(P_(w.qkv), qkv_cols, M, 0, Hq * 128, (Hq + Hkv) * 128, P_(w.attn), Hq * 128, pk->n_seq, pk->max_seq_len, 0,
+                                              Hq, Hq / Hkv, pk->cu_seqlens, nullptr, tscale, true, st, pk->kv_prefix), "llm attention (packed)"));
+            else
+                TRY(cuda_ok(launch_attn_tc128(P_(w.qkv), qkv_cols, M, 0, Hq * 128, (Hq + Hkv) * 128, P_(w.attn), Hq * 128, B, S, S, Hq, Hq / Hkv, nullptr,
+                                              seq_lens, tscale, true, st), "llm attention"));
         }
         TRY(gemm(P_(w.attn), Hq * 128, Lw.o_w, Hq * 128, D, P_(w.x), D, M, D, Hq * 128, nullptr, P_(w.x), D, EPI_STORE, 0));
         TRY(rms(P_(w.x), Lw.ln2, P_(w.xn), M, D));
@@ -238,7 +258,8 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     {
         ProfScope ps(h, CAT_OTHER, 0, st);
         ++*lc;
-        gather_last_rows_kernel<<<B, 128, 0, st>>>(P_(w.x), seq_lens, P_(w.last), S, D);
+        if (pk) gather_rows_by_index_kernel<<<B, 128, 0, st>>>(P_(w.x), pk->pair_row, P_(w.last), D);
+        else    gather_last_rows_kernel<<<B, 128, 0, st>>>(P_(w.x), seq_lens, P_(w.last), S, D);
         TRY(cuda_ok(cudaSuccess, "last-row gather"));
     }
     TRY(rms(P_(w.last), q.final_norm, P_(w.lastn), B, D));
@@ -251,8 +272,12 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         ProfScope ps(h, CAT_OTHER, 0, st);
         *lc += 2;
         TRY(cuda_ok(cudaMemsetAsync(P8_(w.pen_bitmap), 0, (size_t)B * pen_words * 4, st), "penalty bitmap clear"));
-        token_bitmap_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(input_ids, seq_lens, B, S, c.vocab,
-                                                                 reinterpret_cast<uint32_t*>(P8_(w.pen_bitmap)), pen_words);
+        if (pk)
+            token_bitmap_packed_kernel<<<dim3((pk->max_prompt_len + 255) / 256, B), 256, 0, st>>>(input_ids, pk->cu_seqlens, pk->kv_prefix, pk->pair_seq,
+                                                                                                   c.vocab, reinterpret_cast<uint32_t*>(P8_(w.pen_bitmap)), pen_words);
+        else
+            token_bitmap_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(input_ids, seq_lens, B, S, c.vocab,
+                                                                     reinterpret_cast<uint32_t*>(P8_(w.pen_bitmap)), pen_words);
         TRY(cuda_ok(cudaSuccess, "penalty bitmap"));
     }
     {
@@ -273,24 +298,20 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
     return VQA_OK;
 }
 
-// forward_with_trace support: top-k of the last-position distribution of the LAST scoring call (its final hidden states are still in the
-// workspace). Materialises the [B, vocab] bf16 logits of that one position -- trace mode only.
-static int qwen_topk(vqa_handle* h, QwenState& q, const int* input_ids, const int* seq_lens, int B, int S, int n_patches, int K, float temperature,
-                     float repetition_penalty, int* out_ids, float* out_probs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// forward_with_trace support: top-k of the last-position distribution of the LAST scoring call (its final hidden states -- and, when a
+// repetition penalty is in use, its prompt-token bitmap -- are still in the workspace). Materialises the [B, vocab] bf16 logits of that
+// one position -- trace mode only.
+static int qwen_topk(vqa_handle* h, QwenState& q, int B, size_t rows, int n_patches, int K, float temperature, float repetition_penalty, int* out_ids,
+                     float* out_probs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const vqa_qwen25vl_config& c = q.cfg;
-    const QwenWorkspace w = qwen_plan(c, B, S, n_patches);
+    const QwenWorkspace w = qwen_plan_rows(c, B, rows, n_patches);
     if (workspace_bytes < w.total) return fail(h, VQA_ERR_WORKSPACE, "workspace too small");
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     bf16* lastn = reinterpret_cast<bf16*>(ws + w.lastn);
     bf16* logits = reinterpret_cast<bf16*>(ws + w.trace_logits);
     const int pen_words = (c.vocab + 31) / 32;
     const bool penalise = repetition_penalty != 1.0f;
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + w.pen_bitmap);
-    if (penalise) {
-        CUDA_TRY(h, cudaMemsetAsync(bitmap, 0, (size_t)B * pen_words * 4, st));
-        token_bitmap_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(input_ids, seq_lens, B, S, c.vocab, bitmap, pen_words);
-        CUDA_TRY(h, cudaGetLastError());
-    }
+    const uint32_t* bitmap = reinterpret_cast<const uint32_t*>(ws + w.pen_bitmap);      // built by the scoring call with the same penalty
     CUDA_TRY(h, run_gemm(lastn, c.hidden, q.lm_head, c.hidden, c.vocab, logits, c.vocab, B, c.vocab, c.hidden, nullptr, nullptr, 0, EPI_STORE, 0, 0,
                          h->num_sms, st, nullptr));
     topk_softmax_kernel<<<B, 256, 0, st>>>(logits, (long long)c.vocab, c.vocab, 1.0f / temperature, penalise ? bitmap : nullptr, pen_words,

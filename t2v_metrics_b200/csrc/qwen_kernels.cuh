@@ -137,6 +137,27 @@ __global__ void token_bitmap_kernel(const int* __restrict__ ids, const int* __re
     atomicOr(&bitmap[(size_t)b * words + (id >> 5)], 1u << (id & 31));
 }
 
+// Packed-rows mode (shared vision prefixes): out[b] = x[row[b]], the last prompt position of pair b.
+__global__ void gather_rows_by_index_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ row, __nv_bfloat16* __restrict__ out, int D) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row[blockIdx.x] * D);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * D);
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+// Packed-rows mode: the prompt of pair b = rows of its prefix sequence (kv_prefix[pair_seq[b]], if any) + rows of its own sequence.
+// grid (ceil(max_prompt_len / 256), B).
+__global__ void token_bitmap_packed_kernel(const int* __restrict__ ids, const int* __restrict__ cu, const int* __restrict__ kv_prefix,
+                                           const int* __restrict__ pair_seq, int vocab, uint32_t* __restrict__ bitmap, int words) {
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sq = pair_seq[b], pre = kv_prefix ? kv_prefix[sq] : -1;
+    const int pre_len = pre >= 0 ? cu[pre + 1] - cu[pre] : 0;
+    const int own_len = cu[sq + 1] - cu[sq];
+    if (t >= pre_len + own_len) return;
+    const int id = t < pre_len ? ids[cu[pre] + t] : ids[cu[sq] + (t - pre_len)];
+    if (id < 0 || id >= vocab) return;
+    atomicOr(&bitmap[(size_t)b * words + (id >> 5)], 1u << (id & 31));
+}
+
 // prob[b] = exp(logprob[b])
 __global__ void exp_kernel(const float* __restrict__ lp, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

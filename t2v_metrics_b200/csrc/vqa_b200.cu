@@ -1018,16 +1018,49 @@ extern "C" int vqa_qwen25vl_score(vqa_handle* h, const void* pixel_patches, int3
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vqa_qwen25vl_topk(vqa_handle* h, const int32_t* input_ids, const int32_t* seq_lens, int32_t batch, int32_t seq_len, int32_t n_patches,
-                                 int32_t k, float temperature, float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+extern "C" int vqa_qwen25vl_topk(vqa_handle* h, int32_t batch, int64_t total_rows, int32_t n_patches, int32_t k, float temperature,
+                                 float repetition_penalty, int32_t* out_ids, float* out_probs, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || h->kind != 1) return fail(h, VQA_ERR_INVALID_ARG, "not a Qwen2.5-VL handle");
     if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
-    if (!out_ids || !out_probs || !workspace || batch <= 0 || seq_len <= 0 || n_patches <= 0 || k <= 0 || k > TOPK_MAX || !(temperature > 0.f) ||
-        !(repetition_penalty > 0.f) || (repetition_penalty != 1.0f && (!input_ids || !seq_lens)))
-        return fail(h, VQA_ERR_INVALID_ARG, "bad top-k argument (1 <= k <= 8; the prompt ids are needed when a repetition penalty applies)");
-    return qwen_topk(h, *h->qwen, input_ids, seq_lens, batch, seq_len, n_patches, k, temperature, repetition_penalty, out_ids, out_probs, workspace,
+    if (!out_ids || !out_probs || !workspace || batch <= 0 || total_rows <= 0 || n_patches <= 0 || k <= 0 || k > TOPK_MAX || !(temperature > 0.f) ||
+        !(repetition_penalty > 0.f))
+        return fail(h, VQA_ERR_INVALID_ARG, "bad top-k argument (1 <= k <= 8)");
+    return qwen_topk(h, *h->qwen, batch, (size_t)total_rows, n_patches, k, temperature, repetition_penalty, out_ids, out_probs, workspace,
                      workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t vqa_qwen25vl_packed_workspace_bytes(vqa_handle* h, int32_t n_prompts, int64_t total_rows, int32_t n_patches) {
+    if (!h || h->kind != 1 || n_prompts <= 0 || total_rows <= 0 || n_patches <= 0) return 0;
+    return qwen_plan_rows(h->qwen->cfg, n_prompts, (size_t)total_rows, n_patches).total;
+}
+
+extern "C" int vqa_qwen25vl_score_packed(vqa_handle* h, const void* pixel_patches, int32_t pixel_dtype, int32_t n_patches,
+                                         const int32_t* vis_pos_hw, const int32_t* window_index, const int32_t* reverse_index,
+                                         const int32_t* cu_window, int32_t n_windows, int32_t max_window_len, const int32_t* cu_frames,
+                                         int32_t n_frames, int32_t max_frame_len, const int32_t* input_ids, const int32_t* feat_index,
+                                         const int32_t* position_ids, int32_t total_rows, const int32_t* cu_seqlens, const int32_t* kv_prefix,
+                                         int32_t n_seq, int32_t max_seq_len, const int32_t* pair_row, const int32_t* pair_seq,
+                                         const int32_t* answer_ids, int32_t n_prompts, int32_t max_prompt_len, float temperature,
+                                         float repetition_penalty, float* out_probs, float* out_logprobs, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    if (!h || h->kind != 1) return fail(h, VQA_ERR_INVALID_ARG, "not a Qwen2.5-VL handle");
+    if (!h->finalized) return fail(h, VQA_ERR_MISSING_WEIGHT, "vqa_finalize_weights has not succeeded");
+    if (!pixel_patches || !vis_pos_hw || !window_index || !reverse_index || !cu_window || !cu_frames || !input_ids || !feat_index || !position_ids ||
+        !cu_seqlens || !kv_prefix || !pair_row || !pair_seq || !answer_ids || !out_probs || !workspace)
+        return fail(h, VQA_ERR_INVALID_ARG, "null device pointer");
+    const int unit = h->qwen->cfg.spatial_merge * h->qwen->cfg.spatial_merge;
+    if (n_prompts <= 0 || total_rows <= 0 || n_seq <= 0 || max_seq_len <= 0 || max_prompt_len <= 0 || n_patches <= 0 || n_patches % unit ||
+        n_windows <= 0 || n_frames <= 0 || !(temperature > 0.f) || !(repetition_penalty > 0.f))
+        return fail(h, VQA_ERR_INVALID_ARG, "bad size / temperature / repetition penalty");
+    if (pixel_dtype != VQA_DTYPE_F32 && pixel_dtype != VQA_DTYPE_BF16) return fail(h, VQA_ERR_INVALID_ARG, "pixel_dtype must be F32 or BF16");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(h, VQA_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+    QwenPacked pk;
+    pk.total_rows = total_rows; pk.n_seq = n_seq; pk.max_seq_len = max_seq_len; pk.max_prompt_len = max_prompt_len;
+    pk.cu_seqlens = cu_seqlens; pk.kv_prefix = kv_prefix; pk.pair_row = pair_row; pk.pair_seq = pair_seq;
+    return qwen_score(h, *h->qwen, pixel_patches, pixel_dtype, n_patches, vis_pos_hw, window_index, reverse_index, cu_window, n_windows,
+                      max_window_len, cu_frames, n_frames, max_frame_len, input_ids, nullptr, feat_index, position_ids, answer_ids, n_prompts,
+                      total_rows, temperature, repetition_penalty, out_probs, out_logprobs, workspace, workspace_bytes,
+                      reinterpret_cast<cudaStream_t>(stream), &pk);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI

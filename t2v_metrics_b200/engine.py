@@ -630,7 +630,7 @@ class QwenVLEngine:
                                              float(temperature), float(repetition_penalty), _ptr(out), _ptr(logp), _ptr(self._workspace),
                                              self._workspace.numel(), _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_score")
-        self._last_call = (B, S, vi["n_patches"], input_ids, seq_lens)       # what topk_last() needs to find the final hidden states again
+        self._last_call = (B, B * S, vi["n_patches"])       # what topk_last() needs to find the final hidden states again
         return (out, logp) if return_logprobs else out
 
     def topk_last(self, k: int = 5, temperature: float = 1.0, repetition_penalty: float = 1.0):
@@ -639,14 +639,13 @@ class QwenVLEngine:
         (qwen2vl_model.py:439-447). Trace mode only: materialises the last position's [B, vocab] logits in the workspace."""
         if getattr(self, "_last_call", None) is None:
             raise RuntimeError("topk_last() follows a scoring call")
-        B, S, n_patches, input_ids, seq_lens = self._last_call
+        B, rows, n_patches = self._last_call
         dev = self.device
         ids = torch.empty(B, k, dtype=torch.int32, device=dev)
         probs = torch.empty(B, k, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = self.lib.vqa_qwen25vl_topk(self._h, _ptr(input_ids), _ptr(seq_lens), B, S, n_patches, k, float(temperature),
-                                            float(repetition_penalty), _ptr(ids), _ptr(probs), _ptr(self._workspace), self._workspace.numel(),
-                                            _stream_ptr(dev))
+            rc = self.lib.vqa_qwen25vl_topk(self._h, B, rows, n_patches, k, float(temperature), float(repetition_penalty), _ptr(ids), _ptr(probs),
+                                            _ptr(self._workspace), self._workspace.numel(), _stream_ptr(dev))
         _check(rc, self._h, "vqa_qwen25vl_topk")
         return ids, probs
 
@@ -661,14 +660,52 @@ class QwenVLEngine:
             return ws[o:o + rows * cols * 2].view(torch.bfloat16).view(rows, cols)
         return dict(last_hidden=view(off[0], batch, cfg.hidden), vision_feats=view(off[1], n_patches // unit, cfg.out_hidden))
 
+    def score_packed(self, pixel_patches: torch.Tensor, grid_thw, packed: Dict[str, torch.Tensor], answer_ids: torch.Tensor,
+                     temperature: float = 1.0, repetition_penalty: float = 1.0, out: Optional[torch.Tensor] = None):
+        """One prefill over PACKED rows (qwen_host.build_packed_indices, tensors already on the device): prompts over the same image share
+        the K/V of their [chat prefix + vision tokens]."""
+        dev = self.device
+        vi = self.vision_indices(grid_thw)
+        assert pixel_patches.is_cuda and pixel_patches.is_contiguous() and pixel_patches.shape == (vi["n_patches"], self.cfg.patch_dim)
+        B, R = int(answer_ids.numel()), int(packed["total_rows"])
+        need = int(self.lib.vqa_qwen25vl_packed_workspace_bytes(self._h, B, R, vi["n_patches"]))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32, device=dev)
+        pdt = _lib.VQA_DTYPE_F32 if pixel_patches.dtype == torch.float32 else _lib.VQA_DTYPE_BF16
+        with torch.cuda.device(dev):
+            rc = self.lib.vqa_qwen25vl_score_packed(
+                self._h, _ptr(pixel_patches), pdt, vi["n_patches"], _ptr(vi["vis_pos_hw"]), _ptr(vi["window_index"]), _ptr(vi["reverse_index"]),
+                _ptr(vi["cu_window"]), vi["n_windows"], vi["max_window"], _ptr(vi["cu_frames"]), vi["n_frames"], vi["max_frame"],
+                _ptr(packed["input_ids"]), _ptr(packed["feat_index"]), _ptr(packed["position_ids"]), R, _ptr(packed["cu_seqlens"]),
+                _ptr(packed["kv_prefix"]), int(packed["n_seq"]), int(packed["max_seq_len"]), _ptr(packed["pair_row"]), _ptr(packed["pair_seq"]),
+                _ptr(answer_ids), B, int(packed["max_prompt_len"]), float(temperature), float(repetition_penalty), _ptr(out), None,
+                _ptr(self._workspace), self._workspace.numel(), _stream_ptr(dev))
+        _check(rc, self._h, "vqa_qwen25vl_score_packed")
+        self._last_call = (B, R, vi["n_patches"])
+        return out
+
     def score_prompts(self, pixel_patches, grid_thw, prompts, answer_ids, image_of_sample=None, temperature: float = 1.0,
-                      repetition_penalty: float = 1.0, second_per_grid_ts=None):
+                      repetition_penalty: float = 1.0, second_per_grid_ts=None, share_prefix: Optional[bool] = None):
         """Convenience: prompts = list of 1-D id lists (each with one image- or video-token run). Host index logic + one engine
-        call. Videos are grids with t > 1 whose prompt run uses cfg.video_token_id (second_per_grid_ts = temporal_patch / fps)."""
+        call. Videos are grids with t > 1 whose prompt run uses cfg.video_token_id (second_per_grid_ts = temporal_patch / fps).
+        share_prefix: None = automatically when at least two prompts start with the same [chat prefix + vision run] over the same image
+        (the M x N scoring API repeats every image N times, reference score.py:104-106); their prefix then runs through the language
+        model once (KV-prefix sharing, exact under causal attention)."""
         from . import qwen_host
         cfg, dev = self.cfg, self.device
         B = len(prompts)
         img = list(image_of_sample) if image_of_sample is not None else list(range(B))
+        if share_prefix is None or share_prefix:
+            pk = qwen_host.build_packed_indices([list(map(int, p)) for p in prompts], [tuple(map(int, g)) for g in grid_thw], img,
+                                                cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second,
+                                                video_token_id=cfg.video_token_id, second_per_grid_ts=second_per_grid_ts)
+            if pk["n_shared"] > 0 or share_prefix:
+                d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in pk.items()}
+                ans = torch.as_tensor(list(map(int, answer_ids)), dtype=torch.int32).to(dev)
+                return self.score_packed(pixel_patches.to(dev), grid_thw, d, ans, temperature, repetition_penalty)
         idx = qwen_host.build_batch_indices([list(map(int, p)) for p in prompts], [tuple(map(int, g)) for g in grid_thw], img,
                                             cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second,
                                             video_token_id=cfg.video_token_id, second_per_grid_ts=second_per_grid_ts)

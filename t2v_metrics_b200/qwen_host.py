@@ -129,3 +129,78 @@ def build_batch_indices(input_ids: List[Sequence[int]], grids: Sequence[Sequence
         pos[:, b, :n] = mrope_position_ids(seq_t.tolist(), [grids[img]], image_token_id, merge, tokens_per_second, video_token_id,
                                            spg).to(torch.int32)
     return dict(input_ids=ids, seq_lens=lens, feat_index=feat, position_ids=pos.reshape(3, B * S).contiguous())
+
+
+def build_packed_indices(input_ids: List[Sequence[int]], grids: Sequence[Sequence[int]], image_of_sample: Sequence[int],
+                         image_token_id: int, merge: int, tokens_per_second: int, video_token_id: Optional[int] = None,
+                         second_per_grid_ts: Optional[Sequence[float]] = None):
+    """KV-prefix sharing: prompts that start with the same tokens up to the end of their vision run -- the chat prefix and
+    the image's pad tokens, i.e. every text scored against one image (reference score.py:104-106) -- share that prefix as ONE packed
+    sequence; each prompt keeps only its remaining tokens as its own sequence. Returns the int32 CPU arrays vqa_qwen25vl_score_packed takes
+    plus sizes: dict(input_ids [R], feat_index [R], position_ids [3, R], cu_seqlens [n_seq + 1], kv_prefix [n_seq], pair_row [B],
+    pair_seq [B], total_rows, n_seq, max_seq_len, max_prompt_len, n_shared). A prompt whose prefix nobody else uses is stored whole
+    (kv_prefix -1), so the packed form never has more rows than sum(len(prompt))."""
+    unit = merge * merge
+    feat_off = [0]
+    for t, h, w in grids:
+        feat_off.append(feat_off[-1] + t * h * w // unit)
+    vis = {image_token_id} | ({video_token_id} if video_token_id is not None else set())
+    prompts = [list(map(int, p)) for p in input_ids]
+    cut = []                                    # prefix length of each prompt = index after its last vision token
+    for p in prompts:
+        last = max((i for i, t in enumerate(p) if t in vis), default=-1)
+        cut.append(last + 1)
+    groups = {}
+    for b, p in enumerate(prompts):
+        if cut[b] > 0 and cut[b] < len(p):
+            groups.setdefault((image_of_sample[b], tuple(p[:cut[b]])), []).append(b)
+    shared = {k: v for k, v in groups.items() if len(v) > 1}
+    seqs, kvp, pos_rows, feat_rows = [], [], [], []       # packed sequences in order: shared prefixes first, then one per prompt
+    prefix_seq = {}
+
+    def positions(b):
+        img = image_of_sample[b]
+        spg = None if second_per_grid_ts is None else [second_per_grid_ts[img]]
+        return mrope_position_ids(prompts[b], [grids[img]], image_token_id, merge, tokens_per_second, video_token_id, spg).to(torch.int32)
+
+    def feats(ids, img):
+        t = torch.as_tensor(ids, dtype=torch.int32)
+        f = torch.full((len(ids),), -1, dtype=torch.int32)
+        m = torch.zeros(len(ids), dtype=torch.bool)
+        for v in vis:
+            m |= t == v
+        if bool(m.any()):
+            f[m] = torch.arange(feat_off[img], feat_off[img + 1], dtype=torch.int32)
+        return f
+
+    pos_cache = {}
+    for key, members in shared.items():
+        img, pre = key
+        b0 = members[0]
+        pos_cache[b0] = positions(b0)
+        prefix_seq[key] = len(seqs)
+        seqs.append(list(pre)); kvp.append(-1)
+        pos_rows.append(pos_cache[b0][:, :len(pre)]); feat_rows.append(feats(pre, img))
+    pair_seq, pair_last = [], []
+    for b, p in enumerate(prompts):
+        key = (image_of_sample[b], tuple(p[:cut[b]]))
+        pos = pos_cache.get(b)
+        if pos is None:
+            pos = positions(b)
+        if key in shared:
+            own, start, pre = p[cut[b]:], cut[b], prefix_seq[key]
+        else:
+            own, start, pre = p, 0, -1
+        pair_seq.append(len(seqs))
+        seqs.append(own); kvp.append(pre)
+        pos_rows.append(pos[:, start:])
+        feat_rows.append(feats(own, image_of_sample[b]) if pre < 0 else torch.full((len(own),), -1, dtype=torch.int32))
+    lens = [len(x) for x in seqs]
+    cu = torch.zeros(len(seqs) + 1, dtype=torch.int32)
+    cu[1:] = torch.as_tensor(lens, dtype=torch.int32).cumsum(0)
+    pair_row = torch.as_tensor([int(cu[sq + 1]) - 1 for sq in pair_seq], dtype=torch.int32)
+    max_prompt = max(lens[sq] + (lens[kvp[sq]] if kvp[sq] >= 0 else 0) for sq in pair_seq)
+    return dict(input_ids=torch.as_tensor([t for x in seqs for t in x], dtype=torch.int32), feat_index=torch.cat(feat_rows),
+                position_ids=torch.cat(pos_rows, dim=1).contiguous(), cu_seqlens=cu, kv_prefix=torch.as_tensor(kvp, dtype=torch.int32),
+                pair_row=pair_row, pair_seq=torch.as_tensor(pair_seq, dtype=torch.int32), total_rows=int(cu[-1]), n_seq=len(seqs),
+                max_seq_len=max(lens), max_prompt_len=max_prompt, n_shared=len(shared))

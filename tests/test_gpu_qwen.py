@@ -226,3 +226,39 @@ def test_qwen_trace_topk(dev):
         p_top = eng.score_prompts(inp["pixel_patches"], inp["grid_thw"], prompts, top1, temperature=T, repetition_penalty=pen).cpu()
         ids2, probs2 = eng.topk_last(5, temperature=T, repetition_penalty=pen)
         assert torch.equal(ids2.cpu(), ids) and float((probs2.cpu()[:, 0] - p_top).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("pen", [1.0, 1.2])
+def test_qwen_kv_prefix_sharing_is_exact(dev, pen):
+    """M x N scoring repeats each image N times (reference score.py:104-106). With share_prefix the
+    [chat prefix + vision tokens] of an image go through the language model once and every text's suffix attends to those shared K/V rows;
+    causal attention makes the scores identical to the unshared prefill (only the fp32 accumulation order over key tiles differs)."""
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    sd = qo.make_synthetic_state_dict(cfg, seed=6)
+    g = torch.Generator().manual_seed(3)
+    grids = [(1, 12, 10), (1, 6, 8)]                       # 30 and 12 vision tokens -> prefixes of 34 / 16 rows; with the text > 128 rows for image 0?
+    grids = [(1, 24, 22), (1, 6, 8)]                       # 132 vision tokens: the shared prefix spans two 128-key tiles
+    patches = torch.randn(sum(t * h * w for t, h, w in grids), cfg.patch_dim, generator=g)
+    ntok = [t * h * w // 4 for t, h, w in grids]
+    prompts, img = [], []
+    for i in (0, 1):
+        for k in range(3):
+            prompts.append([5, 6, 7, 8] + [cfg.image_token_id] * ntok[i] + [9] + torch.randint(0, 500, (5 + 3 * k,), generator=g).tolist())
+            img.append(i)
+    answers = [9, 11, 13, 9, 11, 500]
+    eng = make_engine(cfg, sd, dev)
+    plain = eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen, share_prefix=False).cpu()
+    shared = eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen, share_prefix=True).cpu()
+    ids_s, p_s = eng.topk_last(3, repetition_penalty=pen)
+    auto = eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen).cpu()
+    print(f"\n[prefix sharing pen={pen}] plain {plain.tolist()} shared {shared.tolist()}")
+    assert torch.equal(shared, auto)
+    assert float((torch.log(shared) - torch.log(plain)).abs().max()) < 2e-3
+    o32 = qo.qwen25vl_score(sd, cfg, patches, grids, [torch.tensor(p) for p in prompts], answers, img, mode="fp32", repetition_penalty=pen)
+    o16 = qo.qwen25vl_score(sd, cfg, patches, grids, [torch.tensor(p) for p in prompts], answers, img, mode="bf16", repetition_penalty=pen)
+    gap = float((torch.log(o16) - torch.log(o32)).abs().max())
+    assert float((torch.log(shared) - torch.log(o32)).abs().max()) <= 2.0 * gap + 2e-2
+    # trace top-k works after a packed call too
+    eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen, share_prefix=False)
+    ids_p, p_p = eng.topk_last(3, repetition_penalty=pen)
+    assert torch.equal(ids_s.cpu()[:, 0], ids_p.cpu()[:, 0]) or float((p_s.cpu() - p_p.cpu()).abs().max()) < 1e-2

@@ -185,3 +185,35 @@ def test_oracle_matches_committed_hf_golden(golden_dir, case):
     pen = qo.qwen25vl_score(sd, cfg, inp["pixel_patches"], inp["grid_thw"], inp["input_ids"], inp["answer_ids"], inp["image_of_sample"],
                             mode="fp32", temperature=0.5, repetition_penalty=1.3, second_per_grid_ts=c["second_per_grid_ts"])
     assert float((torch.log(pen) - torch.log(hf["probs_penalty_1p3_T_0p5"])).abs().max()) < 1e-4
+
+
+def test_packed_indices_reassemble_every_prompt():
+    """KV-prefix sharing: build_packed_indices stores the [chat prefix + vision run] of prompts over one image once.
+    Re-assembling prefix rows + own rows must give back exactly the ids, mRoPE positions and feature indices of the padded layout."""
+    cfg = qo.Qwen25VLConfig.tiny(**TINY)
+    g = torch.Generator().manual_seed(0)
+    grids = [(1, 6, 4), (1, 4, 4), (1, 4, 6)]
+    ntok = [t * h * w // 4 for t, h, w in grids]
+    prompts, img = [], []
+    for i in (0, 1):
+        for k in range(3):
+            prompts.append([5, 6, 7] + [cfg.image_token_id] * ntok[i] + [9] + torch.randint(0, 500, (4 + k,), generator=g).tolist())
+            img.append(i)
+    prompts.append([1, 2] + [cfg.image_token_id] * ntok[2] + [3, 4, 5])      # nobody shares this one: stored whole
+    img.append(2)
+    args = (cfg.image_token_id, cfg.spatial_merge_size, cfg.tokens_per_second)
+    pk = qwen_host.build_packed_indices(prompts, grids, img, *args, video_token_id=cfg.video_token_id)
+    full = qwen_host.build_batch_indices(prompts, grids, img, *args, video_token_id=cfg.video_token_id)
+    S = full["input_ids"].shape[1]
+    cu = pk["cu_seqlens"].tolist()
+    assert pk["n_shared"] == 2 and pk["n_seq"] == 2 + len(prompts) and pk["total_rows"] == cu[-1] < sum(map(len, prompts))
+    for b, p in enumerate(prompts):
+        sq = int(pk["pair_seq"][b])
+        pre = int(pk["kv_prefix"][sq])
+        rows = (list(range(cu[pre], cu[pre + 1])) if pre >= 0 else []) + list(range(cu[sq], cu[sq + 1]))
+        assert pk["input_ids"][rows].tolist() == p
+        assert torch.equal(pk["position_ids"][:, rows], full["position_ids"].view(3, len(prompts), S)[:, b, :len(p)])
+        assert torch.equal(pk["feat_index"][rows], full["feat_index"][b, :len(p)])
+        assert int(pk["pair_row"][b]) == rows[-1]
+    assert int(pk["kv_prefix"][int(pk["pair_seq"][-1])]) == -1
+    assert pk["max_prompt_len"] == max(map(len, prompts)) and pk["max_seq_len"] == max(cu[i + 1] - cu[i] for i in range(pk["n_seq"]))

@@ -21,4 +21,11 @@ VQA_ATTN_VARIANT=31 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-ba
 for f in 21 31; do python -c "
 import json
 d=json.load(open('$O/bench_attn$f.json')); print('$f', round(d['value'],2), 'pairs/s', d['breakdown_ms'], d['clocks']['sm_mhz'], 'MHz', d['sample_scores'])"; done
+echo "== fused norms: kernel hooks, engine modes, bench"
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k fused_rmsnorm > $O/normfuse_kernels.log 2>&1; echo "rc=$?" >> $O/normfuse_kernels.log; tail -3 $O/normfuse_kernels.log
+timeout 900 python -m pytest tests/test_gpu_clipt5.py -x -q -s -k "modes" > $O/modes.log 2>&1; echo "rc=$?" >> $O/modes.log; grep -E "^\[|passed|failed|rc=" $O/modes.log | tail -12
+for cfgs in "0 0" "1 0" "0 1"; do set -- $cfgs; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-hf-baseline --fuse-norms $1 --round-scores $2 > $O/bench_f$1_r$2.json 2> $O/bench_f$1_r$2.err
+python -c "
+import json
+d=json.load(open('$O/bench_f$1_r$2.json')); print('fuse=$1 round=$2', round(d['value'],2), 'pairs/s', d['breakdown_ms'], d['clocks']['sm_mhz'], 'MHz', d['sample_scores'])"; done
 echo done
