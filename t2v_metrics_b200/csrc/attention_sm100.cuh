@@ -22,7 +22,7 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
-constexpr bool ATTN_STREAM_DEFAULT = false;   // true: attn_tc_d64_stream_kernel is the production softmax stage
+constexpr int ATTN_STAGE_DEFAULT = 1;   // production softmax stage: 0 two-pass (attn_tc_d64_kernel), 1 streaming, 2 split-row streaming
 constexpr int ATTN_POLY_DEFAULT = 0;
 constexpr int ATTN128_POLY_DEFAULT = 2;   // d128 (1 CTA / SM): 2 of 8 pairs on the FMA pipe measured 1-3 % faster (profiles/r02_attention.md)   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
 
@@ -929,6 +929,362 @@ attn_tc_d64_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const At
     if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
 }
 
+// Split-row variant of the streaming stage: EIGHT softmax warps per CTA. Warps w and w + 4 own the same 32 query rows (same TMEM lane
+// quadrant) and half of each tile's key columns (chunks {0,1} / {2,3}), so every SM sub-partition hosts four softmax warps (two per CTA, two
+// CTAs per SM) instead of two -- the stage is latency-bound (profiles/r02_attention.md: 0.19 IPC per softmax warp, MUFU pipe 38 % busy), and
+// the second pair of warps fills the issue slots the first pair leaves empty. The two halves of a row agree on the exponent reference through
+// a 2 x 128-float exchange in shared memory and a 64-thread named barrier: once per query tile (pre-pass maximum), once per key tile (tile
+// maximum for the lazy rescale) and once in the epilogue (row sums). Each half rescales / normalises / stores 32 of O's 64 columns.
+template <bool HAS_BIAS, bool ROUND>
+__global__ void __launch_bounds__(320, 2)
+attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
+    constexpr int POLY = 0;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const size_t row_base = (size_t)b * p.S;
+    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
+    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
+
+    // rows past the last valid query tile: deterministic zeros
+    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
+        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
+        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (nq == 0) return;
+
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
+    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
+    // sliding-window bias table, entry x <-> rel = x - W: !ROUND: float4 log2e * (b[rel], .., b[rel+3]); ROUND: the same four as bf16 (8 bytes)
+    uint8_t* sBiasQ = smem + 6 * AT_TILE_BYTES;
+    constexpr uint32_t BQ_ENTRY = ROUND ? 8u : 16u;
+    const int Wn = 128 * p.near_tiles + 127;
+    const int nQ = HAS_BIAS ? 2 * Wn + 1 : 0;
+    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (((size_t)nQ * BQ_ENTRY + 15) & ~size_t(15)));   // [8]
+    float* sXch = sRed + 16;                                     // [2 buffers][2 halves][128 rows]: row maxima / row sums exchanged between the halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
+    uint64_t* q_full = bars;          // [2]
+    uint64_t* q_empty = bars + 2;     // [2]
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 8);
+        mbar_init(p_full, 8);
+        mbar_init(o_done, 1);
+        mbar_init(o_free, 8);
+        fence_barrier_init();
+        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
+        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
+        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
+        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
+        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    const float LOG2E = 1.4426950408889634f;
+    const float BSC = ROUND ? 1.0f : LOG2E;   // domain the table / constants are kept in
+    float b_left = 0.f, b_right = 0.f;      // constant bias of far tiles to the left / right of the diagonal
+    if (HAS_BIAS) {
+        const int width = 2 * p.S - 1;
+        const float* src = p.bias_table + (size_t)h * width;
+        b_left = __ldg(src) * BSC;
+        b_right = __ldg(src + width - 1) * BSC;
+        float lmax = -INFINITY;
+        for (int x = threadIdx.x; x < nQ; x += blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = min(max(x + k - Wn + (p.S - 1), 0), width - 1);   // rel = x + k - W, clamped to the table
+                v[k] = __ldg(src + idx) * BSC;
+            }
+            if constexpr (ROUND) reinterpret_cast<uint2*>(sBiasQ)[x] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            else                 reinterpret_cast<float4*>(sBiasQ)[x] = make_float4(v[0], v[1], v[2], v[3]);
+            lmax = fmaxf(lmax, v[0]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) sRed[warp] = lmax;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
+    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                if (qi > 0) {   // (tile 0 was issued during set-up)
+                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+                }
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    if (g == 0) continue;
+                    const int st = g & 1;
+                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
+            auto issue_pv = [&](int g) {
+                const int j = g % nkt, qi = g / nkt;
+                mbar_wait(p_full, (uint32_t)g & 1u);
+                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
+                tcgen05_fence_after();
+                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < AT_BK / 16; ++ks)
+                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
+                                (j > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<1>(&kv_empty[g & 1]);
+                umma_commit<1>(o_done);
+            };
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qb = qi & 1;
+                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
+                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
+                for (int j = 0; j < nkt; ++j) {
+                    const int g = qi * nkt + j;
+                    const int st = g & 1;
+                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
+                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit<1>(s_full);
+                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
+                    if (g > 0) issue_pv(g - 1);
+                }
+            }
+            issue_pv(total_tiles - 1);
+        }
+    } else {
+        // ===================== softmax / correction / epilogue: two threads per query row (64 keys of a tile each) =====================
+        const uint32_t quad = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;           // 0: key chunks {0,1} of every tile and O columns [0,32); 1: chunks {2,3}, O columns [32,64)
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (quad * 32u) << 16;
+        uint32_t xphase = 0;
+        auto exchange = [&](float mine) -> float {        // value of the other half of this row
+            float* buf = sXch + xphase * 256;
+            buf[half * 128 + row] = mine;
+            asm volatile("bar.sync %0, 64;" ::"r"(1u + quad) : "memory");
+            const float other = buf[(half ^ 1u) * 128 + row];
+            xphase ^= 1u;
+            return other;
+        };
+        float bmax_near = 0.f;
+        if (HAS_BIAS) {
+            bmax_near = sRed[0];
+#pragma unroll
+            for (int i = 1; i < 10; ++i) bmax_near = fmaxf(bmax_near, sRed[i]);
+        }
+        const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
+        const uint32_t bl2 = pack_bf16x2(b_left, b_left), br2 = pack_bf16x2(b_right, b_right);   // ROUND: far-tile bias as bf16 pairs
+        auto chunk_max = [](const uint32_t (&v)[32], float& m0, float& m1, float& m2, float& m3) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            }
+        };
+        int g = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int q0 = qi * AT_BQ;
+            const int qrow = q0 + row;
+            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D + half * 32;
+            if (q0 + (int)quad * 32 >= len) {
+                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
+                for (int j = 0; j < nkt; ++j, ++g) {
+                    mbar_wait(s_full, (uint32_t)g & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full);
+                }
+                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            float m_run = 0.f, l_run = 0.f, corr_pend = 1.f;       // l_run: this half's share of the row sum
+            bool pend = false;                 // O and l still have to be multiplied by corr_pend (decided at the end of the previous tile)
+            for (int j = 0; j < nkt; ++j, ++g) {
+                const int k0 = j * AT_BK;
+                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks of the tile that contain at least one valid key
+                const int c_lo = 2 * (int)half;
+                const int n_mine = max(0, min(nch - c_lo, 2));  // this half's chunks: c_lo .. c_lo + n_mine - 1
+                const int dt = j - qi;
+                const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
+                const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
+                const uint32_t s_addr = tmem_S + lane_off + c_lo * 32;
+                mbar_wait(s_full, (uint32_t)g & 1u);
+                tcgen05_fence_after();
+                uint32_t buf[32];
+                auto mask = [&](uint32_t (&v)[32], int c) {
+                    if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (k0 + c * 32 + i >= len) v[i] = 0xff800000u;
+                    }
+                };
+                if (j == 0) {
+                    // first key tile of this query tile: no reference yet -> max-only pre-pass (S stays in TMEM for the real pass)
+                    float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < n_mine; ++c) {
+                        tmem_ld_32x32b_x32(s_addr + c * 32, buf);
+                        tmem_ld_wait();
+                        mask(buf, c_lo + c);
+                        chunk_max(buf, a0, a1, a2, a3);
+                    }
+                    const float raw_half = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                    const float raw = fmaxf(raw_half, exchange(raw_half));
+                    m_run = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
+                } else {
+                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                    tcgen05_fence_after();
+                    if (pend) {
+#pragma unroll 1
+                        for (int c = 0; c < 2; ++c) {            // this half's 32 columns of O
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr_pend);
+                            tmem_st_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
+                        }
+                        l_run *= corr_pend;
+                        pend = false;
+                    }
+                }
+                // ---- this half's (up to) two chunks: exponentials against the running reference, tile maximum tracked on the side
+                const float a_add = near ? -m_run : (ROUND ? -m_run : bias_ub - m_run);
+                const uint64_t addc = pack2(a_add, a_add);
+                const uint32_t bq = near ? smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * BQ_ENTRY : 0u;
+                const uint32_t bfar = dt < 0 ? bl2 : br2;
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                if (n_mine == 0) {           // nothing of S to read for this half: release it right away
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                }
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t pk[16];
+                    if (c < n_mine) {
+                        tmem_ld_32x32b_x32(s_addr + c * 32, buf);
+                        tmem_ld_wait();
+                        if (c == n_mine - 1) {   // this half's part of S has left TMEM (the next QK^T starts when all eight warps say so)
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(s_empty);
+                        }
+                        mask(buf, c_lo + c);
+                        chunk_max(buf, t0, t1, t2, t3);
+                        if (near) softmax_chunk<true, POLY, ROUND>(buf, pk, bq + (c_lo + c) * 32 * BQ_ENTRY, cc, addc, 0u, false, acc0, acc1);
+                        else      softmax_chunk<false, POLY, ROUND>(buf, pk, 0u, cc, addc, bfar, HAS_BIAS, acc0, acc1);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    }
+                    tmem_st_32x32b_x16(tmem_P + lane_off + (c_lo + c) * 16, pk);
+                }
+                {
+                    float a0, a1, a2, a3;
+                    unpack2(acc0, a0, a1);
+                    unpack2(acc1, a2, a3);
+                    l_run += (a0 + a1) + (a2 + a3);
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                // ---- did this tile outgrow the reference? both halves see the same row maximum, so the two warps of a row pair take the
+                // same decision; the NEXT tile then starts by rescaling O and l (after P.V of this one retired)
+                const float raw_half = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                const float raw = fmaxf(raw_half, exchange(raw_half));
+                const float bound = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
+                if (__any_sync(0xffffffffu, bound > m_run + 8.f)) {
+                    const float m_new = fmaxf(m_run, bound);
+                    corr_pend = fast_exp2(m_run - m_new);
+                    m_run = m_new;
+                    pend = true;
+                }
+            }
+            // ---- epilogue of this query tile: O / l, 32 columns per half
+            const float l_row = l_run + exchange(l_run);
+            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+            tcgen05_fence_after();
+            const float inv = (qrow < len) ? 1.f / l_row : 0.f;
+            {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + half * 32, ov);
+                tmem_ld_wait();
+                tcgen05_fence_before();      // O copied out: the next query tile's first P.V may overwrite it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free);
+                if (qrow < p.S) {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
+                        *reinterpret_cast<uint4*>(orow + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
+}
+
 // qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
 // bias_const_from: the bias table is constant (per head and side) for |key - query| >= bias_const_from (T5: relative_attention_max_distance);
 // <= 0 or >= S: no such guarantee, every tile reads the table.
@@ -965,6 +1321,22 @@ inline cudaError_t launch_attn_stream_t(const CUtensorMap& tm, const AttnTc2Para
     return cudaGetLastError();
 }
 
+template <bool HAS_BIAS, bool ROUND>
+inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
+    auto kernel = attn_tc_d64_split_kernel<HAS_BIAS, ROUND>;
+    static std::atomic<size_t> max_set[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > max_set[dev & 63].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[dev & 63].store(smem, std::memory_order_release);
+    }
+    kernel<<<dim3(1, p.H, B), 320, smem, stream>>>(tm, p);
+    return cudaGetLastError();
+}
+
 // round_scores: reproduce the bf16 tensors of the reference's eager attention (scores, scores + bias) before the fp32 softmax.
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
                                   int B, int S, int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
@@ -974,7 +1346,10 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
     static const int variant = [] { const char* v = getenv("VQA_ATTN_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();
     if (variant == 20 || variant == 30) round_scores = false;      // A/B: without the score rounding
     if (variant == 21 || variant == 31) round_scores = true;
-    const bool stream = variant >= 30 ? true : (variant >= 20 ? false : ATTN_STREAM_DEFAULT);
+    const int stage = variant >= 40 ? 2 : (variant >= 30 ? 1 : (variant >= 20 ? 0 : ATTN_STAGE_DEFAULT));   // 0 two-pass, 1 streaming, 2 split-row streaming
+    if (variant == 40) round_scores = false;
+    if (variant == 41) round_scores = true;
+    const bool stream = stage == 1;
     AttnTc2Params p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -993,6 +1368,11 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         if (e != cudaSuccess) return e;
         kernel<<<dim3(1, H, B), 192, smem, stream_>>>(tm, p);
         return cudaGetLastError();
+    }
+    if (stage == 2) {
+        const size_t smem4 = smem + 2048 + 64;  // + the row-pair exchange buffers and the wider per-warp reduction scratch
+        if (bias_table) return round_scores ? launch_attn_split_t<true, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<true, false>(tm, p, B, smem4, stream_);
+        return round_scores ? launch_attn_split_t<false, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<false, false>(tm, p, B, smem4, stream_);
     }
     if (stream) {
         if (bias_table) return round_scores ? launch_attn_stream_t<true, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<true, false>(tm, p, B, smem, stream_);

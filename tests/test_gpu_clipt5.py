@@ -161,6 +161,36 @@ def test_batch_padding_and_dedupe_invariance(golden_dir, dev):
     assert torch.equal(a, b_)
 
 
+def test_cuda_graph_replay_equals_direct_launches(golden_dir, dev):
+    """score_tensors_graphed: the whole forward captured once per shape and replayed; identical scores, also after the inputs change and
+    after a bigger call forced a new workspace (stale graphs must be dropped)."""
+    import time
+    blob, cfg, sd = load_case("mid", golden_dir)
+    inp = blob["inputs"]
+    eng = make_engine(cfg, sd, dev)
+    i32 = lambda t: t.to(dev, torch.int32)
+    args = [inp["pixels"].to(dev), i32(inp["input_ids"]), i32(inp["text_lens"]), i32(inp["labels"])]
+    direct = eng.score_tensors(*args).clone()
+    g1 = eng.score_tensors_graphed(*args).clone()
+    perm = torch.arange(args[0].shape[0] - 1, -1, -1, device=dev)
+    args2 = [a[perm].contiguous() for a in args]
+    g2 = eng.score_tensors_graphed(*args2).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(g1, direct) and torch.equal(g2, direct[perm])
+    for fn, name in ((lambda: eng.score_tensors(*args), "direct"), (lambda: eng.score_tensors_graphed(*args), "graph")):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        print(f"\n[{name}] {1000 * (time.perf_counter() - t0) / 10:.3f} ms per call ({eng.last_launch_count()} launches)")
+    big = [torch.cat([a, a]) for a in args]
+    eng.score_tensors(*big)                        # larger workspace -> old graphs dropped
+    g3 = eng.score_tensors_graphed(*args).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(g3, direct)
+
+
 def test_full_size_xxl_properties(dev):
     """BASELINE config-2 size (clip-flant5-xxl dims, B=64, S_enc=672): determinism, finite scores in [0,1], and batch
     invariance of the first pairs (B=64 vs B=4), which exercises every kernel at its production shape."""
