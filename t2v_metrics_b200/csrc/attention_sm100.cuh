@@ -933,8 +933,10 @@ attn_tc_d64_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const At
 // quadrant) and half of each tile's key columns (chunks {0,1} / {2,3}), so every SM sub-partition hosts four softmax warps (two per CTA, two
 // CTAs per SM) instead of two -- the stage is latency-bound (profiles/r02_attention.md: 0.19 IPC per softmax warp, MUFU pipe 38 % busy), and
 // the second pair of warps fills the issue slots the first pair leaves empty. The two halves of a row agree on the exponent reference through
-// a 2 x 128-float exchange in shared memory and a 64-thread named barrier: once per query tile (pre-pass maximum), once per key tile (tile
-// maximum for the lazy rescale) and once in the epilogue (row sums). Each half rescales / normalises / stores 32 of O's 64 columns.
+// a split-phase exchange in shared memory (value slots + mbarriers, see post()/collect() below): once per query tile (pre-pass maximum), once per
+// key tile (the tile's bound, published at its end and read at the start of the next tile, where the lazy rescale is decided) and once in the
+// epilogue (row sums). Each half rescales / normalises / stores 32 of O's 64 columns. The wait for the previous tile's P.V (the P slot in TMEM is
+// single-buffered) sits between the first chunk's exponentials and its store, not at the top of the tile.
 template <bool HAS_BIAS, bool ROUND>
 __global__ void __launch_bounds__(320, 2)
 attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
@@ -975,7 +977,8 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     uint64_t* p_full = bars + 10;
     uint64_t* o_done = bars + 11;
     uint64_t* o_free = bars + 12;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* xbar = bars + 13;       // [4 row quadrants][2 halves][2 phases]: "my value for exchange k is in shared memory"
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 29);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -989,6 +992,8 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         mbar_init(p_full, 8);
         mbar_init(o_done, 1);
         mbar_init(o_free, 8);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 1);
         fence_barrier_init();
         // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
         mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
@@ -1098,13 +1103,19 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         const uint32_t half = (warp - 2u) >> 2;           // 0: key chunks {0,1} of every tile and O columns [0,32); 1: chunks {2,3}, O columns [32,64)
         const int row = quad * 32 + lane;
         const uint32_t lane_off = (quad * 32u) << 16;
-        uint32_t xphase = 0;
-        auto exchange = [&](float mine) -> float {        // value of the other half of this row
-            float* buf = sXch + xphase * 256;
-            buf[half * 128 + row] = mine;
-            asm volatile("bar.sync %0, 64;" ::"r"(1u + quad) : "memory");
-            const float other = buf[(half ^ 1u) * 128 + row];
-            xphase ^= 1u;
+        // Split-phase exchange between the two halves of a row: post(v) publishes this half's value for exchange number xk, collect() waits
+        // for the partner's value of the same exchange. Two value buffers and two mbarriers per (quadrant, half) alternate with xk, so a warp
+        // that runs one exchange ahead of its partner (it cannot run two ahead: the S / P barriers need both) never reuses a live slot.
+        uint32_t xk = 0;
+        auto post = [&](float v) {
+            sXch[(xk & 1u) * 256 + half * 128 + row] = v;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xbar[(quad * 2 + half) * 2 + (xk & 1u)]);
+        };
+        auto collect = [&]() -> float {
+            mbar_wait(&xbar[(quad * 2 + (half ^ 1u)) * 2 + (xk & 1u)], (xk >> 1) & 1u);
+            const float other = sXch[(xk & 1u) * 256 + (half ^ 1u) * 128 + row];
+            ++xk;
             return other;
         };
         float bmax_near = 0.f;
@@ -1148,8 +1159,8 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 }
                 continue;
             }
-            float m_run = 0.f, l_run = 0.f, corr_pend = 1.f;       // l_run: this half's share of the row sum
-            bool pend = false;                 // O and l still have to be multiplied by corr_pend (decided at the end of the previous tile)
+            float m_run = 0.f, l_run = 0.f;       // l_run: this half's share of the row sum
+            float bound_prev = 0.f;               // this half's upper bound of the previous tile's exponents (posted to the partner at its end)
             for (int j = 0; j < nkt; ++j, ++g) {
                 const int k0 = j * AT_BK;
                 const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks of the tile that contain at least one valid key
@@ -1169,6 +1180,7 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                             if (k0 + c * 32 + i >= len) v[i] = 0xff800000u;
                     }
                 };
+                bool p_free = (j == 0);           // P of the previous tile consumed (o_done observed)? -- the first tile's P slot is free by construction
                 if (j == 0) {
                     // first key tile of this query tile: no reference yet -> max-only pre-pass (S stays in TMEM for the real pass)
                     float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
@@ -1180,23 +1192,30 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                         chunk_max(buf, a0, a1, a2, a3);
                     }
                     const float raw_half = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-                    const float raw = fmaxf(raw_half, exchange(raw_half));
-                    m_run = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
+                    const float bound_half = ROUND ? (raw_half + bias_ub) * p.scale_log2e : fmaf(raw_half, p.scale_log2e, bias_ub);
+                    post(bound_half);
+                    m_run = fmaxf(bound_half, collect());
                 } else {
-                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
-                    tcgen05_fence_after();
-                    if (pend) {
+                    // did the previous tile outgrow the reference? (its row maximum = max of the two halves' bounds; both halves see the same
+                    // value and take the same decision) then O and l are rescaled before this tile's P is added
+                    const float bound = fmaxf(bound_prev, collect());
+                    if (__any_sync(0xffffffffu, bound > m_run + 8.f)) {
+                        const float m_new = fmaxf(m_run, bound);
+                        const float corr = fast_exp2(m_run - m_new);
+                        m_run = m_new;
+                        l_run *= corr;
+                        mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
+                        tcgen05_fence_after();
+                        p_free = true;
 #pragma unroll 1
                         for (int c = 0; c < 2; ++c) {            // this half's 32 columns of O
                             uint32_t ov[16];
                             tmem_ld_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr_pend);
+                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
                             tmem_st_32x32b_x16(tmem_O + lane_off + half * 32 + c * 16, ov);
                         }
-                        l_run *= corr_pend;
-                        pend = false;
                     }
                 }
                 // ---- this half's (up to) two chunks: exponentials against the running reference, tile maximum tracked on the side
@@ -1229,6 +1248,13 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
+                    if (!p_free) {
+                        // the P slot is single-buffered: P.V of the previous tile must have read it. Waiting HERE (after the first chunk's
+                        // exponentials) instead of at the top of the tile hides the P.V latency behind them.
+                        mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
+                        tcgen05_fence_after();
+                        p_free = true;
+                    }
                     tmem_st_32x32b_x16(tmem_P + lane_off + (c_lo + c) * 16, pk);
                 }
                 {
@@ -1241,20 +1267,15 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
-                // ---- did this tile outgrow the reference? both halves see the same row maximum, so the two warps of a row pair take the
-                // same decision; the NEXT tile then starts by rescaling O and l (after P.V of this one retired)
-                const float raw_half = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-                const float raw = fmaxf(raw_half, exchange(raw_half));
-                const float bound = ROUND ? (raw + bias_ub) * p.scale_log2e : fmaf(raw, p.scale_log2e, bias_ub);
-                if (__any_sync(0xffffffffu, bound > m_run + 8.f)) {
-                    const float m_new = fmaxf(m_run, bound);
-                    corr_pend = fast_exp2(m_run - m_new);
-                    m_run = m_new;
-                    pend = true;
+                if (j + 1 < nkt) {           // publish this half's bound for the next tile's rescale decision
+                    const float raw_half = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                    bound_prev = ROUND ? (raw_half + bias_ub) * p.scale_log2e : fmaf(raw_half, p.scale_log2e, bias_ub);
+                    post(bound_prev);
                 }
             }
             // ---- epilogue of this query tile: O / l, 32 columns per half
-            const float l_row = l_run + exchange(l_run);
+            post(l_run);
+            const float l_row = l_run + collect();
             mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
             tcgen05_fence_after();
             const float inv = (qrow < len) ? 1.f / l_row : 0.f;
@@ -1370,7 +1391,7 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
         return cudaGetLastError();
     }
     if (stage == 2) {
-        const size_t smem4 = smem + 2048 + 64;  // + the row-pair exchange buffers and the wider per-warp reduction scratch
+        const size_t smem4 = smem + 2048 + 64 + 128;  // + the row-pair exchange buffers / barriers and the wider per-warp reduction scratch
         if (bias_table) return round_scores ? launch_attn_split_t<true, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<true, false>(tm, p, B, smem4, stream_);
         return round_scores ? launch_attn_split_t<false, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<false, false>(tm, p, B, smem4, stream_);
     }

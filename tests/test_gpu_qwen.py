@@ -229,10 +229,13 @@ def test_qwen_trace_topk(dev):
 
 
 @pytest.mark.parametrize("pen", [1.0, 1.2])
-def test_qwen_kv_prefix_sharing_is_exact(dev, pen):
+def test_qwen_kv_prefix_sharing_matches_the_unshared_prefill(dev, pen):
     """M x N scoring repeats each image N times (reference score.py:104-106). With share_prefix the
     [chat prefix + vision tokens] of an image go through the language model once and every text's suffix attends to those shared K/V rows;
-    causal attention makes the scores identical to the unshared prefill (only the fp32 accumulation order over key tiles differs)."""
+    causal attention makes the scores identical to the unshared prefill in real arithmetic. On the device the key tiles are cut at
+    different places (prefix tiles, then the suffix's own tiles), so the online-softmax reference of a row -- and with it the bf16 rounding
+    of P = 2^(s - m) -- can differ: image 0 (prefix longer than one 128-key tile: same first tile, same reference) comes out bit-identical,
+    image 1 (17-row prefix) moves by bf16 noise. Bound: twice the oracle's own bf16-vs-fp32 gap on the same inputs."""
     cfg = qo.Qwen25VLConfig.tiny(**TINY)
     sd = qo.make_synthetic_state_dict(cfg, seed=6)
     g = torch.Generator().manual_seed(3)
@@ -253,11 +256,15 @@ def test_qwen_kv_prefix_sharing_is_exact(dev, pen):
     auto = eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen).cpu()
     print(f"\n[prefix sharing pen={pen}] plain {plain.tolist()} shared {shared.tolist()}")
     assert torch.equal(shared, auto)
-    assert float((torch.log(shared) - torch.log(plain)).abs().max()) < 2e-3
     o32 = qo.qwen25vl_score(sd, cfg, patches, grids, [torch.tensor(p) for p in prompts], answers, img, mode="fp32", repetition_penalty=pen)
     o16 = qo.qwen25vl_score(sd, cfg, patches, grids, [torch.tensor(p) for p in prompts], answers, img, mode="bf16", repetition_penalty=pen)
     gap = float((torch.log(o16) - torch.log(o32)).abs().max())
+    d = (torch.log(shared) - torch.log(plain)).abs()
+    print(f"   |dlog p| shared vs plain {d.tolist()}  oracle bf16-vs-fp32 gap {gap:.3e}")
+    assert float(d[:3].max()) < 1e-4            # image 0: identical first key tile -> identical softmax reference
+    assert float(d.max()) <= 2.0 * gap + 2e-3
     assert float((torch.log(shared) - torch.log(o32)).abs().max()) <= 2.0 * gap + 2e-2
+    assert float((torch.log(plain) - torch.log(o32)).abs().max()) <= 2.0 * gap + 2e-2
     # trace top-k works after a packed call too
     eng.score_prompts(patches, grids, prompts, answers, image_of_sample=img, repetition_penalty=pen, share_prefix=False)
     ids_p, p_p = eng.topk_last(3, repetition_penalty=pen)

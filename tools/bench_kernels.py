@@ -133,15 +133,21 @@ def gemm(mode):
     torch.manual_seed(0)
     rows = []
     only = os.environ.get("SHAPES", "").split(",") if os.environ.get("SHAPES") else list(SHAPES)
+    scheds = [tuple(int(x) for x in s.split(":")) for s in os.environ["SCHEDS"].split(",")] if os.environ.get("SCHEDS") else SCHEDULES
+    ballast = None
+    if os.environ.get("BALLAST_GB"):      # mimic the footprint of the real step (weights + workspace) around the operands
+        ballast = torch.empty(int(os.environ["BALLAST_GB"]) << 30, dtype=torch.uint8, device="cuda").fill_(1)
     for name in only:
         M, N, K, epi, res = SHAPES[name]
         a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
         w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+        if os.environ.get("ZERO_OPERANDS"):
+            a.zero_(); w.zero_()
         n_out = N // 2 if epi == "gated_gelu" else N
         c = torch.empty(M, n_out, dtype=torch.bfloat16, device="cuda")
         r = torch.randn(M, n_out, device="cuda").bfloat16() if res else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        for (g, ch) in SCHEDULES:
+        for (g, ch) in scheds:
             lib.vqa_set_gemm_schedule(g, ch)
             fn = lambda: ops.gemm(a, w, residual=r, epilogue=epi, out=c, gate_up_offset=N // 2 if epi == "gated_gelu" else 0)
             if mode == "ncu":
