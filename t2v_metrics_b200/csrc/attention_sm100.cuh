@@ -22,7 +22,7 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
-constexpr int ATTN_STAGE_DEFAULT = 1;   // production softmax stage: 0 two-pass (attn_tc_d64_kernel), 1 streaming, 2 split-row streaming
+constexpr int ATTN_STAGE_DEFAULT = 2;   // production softmax stage: 0 two-pass (attn_tc_d64_kernel), 1 streaming, 2 split-row streaming
 constexpr int ATTN_POLY_DEFAULT = 0;
 constexpr int ATTN128_POLY_DEFAULT = 2;   // d128 (1 CTA / SM): 2 of 8 pairs on the FMA pipe measured 1-3 % faster (profiles/r02_attention.md)   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
 

@@ -20,6 +20,19 @@
 
 namespace vqa {
 
+#ifndef VQA_GEMM_WAIT_HINT
+#define VQA_GEMM_WAIT_HINT 1
+#endif
+// mbarrier wait used by the GEMM's producer / MMA / epilogue warps: with the suspend-time hint (default) or the plain polling loop
+__device__ __forceinline__ void gemm_wait(uint64_t* bar, uint32_t parity) {
+#if VQA_GEMM_WAIT_HINT
+    mbar_wait(bar, parity);
+#else
+    mbar_wait_spin(bar, parity);
+#endif
+}
+
+
 enum GemmEpilogue : int {
     EPI_STORE = 0,       // C = [residual +] bf16(acc [+ bias])
     EPI_QUICK_GELU = 1,  // C = quick_gelu(bf16(acc + bias))                 (CLIP MLP fc1)
@@ -209,7 +222,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const int m_row = (m_blk * CG + (int)cta_rank) * BLOCK_M + batch * p.a_row_off;
                 const int w_row_base = batch * p.w_row_off;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    gemm_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem_a + stage * Cfg::A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                     const int k0 = kb * BLOCK_K + batch * p.a_k_off;
@@ -247,11 +260,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             for (int t = worker; t < num_tiles; t += num_workers, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1u;
-                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+                gemm_wait(&tmem_empty_bar[as], aphase ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    gemm_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::A_STAGE_BYTES));
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
@@ -302,7 +315,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
             if constexpr (epi_is_gated(EPI)) {
                 const int n_out0 = n_blk * OUT_TILE_COLS;
-                mbar_wait(&tmem_full_bar[as], aphase);
+                gemm_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
@@ -349,7 +362,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const int n0 = n_blk * BLOCK_N;
                 const int label = row_ok ? p.labels[m] : -1;
                 float run_max = -INFINITY, run_sum = 0.f;
-                mbar_wait(&tmem_full_bar[as], aphase);
+                gemm_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
@@ -389,7 +402,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const int n0 = n_blk * BLOCK_N;
                 float* Cf = reinterpret_cast<float*>(p.C);
                 const float* Rf = reinterpret_cast<const float*>(p.residual);
-                mbar_wait(&tmem_full_bar[as], aphase);
+                gemm_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
@@ -437,7 +450,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 };
                 prefetch(c_begin);
                 float ssq_acc = 0.f;        // producer side of the fused RMSNorm: sum of squares of the bf16 values this thread stores
-                mbar_wait(&tmem_full_bar[as], aphase);
+                gemm_wait(&tmem_full_bar[as], aphase);
                 tcgen05_fence_after();
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + NCH_PER; ++c) {
