@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-eager-bf16-on-this-GPU comparison point (hf_gpu_baseline)")
     ap.add_argument("--config1", action="store_true", help="--impl reference: BASELINE config 1 only (clip-flant5-xl, the reference's 4 PNGs x 4 prompts, batch 1, CPU)")
+    ap.add_argument("--graph", action="store_true", help="clip-flant5: replay the step from a CUDA graph (ClipT5Engine.score_tensors_graphed); "
+                    "meant for small --batch, where ~700 launches of host work are the floor")
     ap.add_argument("--ncu", action="store_true", help="profiling pass: 2 device steps only, no JSON (run under ncu)")
     return ap.parse_args()
 
@@ -454,7 +456,10 @@ def run_engine(args, rank, local_rank, world):
             torch.cuda.synchronize(dev)
 
     def step_device():
-        s = eng.score_tensors(d["pixels"], d["input_ids"], d["text_lens"], d["labels"])
+        if args.graph:
+            s = eng.score_tensors_graphed(d["pixels"], d["input_ids"], d["text_lens"], d["labels"])
+        else:
+            s = eng.score_tensors(d["pixels"], d["input_ids"], d["text_lens"], d["labels"])
         return gather_scores(s, total_pairs) if world > 1 else s
 
     def step_host():

@@ -209,6 +209,8 @@ class ClipT5Engine:
         _check(rc, self._h, "vqa_clipt5_score")
         return (out, logp) if return_logprobs else out
 
+    MAX_GRAPHS = 16
+
     def score_tensors_graphed(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, text_lens: torch.Tensor, labels: torch.Tensor,
                               image_index: Optional[torch.Tensor] = None) -> torch.Tensor:
         """score_tensors replayed from a CUDA graph captured once per call shape: the forward is ~700 launches whose
@@ -225,6 +227,8 @@ class ClipT5Engine:
             with torch.cuda.graph(graph):
                 out = self.score_tensors(static[0], static[1], static[2], static[3], image_index=static[4])
             entry = self._graphs[key] = (graph, static, out)
+            while len(self._graphs) > self.MAX_GRAPHS:          # oldest shape first (dict order = insertion order)
+                self._graphs.pop(next(iter(self._graphs)))
         graph, static, out = entry
         for dst, src in zip(static, (pixel_values, input_ids, text_lens, labels, image_index)):
             if dst is not None:

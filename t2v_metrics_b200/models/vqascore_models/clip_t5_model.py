@@ -47,8 +47,11 @@ class CLIPT5Model(VQAScoreModel):
 
     def __init__(self, model_name="clip-flant5-xxl", device="cuda", cache_dir=HF_CACHE_DIR, tokenizer=None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, config: Optional[ClipT5Config] = None,
-                 checkpoint: Optional[str] = None, vision_tower_checkpoint: Optional[str] = None, **kwargs):
+                 checkpoint: Optional[str] = None, vision_tower_checkpoint: Optional[str] = None, cuda_graph_max_pairs: int = 16, **kwargs):
         assert model_name in CLIP_T5_MODELS
+        # calls with at most this many pairs replay a CUDA graph captured per (pairs, images, padded text length, answer length): the
+        # ~700 launches of a forward cost more host time than device time at batch 1 (0 disables)
+        self.cuda_graph_max_pairs = int(cuda_graph_max_pairs)
         self._vision_checkpoint = vision_tower_checkpoint
         self._tokenizer_override = tokenizer
         self._state_dict = state_dict
@@ -119,6 +122,8 @@ class CLIPT5Model(VQAScoreModel):
             if any(t < 0 or t >= self.cfg.vocab for t in row):
                 raise ValueError(f"answer token id outside [0, vocab) (answers must not contain {DEFAULT_IMAGE_TOKEN!r})")
         L, T = max(map(len, ids)), max(map(len, labs))
+        if 0 < len(ids) <= getattr(self, "cuda_graph_max_pairs", 0):
+            L = (L + 15) // 16 * 16          # few distinct shapes -> few graphs; padded columns are masked by `lens` in the engine
         input_ids = torch.full((len(ids), L), pad, dtype=torch.int32)
         labels = torch.full((len(labs), T), IGNORE_INDEX, dtype=torch.int32)
         lens = torch.zeros(len(ids), dtype=torch.int32)
@@ -144,7 +149,7 @@ class CLIPT5Model(VQAScoreModel):
         pixels = self.load_images(list(uniq.keys()))
         dev = self.engine.device
         image_index = torch.tensor(index, dtype=torch.int32).to(dev, non_blocking=True)
-        scores = self.engine.score_tensors(pixels, input_ids.to(dev, non_blocking=True), lens.to(dev, non_blocking=True),
-                                           labels.to(dev, non_blocking=True),
-                                           image_index=image_index if len(uniq) != len(images) else None)
+        run = self.engine.score_tensors_graphed if 0 < len(images) <= self.cuda_graph_max_pairs else self.engine.score_tensors
+        scores = run(pixels, input_ids.to(dev, non_blocking=True), lens.to(dev, non_blocking=True), labels.to(dev, non_blocking=True),
+                     image_index=image_index if len(uniq) != len(images) else None)
         return scores.float().cpu()
