@@ -228,6 +228,10 @@ int vqa_qwen25vl_debug_layout(vqa_handle* h, int32_t batch, int32_t seq_len, int
  * L2-resident chunk, chunk_rows < 0 = one chunk; 0 = automatic. */
 int vqa_set_gemm_schedule(int32_t group_rows, int32_t chunk_rows);
 
+/* Tuning aid: number of clusters of `cluster_size` CTAs of the 256-wide GEMM kernel (one CTA per SM) the current device can hold at once
+ * (cudaOccupancyMaxActiveClusters); negative vqa_status on error. */
+int vqa_debug_max_active_clusters(int32_t cluster_size);
+
 const char* vqa_last_error(vqa_handle* h);
 void vqa_destroy(vqa_handle* h);
 

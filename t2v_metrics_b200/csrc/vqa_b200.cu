@@ -907,6 +907,34 @@ extern "C" int vqa_set_gemm_schedule(int32_t group_rows, int32_t chunk_rows) {
     return VQA_OK;
 }
 
+// How many clusters of `cluster_size` CTAs of the 256-wide cta_group::2 GEMM kernel (one CTA per SM: ~198 KB of shared memory) the current
+// device can hold at once (cudaOccupancyMaxActiveClusters). 148 SMs do not always divide into GPC-local clusters of 4 or 8: this is the
+// number a cluster-multicast variant of the GEMM has to be sized against. Returns the count, or a negative vqa_status.
+extern "C" int vqa_debug_max_active_clusters(int32_t cluster_size) {
+    if (cluster_size < 1 || cluster_size > 16) return VQA_ERR_INVALID_ARG;
+    using Cfg = GemmConfig<256, 2>;
+    auto kernel = gemm_bf16_sm100_kernel<256, 2, EPI_STORE>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return VQA_ERR_CUDA;
+    if (cluster_size > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return VQA_ERR_CUDA;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sms / cluster_size * cluster_size));
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = (unsigned)cluster_size;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return VQA_ERR_CUDA; }
+    return n;
+}
+
 extern "C" int vqa_set_profile(vqa_handle* h, int32_t enable) {
     if (!h) return VQA_ERR_INVALID_ARG;
     h->profile = enable != 0;
