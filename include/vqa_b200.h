@@ -302,12 +302,6 @@ int vqa_op_lmhead_logprob(const void* H, int32_t ldh, const void* W, int32_t ldw
 int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
                          const float* bias_table, float scale, int32_t bias_const_from, int32_t round_scores, void* stream);
 
-/* Instrumented run of the T5-encoder attention kernel (bias table, score rounding on): counters = DEVICE uint64[9], zeroed by the
- * caller; afterwards cycles summed over one softmax warp per CTA in {wait S, TMEM load, max + vote, wait O / rescale, exp2 + P store,
- * store wait + arrive, epilogue, total} and [8] = key tiles those warps went through (tools/bench_kernels.py attn-phases). */
-int vqa_debug_attention_d64_phases(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                                   const float* bias_table, int32_t bias_const_from, uint64_t* counters, void* stream);
-
 /* T5LayerNorm / nn.LayerNorm on [rows, D] bf16. beta == NULL selects T5 RMS norm. */
 int vqa_op_norm(const void* x, const void* gamma, const void* beta, void* y, int32_t rows, int32_t D, float eps,
                 void* stream);

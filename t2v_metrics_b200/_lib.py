@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "vqa_create_qwen25vl", "vqa_qwen25vl_set_rope", "vqa_qwen25vl_workspace_bytes", "vqa_qwen25vl_score",
     "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess", "vqa_resample_table", "vqa_qwen_preprocess_plan",
     "vqa_qwen_preprocess", "vqa_clipt5_debug_layout", "vqa_qwen25vl_debug_layout", "vqa_set_gemm_schedule",
-    "vqa_debug_attention_d64_phases", "vqa_qwen25vl_topk", "vqa_op_gemm_bf16_normfuse",
+    "vqa_qwen25vl_topk", "vqa_op_gemm_bf16_normfuse",
     "vqa_qwen25vl_packed_workspace_bytes", "vqa_qwen25vl_score_packed", "vqa_debug_max_active_clusters",
 ]
 
@@ -100,8 +100,6 @@ def load() -> C.CDLL:
     lib.vqa_op_lmhead_logprob.restype = C.c_int
     lib.vqa_op_attention_d64.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, i32, i32, vp]
     lib.vqa_op_attention_d64.restype = C.c_int
-    lib.vqa_debug_attention_d64_phases.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp, vp]
-    lib.vqa_debug_attention_d64_phases.restype = C.c_int
     lib.vqa_op_norm.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp]
     lib.vqa_op_norm.restype = C.c_int
     lib.vqa_op_attention_d128.argtypes = [vp, i32, i64, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp]

@@ -5,10 +5,13 @@
 //   warp 0   TMA producer : Q tile once, then K/V tiles (128 keys x 64) through a 2-stage smem ring
 //   warp 1   MMA issuer   : S = Q K^T   (UMMA 128x128x16, SS: both operands in 128B-swizzled smem, D in TMEM)
 //                           O += P V    (UMMA 128x64x16,  TS: P read from TMEM as bf16, V from smem MN-major)
-//   warps 2-5 softmax     : one thread per query row: tcgen05.ld the 128 scores, + bias (log2 domain), online max with
-//                           lazy rescale of O in TMEM, exp2, P -> bf16 -> tcgen05.st; final O / l -> HBM
+//   warps 2.. softmax     : tcgen05.ld the scores in 32-key chunks, + bias (log2 domain), speculative row reference with lazy rescale
+//                           of O in TMEM, exp2, P -> bf16 -> tcgen05.st; final O / l -> HBM.
+//                           attn_tc_d64_split_kernel (shipped): 8 warps, two threads per query row (64 keys of a tile each);
+//                           attn_tc_d64_stream_kernel (A/B, VQA_ATTN_VARIANT=30/31): 4 warps, one thread per row
 //
-// Two CTAs are resident per SM (<= 96 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Two CTAs are resident per SM (<= 110 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Measurements and the history of the stage (round-1 kernel, two-pass stage with clock64 phase counters): profiles/r02_attention.md.
 // Replaces the eager attention of transformers/models/t5/modeling_t5.py:308-334 (which materialises [B,H,S,S] scores in
 // HBM) and transformers/models/clip/modeling_clip.py:261-336.
 #pragma once
@@ -22,9 +25,8 @@ constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
 constexpr int AT_TMEM_COLS = 256;            // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int AT_BIAS_PAD = 128;
-constexpr int ATTN_STAGE_DEFAULT = 2;   // production softmax stage: 0 two-pass (attn_tc_d64_kernel), 1 streaming, 2 split-row streaming
-constexpr int ATTN_POLY_DEFAULT = 0;
-constexpr int ATTN128_POLY_DEFAULT = 2;   // d128 (1 CTA / SM): 2 of 8 pairs on the FMA pipe measured 1-3 % faster (profiles/r02_attention.md)   // score pairs of every 8 whose exp2 runs on the FMA pipe (measured on B200: no gain, the kernel is not MUFU-bound)
+constexpr int ATTN_STAGE_DEFAULT = 2;   // production softmax stage: 1 streaming (4 softmax warps), 2 split-row streaming (8 softmax warps)
+constexpr int ATTN128_POLY_DEFAULT = 2;   // d128 (1 CTA / SM): score pairs of every 8 whose exp2 runs on the FMA pipe; 2 measured 1-3 % faster (profiles/r02_attention.md)
 
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -97,9 +99,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 //     Q[x] = (b[x], b[x+1], b[x+2], b[x+3]), so a row reads its 128 biases with 32 conflict-free LDS.128 (lane l's window is lane 0's
 //     shifted by -l entries = -16 B); tiles further out see one constant per side (T5 buckets saturate at max_distance) folded into
 //     the FFMA2 addend, as do bias-free heads (CLIP);
-//   * POLY of every 8 score pairs take their exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error
-//     7.5e-5, well under the bf16 rounding of P) instead of the MUFU;
-//   * all tcgen05.ld of a tile are issued back to back and waited on once.
+//   * POLY of every 8 score pairs can take their exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error
+//     7.5e-5, well under the bf16 rounding of P) instead of the MUFU (used by the d128 kernel only: the d64 stage is not MUFU-bound).
 struct AttnTc2Params {
     __nv_bfloat16* o; int ldo;
     const int* seq_lens; const float* bias_table;   // [H, 2S-1] fp32 (natural-log domain) or nullptr
@@ -107,7 +108,6 @@ struct AttnTc2Params {
     float scale_log2e;
     int near_tiles;     // key tiles with |kt - qt| <= near_tiles read the bias table; beyond, the table's end values (constant there)
     float scale;        // ROUND kernels: softmax scale applied after the bf16 rounding of the scores (1 for T5, 1/8 for CLIP)
-    unsigned long long* prof;   // PROF kernels only: 8 cycle counters summed over the quad-0 softmax warps of all CTAs (tools/bench_kernels.py)
 };
 
 inline size_t attn_tc2_smem_bytes(int near_tiles, bool has_bias, bool round_scores) {
@@ -214,366 +214,6 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t
         pk[2 * q] = pack_bf16x2(e0, e1);
         pk[2 * q + 1] = pack_bf16x2(e2, e3);
     }
-}
-
-// PROF: clock64() stamps around the phases of the softmax loop (one warp per CTA reports), for the phase table in profiles/.
-template <bool HAS_BIAS, int POLY, bool ROUND, bool PROF = false>
-__global__ void __launch_bounds__(192, 2)
-attn_tc_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
-    const int h = blockIdx.y, b = blockIdx.z;
-    const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const size_t row_base = (size_t)b * p.S;
-    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
-    const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
-
-    // rows past the last valid query tile: deterministic zeros
-    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
-        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
-        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
-    }
-    if (nq == 0) return;
-
-    extern __shared__ uint8_t at_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                          // [2]
-    uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // [2]
-    uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // [2]
-    // sliding-window bias table, entry x <-> rel = x - W: !ROUND: float4 log2e * (b[rel], .., b[rel+3]); ROUND: the same four as bf16 (8 bytes)
-    uint8_t* sBiasQ = smem + 6 * AT_TILE_BYTES;
-    constexpr uint32_t BQ_ENTRY = ROUND ? 8u : 16u;
-    const int Wn = 128 * p.near_tiles + 127;
-    const int nQ = HAS_BIAS ? 2 * Wn + 1 : 0;
-    float* sRed = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES + (((size_t)nQ * BQ_ENTRY + 15) & ~size_t(15)));   // [8]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8);
-    uint64_t* q_full = bars;          // [2]
-    uint64_t* q_empty = bars + 2;     // [2]
-    uint64_t* kv_full = bars + 4;     // [2]
-    uint64_t* kv_empty = bars + 6;    // [2]
-    uint64_t* s_full = bars + 8;
-    uint64_t* s_empty = bars + 9;
-    uint64_t* p_full = bars + 10;
-    uint64_t* o_done = bars + 11;
-    uint64_t* o_free = bars + 12;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_qkv);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-        }
-        mbar_init(s_full, 1);
-        mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);
-        mbar_init(o_done, 1);
-        mbar_init(o_free, 4);
-        fence_barrier_init();
-        // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
-        mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
-        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
-        mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
-        tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
-        tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
-    }
-    if (warp == 1) {
-        tmem_alloc<1>(tmem_ptr_smem, AT_TMEM_COLS);
-        tmem_relinquish<1>();
-    }
-    const float LOG2E = 1.4426950408889634f;
-    const float BSC = ROUND ? 1.0f : LOG2E;   // domain the table / constants are kept in
-    float b_left = 0.f, b_right = 0.f;      // constant bias of far tiles to the left / right of the diagonal
-    if (HAS_BIAS) {
-        const int width = 2 * p.S - 1;
-        const float* src = p.bias_table + (size_t)h * width;
-        b_left = __ldg(src) * BSC;
-        b_right = __ldg(src + width - 1) * BSC;
-        float lmax = -INFINITY;
-        for (int x = threadIdx.x; x < nQ; x += blockDim.x) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int idx = min(max(x + k - Wn + (p.S - 1), 0), width - 1);   // rel = x + k - W, clamped to the table
-                v[k] = __ldg(src + idx) * BSC;
-            }
-            if constexpr (ROUND) reinterpret_cast<uint2*>(sBiasQ)[x] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-            else                 reinterpret_cast<float4*>(sBiasQ)[x] = make_float4(v[0], v[1], v[2], v[3]);
-            lmax = fmaxf(lmax, v[0]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        if (lane == 0) sRed[warp] = lmax;
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192;
-    const int total_tiles = nq * nkt;   // global tile index g = qi * nkt + j
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int qi = 0; qi < nq; ++qi) {
-                const int qb = qi & 1;
-                if (qi > 0) {   // (tile 0 was issued during set-up)
-                    mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
-                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
-                }
-                for (int j = 0; j < nkt; ++j) {
-                    const int g = qi * nkt + j;
-                    if (g == 0) continue;
-                    const int st = g & 1;
-                    mbar_wait(&kv_empty[st], (((uint32_t)g >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
-                    tma_load_2d(sK + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col0 + h * AT_D, (int)(row_base + j * AT_BK));
-                    tma_load_2d(sV + st * AT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col0 + h * AT_D, (int)(row_base + j * AT_BK));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
-            constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64) | (1u << 16);   // B operand MN-major
-            auto issue_pv = [&](int g) {
-                const int j = g % nkt, qi = g / nkt;
-                mbar_wait(p_full, (uint32_t)g & 1u);
-                if (j == 0 && qi > 0) mbar_wait(o_free, (uint32_t)(qi - 1) & 1u);   // previous query tile's O has been read out
-                tcgen05_fence_after();
-                const uint64_t vdesc = make_mnmajor_sw128_desc(smem_u32(sV + (g & 1) * AT_TILE_BYTES), AT_TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < AT_BK / 16; ++ks)
-                    umma_f16_ts(tmem_O, tmem_P + ks * 8, vdesc + (uint64_t)(ks * (16 * 128 / 16)), idesc_o,
-                                (j > 0 || ks > 0) ? 1u : 0u);
-                umma_commit<1>(&kv_empty[g & 1]);
-                umma_commit<1>(o_done);
-            };
-            for (int qi = 0; qi < nq; ++qi) {
-                const int qb = qi & 1;
-                mbar_wait(&q_full[qb], ((uint32_t)qi >> 1) & 1u);
-                const uint64_t qdesc = make_kmajor_sw128_desc(smem_u32(sQ + qb * AT_TILE_BYTES));
-                for (int j = 0; j < nkt; ++j) {
-                    const int g = qi * nkt + j;
-                    const int st = g & 1;
-                    mbar_wait(&kv_full[st], ((uint32_t)g >> 1) & 1u);
-                    mbar_wait(s_empty, ((uint32_t)g & 1u) ^ 1u);
-                    tcgen05_fence_after();
-                    const uint64_t kdesc = make_kmajor_sw128_desc(smem_u32(sK + st * AT_TILE_BYTES));
-#pragma unroll
-                    for (int k = 0; k < AT_D / 16; ++k)
-                        umma_f16<1>(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                    umma_commit<1>(s_full);
-                    if (j == nkt - 1) umma_commit<1>(&q_empty[qb]);   // Q buffer reusable once this tile's QK^T retired
-                    if (g > 0) issue_pv(g - 1);
-                }
-            }
-            issue_pv(total_tiles - 1);
-        }
-    } else {
-        // ===================== softmax / correction / epilogue: one thread per query row =====================
-        const uint32_t quad = warp & 3u;
-        const int row = quad * 32 + lane;
-        const uint32_t lane_off = (quad * 32u) << 16;
-        float bmax_near = 0.f;
-        if (HAS_BIAS) {
-            bmax_near = sRed[0];
-#pragma unroll
-            for (int i = 1; i < 6; ++i) bmax_near = fmaxf(bmax_near, sRed[i]);
-        }
-        const uint64_t cc = pack2(p.scale_log2e, p.scale_log2e);
-        const uint32_t bl2 = pack_bf16x2(b_left, b_left), br2 = pack_bf16x2(b_right, b_right);   // ROUND: far-tile bias as bf16 pairs
-        int g = 0;
-        for (int qi = 0; qi < nq; ++qi) {
-            const int q0 = qi * AT_BQ;
-            const int qrow = q0 + row;
-            __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D;
-            if (q0 + (int)quad * 32 >= len) {
-                // every row of this warp is padding in this query tile: keep the barrier protocol in lock-step, no math
-                for (int j = 0; j < nkt; ++j, ++g) {
-                    mbar_wait(s_full, (uint32_t)g & 1u);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(s_empty);
-                    if (g > 0) mbar_wait(p_full, (uint32_t)(g - 1) & 1u);   // previous phase must be closed before arriving again
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(p_full);
-                }
-                mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(o_free);
-                if (qrow < p.S) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
-                }
-                continue;
-            }
-            float m_run = -INFINITY, l_run = 0.f;
-            long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = 0;
-            if constexpr (PROF) tq0 = clock64();
-            for (int j = 0; j < nkt; ++j, ++g) {
-                const int k0 = j * AT_BK;
-                const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks that contain at least one valid key
-                const int dt = j - qi;
-                const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
-                long long t0 = 0, t1 = 0;
-                if constexpr (PROF) t0 = clock64();
-                mbar_wait(s_full, (uint32_t)g & 1u);
-                tcgen05_fence_after();
-                if constexpr (PROF) { t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
-                uint32_t sv[4][32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < nch) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
-                tmem_ld_wait();
-                if constexpr (PROF) { t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
-                // S is in registers: hand the TMEM columns back so the next QK^T can start
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_empty);
-
-                // ---- pass 1: row maximum of the raw scores (masked keys -> -inf)
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < nch) {
-                        if (k0 + c * 32 + 32 > len) {   // the one chunk that straddles the sample's length
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (k0 + c * 32 + i >= len) sv[c][i] = 0xff800000u;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            mx0 = fmax3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-                            mx1 = fmax3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
-                            mx2 = fmax3(mx2, __uint_as_float(sv[c][i + 4]), __uint_as_float(sv[c][i + 5]));
-                            mx3 = fmax3(mx3, __uint_as_float(sv[c][i + 6]), __uint_as_float(sv[c][i + 7]));
-                        }
-                    }
-                }
-                const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
-                const float raw_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                // upper bound of this tile's exponent arguments (log2 domain); ROUND: the bf16 roundings move a value by < 2^-7 relative,
-                // well inside the 2^8 headroom of the lazy rescale
-                const float tile_max = ROUND ? (raw_max + bias_ub) * p.scale_log2e : fmaf(raw_max, p.scale_log2e, bias_ub);
-                // lazy rescale: only move the reference max when some row of this warp grew by more than 2^8
-                float corr = 1.f;
-                bool rescale = false;
-                if (j == 0) {
-                    m_run = tile_max;
-                } else {
-                    const bool need = tile_max > m_run + 8.f;
-                    rescale = __any_sync(0xffffffffu, need);
-                    if (rescale) {
-                        const float m_new = fmaxf(m_run, tile_max);
-                        corr = fast_exp2(m_run - m_new);
-                        m_run = m_new;
-                    }
-                }
-                if constexpr (PROF) { t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
-                if (j > 0) {
-                    mbar_wait(o_done, (uint32_t)(g - 1) & 1u);   // P_{g-1} consumed, O complete up to tile g-1
-                    tcgen05_fence_after();
-                    if (rescale) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t ov[16];
-                            tmem_ld_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                            tmem_st_32x32b_x16(tmem_O + lane_off + c * 16, ov);
-                        }
-                    }
-                }
-                if constexpr (PROF) { t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
-                // ---- pass 2: exp2 and P -> TMEM, one 32-key chunk (16 packed bf16 pairs) at a time
-                uint64_t acc0 = 0ull, acc1 = 0ull;
-                if (near) {
-                    const uint64_t negm = pack2(-m_run, -m_run);
-                    const uint32_t bq = smem_u32(sBiasQ) + (uint32_t)(dt * 128 - row + Wn) * BQ_ENTRY;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[16];
-                        if (c < nch) softmax_chunk<true, POLY, ROUND>(sv[c], pk, bq + c * 32 * BQ_ENTRY, cc, negm, 0u, false, acc0, acc1);
-                        else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-                        }
-                        tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-                    }
-                } else {
-                    const float a = ROUND ? -m_run : (dt < 0 ? b_left : b_right) - m_run;
-                    const uint64_t addc = pack2(a, a);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[16];
-                        if (c < nch) softmax_chunk<false, POLY, ROUND>(sv[c], pk, 0u, cc, addc, dt < 0 ? bl2 : br2, HAS_BIAS, acc0, acc1);
-                        else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-                        }
-                        tmem_st_32x32b_x16(tmem_P + lane_off + c * 16, pk);
-                    }
-                }
-                {
-                    float a0, a1, a2, a3;
-                    unpack2(acc0, a0, a1);
-                    unpack2(acc1, a2, a3);
-                    l_run = l_run * corr + ((a0 + a1) + (a2 + a3));
-                }
-                if constexpr (PROF) { t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
-                tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full);
-                if constexpr (PROF) { t1 = clock64(); pc[5] += t1 - t0; }
-            }
-            // ---- epilogue of this query tile: O / l
-            long long te0 = 0;
-            if constexpr (PROF) te0 = clock64();
-            mbar_wait(o_done, (uint32_t)(g - 1) & 1u);
-            tcgen05_fence_after();
-            const float inv = (qrow < len) ? 1.f / l_run : 0.f;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-                tmem_ld_wait();
-                if (c == 1) {   // O fully copied out: the next query tile's first P.V may overwrite it now
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(o_free);
-                }
-                if (qrow < p.S) {
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            w[e] = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2 * e]) * inv, __uint_as_float(ov[gq * 8 + 2 * e + 1]) * inv);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-            if constexpr (PROF) {
-                const long long te1 = clock64();
-                pc[6] += te1 - te0;
-                pc[7] += te1 - tq0;
-                if (quad == 0 && lane == 0 && p.prof) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) atomicAdd(p.prof + i, (unsigned long long)pc[i]);
-                    atomicAdd(p.prof + 8, (unsigned long long)nkt);     // key tiles this warp went through
-                }
-            }
-        }
-        tcgen05_fence_before();
-    }
-
-    __syncthreads();
-    tcgen05_fence_after();
-    if (warp == 1) tmem_dealloc<1>(tmem_base, AT_TMEM_COLS);
 }
 
 // Streaming variant of the softmax stage: the same CTA skeleton, barriers and MMA schedule, but a softmax thread never holds more than
@@ -1309,23 +949,6 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
 // qkv: packed [B*S, ld] buffer; q/k/v head 0 start at columns q_col0/k_col0/v_col0.
 // bias_const_from: the bias table is constant (per head and side) for |key - query| >= bias_const_from (T5: relative_attention_max_distance);
 // <= 0 or >= S: no such guarantee, every tile reads the table.
-template <bool HAS_BIAS, int POLY, bool ROUND>
-inline cudaError_t launch_attn_tc2_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
-    auto kernel = attn_tc_d64_kernel<HAS_BIAS, POLY, ROUND>;
-    static std::atomic<size_t> max_set[64];   // per device: largest dynamic smem size opted into so far
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (smem > max_set[dev & 63].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        max_set[dev & 63].store(smem, std::memory_order_release);
-    }
-    dim3 grid(1, p.H, B);   // one CTA per (sample, head); it loops over the query tiles
-    kernel<<<grid, 192, smem, stream>>>(tm, p);
-    return cudaGetLastError();
-}
-
 template <bool HAS_BIAS, bool ROUND>
 inline cudaError_t launch_attn_stream_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
     auto kernel = attn_tc_d64_stream_kernel<HAS_BIAS, ROUND>;
@@ -1361,16 +984,14 @@ inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Param
 // round_scores: reproduce the bf16 tensors of the reference's eager attention (scores, scores + bias) before the fp32 softmax.
 inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, int k_col0, int v_col0, __nv_bfloat16* o, int ldo,
                                   int B, int S, int H, const int* seq_lens, const float* bias_table, float scale, int bias_const_from,
-                                  bool round_scores, cudaStream_t stream_, unsigned long long* prof = nullptr) {
+                                  bool round_scores, cudaStream_t stream_) {
     CUtensorMap tm;
     if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)B * S, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
+    // A/B switch (tools/bench_kernels.py): 30 / 31 = streaming stage without / with the score rounding, 40 / 41 = split-row stage
     static const int variant = [] { const char* v = getenv("VQA_ATTN_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();
-    if (variant == 20 || variant == 30) round_scores = false;      // A/B: without the score rounding
-    if (variant == 21 || variant == 31) round_scores = true;
-    const int stage = variant >= 40 ? 2 : (variant >= 30 ? 1 : (variant >= 20 ? 0 : ATTN_STAGE_DEFAULT));   // 0 two-pass, 1 streaming, 2 split-row streaming
-    if (variant == 40) round_scores = false;
-    if (variant == 41) round_scores = true;
-    const bool stream = stage == 1;
+    if (variant == 30 || variant == 40) round_scores = false;
+    if (variant == 31 || variant == 41) round_scores = true;
+    const int stage = variant >= 40 ? 2 : (variant >= 30 ? 1 : ATTN_STAGE_DEFAULT);
     AttnTc2Params p;
     p.o = o; p.ldo = ldo; p.seq_lens = seq_lens; p.bias_table = bias_table; p.S = S; p.H = H;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -1380,27 +1001,14 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
     int near = n_tiles;                                  // every tile reads the table
     if (bias_table && bias_const_from > 0 && bias_const_from < S) near = min(n_tiles, (bias_const_from - 1 + 127) / 128);
     p.near_tiles = bias_table ? near : 0;
-    p.prof = prof;
     const size_t smem = attn_tc2_smem_bytes(p.near_tiles, bias_table != nullptr, round_scores);
-    if (prof) {   // instrumented build of the T5 variant (bias + rounding) only
-        if (!bias_table || !round_scores) return cudaErrorInvalidValue;
-        auto kernel = attn_tc_d64_kernel<true, 0, true, true>;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kernel<<<dim3(1, H, B), 192, smem, stream_>>>(tm, p);
-        return cudaGetLastError();
-    }
     if (stage == 2) {
         const size_t smem4 = smem + 2048 + 64 + 128;  // + the row-pair exchange buffers / barriers and the wider per-warp reduction scratch
         if (bias_table) return round_scores ? launch_attn_split_t<true, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<true, false>(tm, p, B, smem4, stream_);
         return round_scores ? launch_attn_split_t<false, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<false, false>(tm, p, B, smem4, stream_);
     }
-    if (stream) {
-        if (bias_table) return round_scores ? launch_attn_stream_t<true, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<true, false>(tm, p, B, smem, stream_);
-        return round_scores ? launch_attn_stream_t<false, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<false, false>(tm, p, B, smem, stream_);
-    }
-    if (bias_table) return round_scores ? launch_attn_tc2_t<true, 0, true>(tm, p, B, smem, stream_) : launch_attn_tc2_t<true, 0, false>(tm, p, B, smem, stream_);
-    return round_scores ? launch_attn_tc2_t<false, 0, true>(tm, p, B, smem, stream_) : launch_attn_tc2_t<false, 0, false>(tm, p, B, smem, stream_);
+    if (bias_table) return round_scores ? launch_attn_stream_t<true, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<true, false>(tm, p, B, smem, stream_);
+    return round_scores ? launch_attn_stream_t<false, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<false, false>(tm, p, B, smem, stream_);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

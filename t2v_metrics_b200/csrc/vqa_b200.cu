@@ -1166,19 +1166,6 @@ extern "C" int vqa_op_attention_d64(const void* qkv, void* out, int32_t B, int32
     return VQA_OK;
 }
 
-// Instrumented run of the T5-encoder attention kernel (bias table + score rounding): `counters` = DEVICE uint64[9], zeroed by the caller;
-// after the stream has passed: cycles summed over one softmax warp per CTA in {wait S, TMEM load, max + vote, wait O / rescale, exp2 + P store,
-// store wait + arrive, epilogue, total}, and [8] = key tiles those warps processed.
-extern "C" int vqa_debug_attention_d64_phases(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, const int32_t* seq_lens,
-                                              const float* bias_table, int32_t bias_const_from, uint64_t* counters, void* stream) {
-    if (!qkv || !out || !bias_table || !counters || B <= 0 || S <= 0 || H <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
-    const bf16* q = (const bf16*)qkv;
-    cudaError_t e = launch_attn_tc(q, 3 * H * 64, 0, H * 64, 2 * H * 64, (bf16*)out, H * 64, B, S, H, seq_lens, bias_table, 1.0f, bias_const_from,
-                                   true, (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(counters));
-    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention (phases) launch: ") + cudaGetErrorString(e));
-    return VQA_OK;
-}
-
 extern "C" int vqa_op_attention_d128(const void* qkv, int32_t ld, int64_t rows, int32_t q_col0, int32_t k_col0, int32_t v_col0,
                                      void* out, int32_t ldo, int32_t n_seq, int32_t max_len, int32_t S, int32_t q_heads, int32_t kv_group,
                                      const int32_t* cu_seqlens, const int32_t* seq_lens, float scale, int32_t causal, void* stream) {

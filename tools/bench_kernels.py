@@ -58,26 +58,6 @@ def _t5_attn_inputs(B=64, S=672, H=64):
     return qkv, table
 
 
-def attn_phases():
-    """clock64() phase table of the T5-encoder attention kernel (instrumented build, one softmax warp per CTA reports)."""
-    import ctypes as C
-    from t2v_metrics_b200 import _lib
-    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
-    lib = _lib.load()
-    B, S, H = 64, 672, 64
-    qkv, table = _t5_attn_inputs(B, S, H)
-    out = torch.empty(B * S, H * 64, dtype=torch.bfloat16, device="cuda")
-    cnt = torch.zeros(9, dtype=torch.int64, device="cuda")
-    for _ in range(2):
-        cnt.zero_()
-        _check(lib.vqa_debug_attention_d64_phases(_ptr(qkv), _ptr(out), B, S, H, None, _ptr(table), 128, _ptr(cnt), _stream_ptr(qkv.device)), None, "phases")
-        torch.cuda.synchronize()
-    c = cnt.tolist()
-    names = ["wait_S", "tmem_load", "max+vote", "wait_O/rescale", "exp2+P_store", "st_wait+arrive", "epilogue", "total"]
-    tiles = max(c[8], 1)
-    print(json.dumps(dict(tiles=c[8], cycles_per_key_tile={n: round(v / tiles, 1) for n, v in zip(names, c[:8])})))
-
-
 def attn_one():
     """one launch of the production attention kernel at the T5-encoder shape (target of `ncu --set full`)."""
     from t2v_metrics_b200.engine import ops
@@ -167,8 +147,6 @@ if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "attn":
         attn()
-    elif cmd == "attn-phases":
-        attn_phases()
     elif cmd == "attn-one":
         attn_one()
     elif cmd == "attn128":
