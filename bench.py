@@ -645,6 +645,11 @@ def run_engine_qwen(args, rank, local_rank, world):
             s = gather_scores(s, total)
         return s.cpu()
 
+    if args.ncu:
+        for _ in range(2):
+            step_device()
+        torch.cuda.synchronize(dev)
+        return
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     sync_all()
