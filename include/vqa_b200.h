@@ -312,6 +312,17 @@ int vqa_op_attention_d128(const void* qkv, int32_t ld, int64_t rows, int32_t q_c
                           int32_t ldo, int32_t n_seq, int32_t max_len, int32_t S, int32_t q_heads, int32_t kv_group,
                           const int32_t* cu_seqlens, const int32_t* seq_lens, float scale, int32_t causal, void* stream);
 
+/* vqa_op_attention_d128 in variable-length mode with its extras: kv_prefix [n_seq] (or NULL): sequence b also attends to all rows of sequence
+ * kv_prefix[b] >= 0, placed in front of its own keys; pair_sequences: two consecutive sequences (each <= 64 rows) share one 128-row tile under a
+ * block-diagonal mask (non-causal only); output head h is written at column h * o_head_stride, first d_out (multiple of 8) head dims only. */
+int vqa_op_attention_d128_ex(const void* qkv, int32_t ld, int64_t rows, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out, int32_t ldo,
+                             int32_t n_seq, int32_t max_len, int32_t q_heads, int32_t kv_group, const int32_t* cu_seqlens, const int32_t* kv_prefix,
+                             float scale, int32_t causal, int32_t pair_sequences, int32_t o_head_stride, int32_t d_out, void* stream);
+
+/* vqa_op_gemm_bf16 with the plain store epilogue, output columns written in groups: logical column c -> (c / group_in) * group_out + c % group_in. */
+int vqa_op_gemm_bf16_grouped(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M, int32_t N,
+                             int32_t K, const void* bias, int32_t group_in, int32_t group_out, int32_t variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

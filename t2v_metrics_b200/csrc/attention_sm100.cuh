@@ -1023,6 +1023,11 @@ struct AttnTc128Params {
     int q_col0, k_col0, v_col0;
     int kv_group;              // query heads per key/value head (GQA); 1 for MHA
     float scale_log2e;
+    int o_head_stride, d_out;  // output column of head h = h * o_head_stride; only the first d_out (multiple of 8) of the 128 head dims are written
+                               // (heads stored zero-padded to 128 in qkv produce d_out real output columns: the projection then contracts over them only)
+    int pair, n_seq;           // varlen mode, pair != 0: CTA z covers the two consecutive sequences 2z and 2z+1 (each <= 64 rows) as ONE 128-row
+                               // tile with a block-diagonal mask -- the 64-token windows of the Qwen2.5-VL vision tower (modeling_qwen2_5_vl.py
+                               // get_window_index: 112-px windows = 8x8 patches) otherwise fill half of a tile and double the CTA count
     const int* kv_prefix;      // varlen mode, [n_seq] or nullptr: sequence b additionally attends to ALL rows of sequence kv_prefix[b] (>= 0),
                                // placed in front of its own keys -- the shared [system + vision] prefix of several prompts over one image
                                // (SURVEY 8(f)1): its K/V rows are computed once and read by every prompt's suffix
@@ -1041,8 +1046,13 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / p.kv_group;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    int row_base, len, write_rows;
-    if (p.cu_seqlens) {
+    int row_base, len, write_rows, mid = 0;
+    if (p.cu_seqlens && p.pair) {
+        row_base = p.cu_seqlens[2 * b];
+        mid = p.cu_seqlens[2 * b + 1] - row_base;                       // rows [0, mid): first sequence, [mid, len): second (absent for an odd tail)
+        len = p.cu_seqlens[min(2 * b + 2, p.n_seq)] - row_base;
+        write_rows = len;
+    } else if (p.cu_seqlens) {
         row_base = p.cu_seqlens[b];
         len = p.cu_seqlens[b + 1] - row_base;
         write_rows = len;                       // rows past the sequence belong to the next one
@@ -1057,7 +1067,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
         for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
             const int r = i >> 4, c = i & 15;
             if (q0 + r < write_rows)
-                *reinterpret_cast<uint4*>(p.o + (size_t)(row_base + q0 + r) * p.ldo + h * 128 + c * 8) = make_uint4(0, 0, 0, 0);
+                if (c * 8 < p.d_out) *reinterpret_cast<uint4*>(p.o + (size_t)(row_base + q0 + r) * p.ldo + h * p.o_head_stride + c * 8) = make_uint4(0, 0, 0, 0);
         }
         return;
     }
@@ -1179,7 +1189,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
                 if (lane == 0) mbar_arrive(s_empty);
 
                 const bool diag = CAUSAL && !in_prefix && (j - nA) == qt;
-                const bool edge = (k0 + 128 > klen) || diag;
+                const bool edge = (k0 + 128 > klen) || diag || p.pair;
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -1187,7 +1197,7 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int kcol = k0 + c * 32 + i;
-                            if (kcol >= klen || (diag && kcol > qrow)) sv[c][i] = 0xff800000u;
+                            if (kcol >= klen || (diag && kcol > qrow) || (p.pair && ((kcol < mid) != (qrow < mid)))) sv[c][i] = 0xff800000u;
                         }
                     }
 #pragma unroll
@@ -1251,15 +1261,17 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
         mbar_wait(o_done, (uint32_t)(nkt - 1) & 1u);
         tcgen05_fence_after();
         const float inv = (qrow < len && l_run > 0.f) ? 1.f / l_run : 0.f;
-        __nv_bfloat16* orow = p.o + (size_t)(row_base + qrow) * p.ldo + h * 128;
+        __nv_bfloat16* orow = p.o + (size_t)(row_base + qrow) * p.ldo + h * p.o_head_stride;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (c * 32 >= p.d_out) break;
             uint32_t ov[32];
             tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
             tmem_ld_wait();
             if (qrow < write_rows) {
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
+                    if (c * 32 + gq * 8 >= p.d_out) break;
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -1279,11 +1291,15 @@ attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc12
 inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long rows, int q_col0, int k_col0, int v_col0,
                                      __nv_bfloat16* o, int ldo, int n_seq, int max_len, int S, int Hq, int kv_group,
                                      const int* cu_seqlens, const int* seq_lens, float scale, bool causal, cudaStream_t stream,
-                                     const int* kv_prefix = nullptr) {
+                                     const int* kv_prefix = nullptr, bool pair_sequences = false, int o_head_stride = 128, int d_out = 128) {
     CUtensorMap tm;
     if (!tmap_bf16_2d_cached(&tm, qkv, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, 128)) return cudaErrorInvalidValue;
     if (kv_prefix && !cu_seqlens) return cudaErrorInvalidValue;
+    if (pair_sequences && (!cu_seqlens || causal || kv_prefix || max_len > 64)) return cudaErrorInvalidValue;
     AttnTc128Params p;
+    if (d_out < 8 || d_out > 128 || (d_out & 7) || (o_head_stride & 7)) return cudaErrorInvalidValue;
+    p.pair = pair_sequences ? 1 : 0; p.n_seq = n_seq;
+    p.o_head_stride = o_head_stride; p.d_out = d_out;
     p.o = o; p.ldo = ldo; p.cu_seqlens = cu_seqlens; p.seq_lens = seq_lens; p.S = S;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.kv_group = kv_group;
     p.scale_log2e = scale * 1.4426950408889634f;
@@ -1291,7 +1307,7 @@ inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long
     const size_t smem = attn_tc128_smem_bytes();
     static const int variant = [] { const char* v = getenv("VQA_ATTN128_VARIANT"); return (v && v[0]) ? atoi(v) : -1; }();   // 10 / 12: POLY 0 / 2
     const int poly = variant >= 10 ? variant - 10 : ATTN128_POLY_DEFAULT;
-    dim3 grid((max_len + 127) / 128, Hq, n_seq);
+    dim3 grid(pair_sequences ? 1 : (max_len + 127) / 128, Hq, pair_sequences ? (n_seq + 1) / 2 : n_seq);
     auto go = [&](auto kernel, PerDeviceOnce& once) -> cudaError_t {
         cudaError_t e = once.ensure([&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         if (e != cudaSuccess) return e;

@@ -54,6 +54,9 @@ struct GemmParams {
     int c_f32;                // EPI_STORE only: C and residual are fp32 buffers (ldc / ldr in floats): C = residual + bf16(acc + bias), unrounded
                               // (the CLIP tower's residual stream stays fp32 under the reference's autocast: LayerNorm is on autocast's fp32 list)
     int gate_up_offset;       // GATED: row offset of the "up" weight block inside W (= d_ff)
+    int c_group_in, c_group_out;   // EPI_STORE without residual, c_group_in > 0: logical output column c is stored at column
+                              // (c / c_group_in) * c_group_out + c % c_group_in -- heads narrower than the attention kernel's 128-wide slots
+                              // (Qwen2.5-VL vision tower, 80-wide) are produced at their native width and written into the slots; both multiples of 8
     // EPI_LSE
     float* lse_max;           // [M, num_n_tiles]
     float* lse_sum;           // [M, num_n_tiles]
@@ -492,7 +495,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                 }
                                 uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                                *reinterpret_cast<uint4*>(crow + j * 8) = o;
+                                __nv_bfloat16* dst = crow + j * 8;
+                                if (p.c_group_in > 0) {
+                                    const int cc = nc + j * 8;
+                                    dst = p.C + c_off + (size_t)m * p.ldc + (cc / p.c_group_in) * p.c_group_out + cc % p.c_group_in;
+                                }
+                                *reinterpret_cast<uint4*>(dst) = o;
                                 if (p.ssq_out) {
                                     const float2 s0 = unpack_bf16x2(o.x), s1 = unpack_bf16x2(o.y), s2 = unpack_bf16x2(o.z), s3 = unpack_bf16x2(o.w);
                                     ssq_acc += (s0.x * s0.x + s0.y * s0.y) + (s1.x * s1.x + s1.y * s1.y) + (s2.x * s2.x + s2.y * s2.y) +

@@ -40,7 +40,7 @@ static QwenWorkspace qwen_plan_rows(const vqa_qwen25vl_config& c, int B, size_t 
     w.vx = pl.take(L * Dv * 2);
     w.vxn = pl.take(L * Dv * 2);
     w.vqkv = pl.take(L * 3 * Hv * 128 * 2);
-    w.vattn = pl.take(L * Hv * 128 * 2);
+    w.vattn = pl.take(L * Hv * 128 * 2);      // used as [L, Hv * head_dim] (compact heads)
     w.vff = pl.take(L * mlp_pad * 2);
     w.vmerge_in = pl.take(L * Dv * 2);
     w.vfc1 = pl.take(L / unit * (Dv * unit) * 2);
@@ -92,8 +92,10 @@ static int qwen_finalize(vqa_handle* h, QwenState& q) {
         const std::string p = "vis." + std::to_string(i) + ".";
         QwenVisLayerW& L = q.vis[i];
         L.norm1 = need(h, p + "norm1", Dv, 1, ok); L.norm2 = need(h, p + "norm2", Dv, 1, ok);
-        L.qkv_w = need(h, p + "qkv.weight", 3 * Hv * 128, Dv, ok); L.qkv_b = need(h, p + "qkv.bias", 3 * Hv * 128, 1, ok);
-        L.proj_w = need(h, p + "proj.weight", Dv, Hv * 128, ok); L.proj_b = need(h, p + "proj.bias", Dv, 1, ok);
+        // native head width (80 for Qwen2.5-VL): the HF qkv weight is already ordered (q|k|v, head, dim); the GEMM epilogue scatters each head's
+        // columns into the 128-wide slots the attention kernel reads, the attention writes compact heads, proj contracts over Hv * head_dim
+        L.qkv_w = need(h, p + "qkv.weight", 3 * Hv * c.vit_head_dim, Dv, ok); L.qkv_b = need(h, p + "qkv.bias", 3 * Hv * c.vit_head_dim, 1, ok);
+        L.proj_w = need(h, p + "proj.weight", Dv, Hv * c.vit_head_dim, ok); L.proj_b = need(h, p + "proj.bias", Dv, 1, ok);
         L.gu_w = need(h, p + "gate_up.weight", 2 * mlp_pad, Dv, ok); L.gu_b = need(h, p + "gate_up.bias", 2 * mlp_pad, 1, ok);
         L.down_w = need(h, p + "down.weight", Dv, mlp_pad, ok); L.down_b = need(h, p + "down.bias", Dv, 1, ok);
     }
@@ -180,13 +182,22 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
         ++*lc;
         gather_rows_kernel<<<L, 128, 0, st>>>(P_(w.vxn), P_(w.vx), window_index, unit, Dv);
         TRY(cuda_ok(cudaSuccess, "window reorder"));
+        if (hdv < 128) {   // the qkv GEMMs write head_dim of every 128-wide head slot; the attention kernel contracts q.k over all 128: zero the rest once
+            ++*lc;
+            CUDA_TRY(h, cudaMemsetAsync(P_(w.vqkv), 0, (size_t)L * 3 * Hv * 128 * 2, st));
+        }
     }
     const float vscale = 1.0f / sqrtf((float)hdv);
     for (int l = 0; l < c.vit_depth; ++l) {
         const QwenVisLayerW& Lw = q.vis[l];
         const bool full = (c.fullatt_mask >> l) & 1ull;
         TRY(rms(P_(w.vx), Lw.norm1, P_(w.vxn), L, Dv));
-        TRY(gemm(P_(w.vxn), Dv, Lw.qkv_w, Dv, 3 * Hv * 128, P_(w.vqkv), 3 * Hv * 128, L, 3 * Hv * 128, Dv, Lw.qkv_b, nullptr, 0, EPI_STORE, 0));
+        {
+            const double nq = 3.0 * Hv * hdv;
+            ProfScope ps(h, CAT_GEMM, 2.0 * L * nq * Dv, st, 2.0 * ((double)L * Dv + nq * Dv + (double)L * nq));
+            TRY(cuda_ok(run_gemm(P_(w.vxn), Dv, Lw.qkv_w, Dv, 3 * Hv * hdv, P_(w.vqkv), 3 * Hv * 128, L, 3 * Hv * hdv, Dv, Lw.qkv_b, nullptr, 0, EPI_STORE,
+                                 0, 0, nsm, st, lc, false, nullptr, hdv < 128 ? hdv : 0, 128), "vision qkv gemm"));
+        }
         {
             ProfScope ps(h, CAT_OTHER, 0, st);
             ++*lc;
@@ -199,10 +210,13 @@ static int qwen_score(vqa_handle* h, QwenState& q, const void* pixel_patches, in
             const int nseq = full ? n_frames : n_windows, mlen = full ? max_frame_len : max_window_len;
             ProfScope ps(h, CAT_ATTENTION, 4.0 * (double)L * mlen * Hv * hdv, st);
             ++*lc;
-            TRY(cuda_ok(launch_attn_tc128(P_(w.vqkv), 3 * Hv * 128, L, 0, Hv * 128, 2 * Hv * 128, P_(w.vattn), Hv * 128, nseq, mlen, 0, Hv, 1,
-                                          full ? cu_frames : cu_window, nullptr, vscale, false, st), "vision attention"));
+            static const bool no_pairs = getenv("VQA_ATTN128_NO_PAIRS") != nullptr;     // A/B switch
+            TRY(cuda_ok(launch_attn_tc128(P_(w.vqkv), 3 * Hv * 128, L, 0, Hv * 128, 2 * Hv * 128, P_(w.vattn), Hv * hdv, nseq, mlen, 0, Hv, 1,
+                                          full ? cu_frames : cu_window, nullptr, vscale, false, st, nullptr,
+                                          /*two windows per tile*/ !full && max_window_len <= 64 && !no_pairs, /*compact heads*/ hdv, hdv),
+                        "vision attention"));
         }
-        TRY(gemm(P_(w.vattn), Hv * 128, Lw.proj_w, Hv * 128, Dv, P_(w.vx), Dv, L, Dv, Hv * 128, Lw.proj_b, P_(w.vx), Dv, EPI_STORE, 0));
+        TRY(gemm(P_(w.vattn), Hv * hdv, Lw.proj_w, Hv * hdv, Dv, P_(w.vx), Dv, L, Dv, Hv * hdv, Lw.proj_b, P_(w.vx), Dv, EPI_STORE, 0));
         TRY(rms(P_(w.vx), Lw.norm2, P_(w.vxn), L, Dv));
         TRY(gemm(P_(w.vxn), Dv, Lw.gu_w, Dv, 2 * mlp_pad, P_(w.vff), mlp_pad, L, 2 * mlp_pad, Dv, Lw.gu_b, nullptr, 0, EPI_GATED_SILU, mlp_pad));
         TRY(gemm(P_(w.vff), mlp_pad, Lw.down_w, mlp_pad, Dv, P_(w.vx), Dv, L, Dv, mlp_pad, Lw.down_b, P_(w.vx), Dv, EPI_STORE, 0));

@@ -196,7 +196,7 @@ struct NormFuse {            // fused RMSNorm hooks of one GEMM launch (see Gemm
 static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M, int N,
                             int K, const bf16* bias, const bf16* residual, int ldr, int epi, int gate_up_offset,
                             int variant, int num_sms, cudaStream_t st, int64_t* launch_counter, bool c_f32 = false,
-                            const NormFuse* nf = nullptr) {
+                            const NormFuse* nf = nullptr, int c_group_in = 0, int c_group_out = 0) {
     GemmLaunch g;
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = w_rows;
     memset(&g.p, 0, sizeof(g.p));
@@ -204,6 +204,11 @@ static cudaError_t run_gemm(const bf16* A, int lda, const bf16* W, int ldw, int 
     g.p.ldr = ldr; g.p.gate_up_offset = gate_up_offset;
     if (c_f32 && epi != EPI_STORE) return cudaErrorInvalidValue;
     g.p.c_f32 = c_f32 ? 1 : 0;
+    if (c_group_in > 0) {   // narrow output column groups written into wider slots (GemmParams::c_group_in)
+        if (epi != EPI_STORE || residual || c_f32 || (c_group_in & 7) || (c_group_out & 7) || c_group_out < c_group_in || N % c_group_in)
+            return cudaErrorInvalidValue;
+        g.p.c_group_in = c_group_in; g.p.c_group_out = c_group_out;
+    }
     if (nf) {
         g.p.ssq_out = nf->ssq_out; g.p.ssq_in = nf->ssq_in; g.p.ssq_out_parts = g.p.ssq_in_parts = nf->stride;
         g.p.ssq_inv_dim = nf->inv_dim; g.p.ssq_eps = nf->eps;
@@ -1115,6 +1120,18 @@ extern "C" int vqa_op_gemm_bf16(const void* A, int32_t lda, const void* W, int32
     return VQA_OK;
 }
 
+// vqa_op_gemm_bf16 (plain store epilogue) whose output columns are written in groups: logical column c lands at (c / group_in) * group_out + c % group_in
+// (heads narrower than the attention kernel's 128-wide slots are produced at their native width; the caller zeroes the slot padding).
+extern "C" int vqa_op_gemm_bf16_grouped(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M,
+                                        int32_t N, int32_t K, const void* bias, int32_t group_in, int32_t group_out, int32_t variant, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || group_in <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad gemm argument");
+    if (lda % 8 || ldw % 8 || ldc % 8 || N % 8 || K % 8) return fail(nullptr, VQA_ERR_INVALID_ARG, "gemm: ld/N/K must be multiples of 8");
+    cudaError_t e = run_gemm((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, (const bf16*)bias, nullptr, 0, EPI_STORE, 0, variant,
+                             device_sms(), (cudaStream_t)stream, nullptr, false, nullptr, group_in, group_out);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
 // vqa_op_gemm_bf16 with the fused-RMSNorm hooks (GemmParams::ssq_*): ssq_in [M, stride] partial sums of squares of the rows of A (the
 // epilogue scales accumulator row m by rsqrt(sum / norm_dim + eps)), ssq_out [M, stride] receives this GEMM's partial sums of squares of the
 // rows it stores (epilogue 0 only); either may be NULL. *parts_out (HOST, optional) = number of slots of ssq_out this launch writes.
@@ -1172,6 +1189,19 @@ extern "C" int vqa_op_attention_d128(const void* qkv, int32_t ld, int64_t rows, 
     if (!qkv || !out || n_seq <= 0 || max_len <= 0 || q_heads <= 0 || kv_group <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
     cudaError_t e = launch_attn_tc128((const bf16*)qkv, ld, rows, q_col0, k_col0, v_col0, (bf16*)out, ldo, n_seq, max_len, S, q_heads, kv_group,
                                       cu_seqlens, seq_lens, scale, causal != 0, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention d128 launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// The same kernel with its variable-length extras: a shared key/value prefix per sequence, two short sequences per 128-row tile, compact output heads.
+extern "C" int vqa_op_attention_d128_ex(const void* qkv, int32_t ld, int64_t rows, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                                        void* out, int32_t ldo, int32_t n_seq, int32_t max_len, int32_t q_heads, int32_t kv_group,
+                                        const int32_t* cu_seqlens, const int32_t* kv_prefix, float scale, int32_t causal,
+                                        int32_t pair_sequences, int32_t o_head_stride, int32_t d_out, void* stream) {
+    if (!qkv || !out || !cu_seqlens || n_seq <= 0 || max_len <= 0 || q_heads <= 0 || kv_group <= 0)
+        return fail(nullptr, VQA_ERR_INVALID_ARG, "bad attention argument");
+    cudaError_t e = launch_attn_tc128((const bf16*)qkv, ld, rows, q_col0, k_col0, v_col0, (bf16*)out, ldo, n_seq, max_len, 0, q_heads, kv_group,
+                                      cu_seqlens, nullptr, scale, causal != 0, (cudaStream_t)stream, kv_prefix, pair_sequences != 0, o_head_stride, d_out);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("attention d128 launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -510,8 +510,9 @@ def qwen_preprocess_u8(images: Sequence[torch.Tensor], device, patch: int = 14, 
 # ================================================================================================ Qwen2.5-VL
 def convert_qwen_state_dict(sd: Dict[str, torch.Tensor], cfg, device) -> Dict[str, torch.Tensor]:
     """HF `Qwen2_5_VLForConditionalGeneration` names -> the engine's fused bf16 layout:
-      * vision qkv: rows regrouped per (q|k|v, head) and every 80-wide head zero-padded to 128 rows, so the packed activation
-        is [L, 3*H*128]; the attention output projection gets matching zero columns;
+      * vision qkv / proj: the HF tensors as they are ([3*H*hd, Dv] rows ordered (q|k|v, head, dim); [Dv, H*hd]). The qkv GEMM's epilogue
+        scatters each 80-wide head into the 128-wide slots of the packed activation [L, 3*H*128] the attention kernel reads (pad columns
+        zeroed once per forward), the attention kernel writes compact heads [L, H*hd];
       * vision gate|up rows concatenated with the MLP width zero-padded to a multiple of 128; down-projection columns padded;
       * language-model q|k|v rows concatenated (+ biases), gate|up rows concatenated."""
     out: Dict[str, torch.Tensor] = {}
@@ -526,14 +527,9 @@ def convert_qwen_state_dict(sd: Dict[str, torch.Tensor], cfg, device) -> Dict[st
     for l in range(cfg.vit_depth):
         p, q = v + f"blocks.{l}.", f"vis.{l}."
         put(q + "norm1", sd[p + "norm1.weight"]); put(q + "norm2", sd[p + "norm2.weight"])
-        w = sd[p + "attn.qkv.weight"].float().reshape(3, H, hd, Dv)
-        b = sd[p + "attn.qkv.bias"].float().reshape(3, H, hd)
-        wp = torch.zeros(3, H, 128, Dv); wp[:, :, :hd] = w
-        bp = torch.zeros(3, H, 128); bp[:, :, :hd] = b
-        put(q + "qkv.weight", wp.reshape(3 * H * 128, Dv)); put(q + "qkv.bias", bp.reshape(-1))
-        pw = sd[p + "attn.proj.weight"].float().reshape(Dv, H, hd)
-        pwp = torch.zeros(Dv, H, 128); pwp[:, :, :hd] = pw
-        put(q + "proj.weight", pwp.reshape(Dv, H * 128)); put(q + "proj.bias", sd[p + "attn.proj.bias"])
+        # HF's fused qkv rows are already ordered (q|k|v, head, dim) and proj's columns (head, dim): bound as they are, at the native head width
+        put(q + "qkv.weight", sd[p + "attn.qkv.weight"]); put(q + "qkv.bias", sd[p + "attn.qkv.bias"])
+        put(q + "proj.weight", sd[p + "attn.proj.weight"]); put(q + "proj.bias", sd[p + "attn.proj.bias"])
         gu = torch.zeros(2 * mp, Dv); gb = torch.zeros(2 * mp)
         gu[: cfg.vit_mlp] = sd[p + "mlp.gate_proj.weight"].float(); gu[mp: mp + cfg.vit_mlp] = sd[p + "mlp.up_proj.weight"].float()
         gb[: cfg.vit_mlp] = sd[p + "mlp.gate_proj.bias"].float(); gb[mp: mp + cfg.vit_mlp] = sd[p + "mlp.up_proj.bias"].float()

@@ -121,11 +121,8 @@ def synthetic_qwen_engine_weights(cfg, device, seed: int = 0) -> Dict[str, torch
     for l in range(cfg.vit_depth):
         q = f"vis.{l}."
         out[q + "norm1"] = gain(Dv); out[q + "norm2"] = gain(Dv)
-        w = torch.zeros(3, H, 128, Dv, device=device, dtype=torch.bfloat16); w[:, :, :hd] = nrm(3, H, hd, Dv, std=Dv ** -0.5)
-        b = torch.zeros(3, H, 128, device=device, dtype=torch.bfloat16); b[:, :, :hd] = nrm(3, H, hd)
-        out[q + "qkv.weight"] = w.reshape(3 * H * 128, Dv).contiguous(); out[q + "qkv.bias"] = b.reshape(-1).contiguous()
-        pw = torch.zeros(Dv, H, 128, device=device, dtype=torch.bfloat16); pw[:, :, :hd] = nrm(Dv, H, hd, std=Dv ** -0.5)
-        out[q + "proj.weight"] = pw.reshape(Dv, H * 128).contiguous(); out[q + "proj.bias"] = nrm(Dv)
+        out[q + "qkv.weight"] = nrm(3 * H * hd, Dv, std=Dv ** -0.5); out[q + "qkv.bias"] = nrm(3 * H * hd)
+        out[q + "proj.weight"] = nrm(Dv, H * hd, std=Dv ** -0.5); out[q + "proj.bias"] = nrm(Dv)
         gu = torch.zeros(2 * mp, Dv, device=device, dtype=torch.bfloat16)
         gu[:mlp_v] = nrm(mlp_v, Dv, std=Dv ** -0.5); gu[mp:mp + mlp_v] = nrm(mlp_v, Dv, std=Dv ** -0.5)
         gb = torch.zeros(2 * mp, device=device, dtype=torch.bfloat16); gb[:mlp_v] = nrm(mlp_v); gb[mp:mp + mlp_v] = nrm(mlp_v)

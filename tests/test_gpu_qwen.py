@@ -31,6 +31,62 @@ def attn_d128(qkv, out_cols, n_seq, max_len, S, Hq, group, cu, lens, scale, caus
     return out
 
 
+@pytest.mark.parametrize("lens", [[64] * 6, [64, 64, 40, 64, 17], [8, 64, 64], [33]])
+def test_window_pairs_and_compact_heads_d128(dev, lens):
+    """Vision-tower windows (<= 64 tokens, modeling_qwen2_5_vl.py get_window_index) two per 128-row tile under a block-diagonal mask, output
+    heads written compactly at their native width (80): must equal the one-window-per-tile launch and the fp32 reference."""
+    import ctypes as C
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    torch.manual_seed(5)
+    H, hd = 3, 80
+    L = sum(lens)
+    x = torch.zeros(L, 3, H, 128, device=dev)
+    x[..., :hd] = torch.randn(L, 3, H, hd, device=dev) * 0.7
+    x[:, 2, :, hd:] = 7.0                                   # V padding need not be zero: those output columns are never written
+    qkv = x.reshape(L, 3 * H * 128).bfloat16()
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+    outs = []
+    for pair in (0, 1):
+        out = torch.full((L, H * hd), 3.0, dtype=torch.bfloat16, device=dev)
+        rc = lib.vqa_op_attention_d128_ex(_ptr(qkv), qkv.shape[1], L, 0, H * 128, 2 * H * 128, _ptr(out), H * hd, len(lens), max(lens), H, 1, _ptr(cu),
+                                          None, float(hd ** -0.5), 0, pair, hd, hd, _stream_ptr(qkv.device))
+        _check(rc, None, "vqa_op_attention_d128_ex")
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    xf = qkv.float().view(L, 3, H, 128)[..., :hd]
+    ref = torch.zeros(L, H, hd, device=dev)
+    o = 0
+    for n in lens:
+        q, k, v = (xf[o:o + n, i].transpose(0, 1) for i in range(3))
+        ref[o:o + n] = (torch.softmax(q @ k.transpose(1, 2) * hd ** -0.5, -1) @ v).transpose(0, 1)
+        o += n
+    assert float((outs[0] - ref.reshape(L, H * hd)).abs().max()) < 0.02
+    assert float((outs[1] - ref.reshape(L, H * hd)).abs().max()) < 0.02
+    assert float((outs[1] - outs[0]).abs().max()) < 4e-3        # same keys, same tile: only masked columns differ
+
+
+def test_gemm_grouped_output_columns(dev):
+    """qkv GEMM at the native head width: logical column c -> (c / 80) * 128 + c % 80 (GemmParams::c_group_in); the slot padding is left untouched."""
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    torch.manual_seed(6)
+    M, K, G, gi, go = 700, 256, 9, 80, 128
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(G * gi, K, device=dev) * K ** -0.5).bfloat16()
+    b = torch.randn(G * gi, device=dev).bfloat16()
+    c = torch.full((M, G * go), -5.0, dtype=torch.bfloat16, device=dev)
+    _check(lib.vqa_op_gemm_bf16_grouped(_ptr(a), K, _ptr(w), K, G * gi, _ptr(c), G * go, M, G * gi, K, _ptr(b), gi, go, 0, _stream_ptr(a.device)),
+           None, "vqa_op_gemm_bf16_grouped")
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t() + b.float()).view(M, G, gi)
+    got = c.float().view(M, G, go)
+    assert float((got[..., :gi] - ref).abs().max()) < 0.03
+    assert bool((got[..., gi:] == -5.0).all())
+
+
 @pytest.mark.parametrize("B,S,Hq,Hkv", [(3, 320, 4, 2), (2, 130, 2, 1), (1, 64, 28, 4)])
 def test_causal_gqa_attention_d128(dev, B, S, Hq, Hkv):
     torch.manual_seed(0)
