@@ -115,6 +115,38 @@ def test_attention_matches_torch(ops, B, S, H, use_bias, ragged, scale):
     assert float(out[~qmask].float().abs().max()) == 0.0 if (~qmask).any() else True
 
 
+@pytest.mark.parametrize("use_bias", [True, False])
+def test_attention_edge_lengths_and_growing_maxima(ops, use_bias):
+    """Every boundary of the split-row softmax stage in one launch: lengths around the 32-key chunk, 64-key half and 128-key tile edges
+    (a half with no chunk to read, the chunk that straddles the length, query quadrants that are all padding, a single valid key), and
+    scores whose row maximum grows by far more than the lazy-rescale threshold (2^8) from one key tile to the next, so the deferred
+    rescale of O and l runs in every tile."""
+    torch.manual_seed(21)
+    lens_list = [1, 2, 31, 32, 33, 63, 64, 65, 96, 97, 127, 128, 129, 160, 161, 255, 256, 257, 290, 300]
+    B, S, H = len(lens_list), 300, 2
+    x = torch.randn(B, S, 3, H, 64, device="cuda") * 0.5
+    ramp = 1.0 + 0.9 * (torch.arange(S, device="cuda") // 64).float()           # later keys are longer vectors: maxima keep growing
+    x[:, :, 1] *= ramp[None, :, None, None]
+    x[:, :, 0] *= 2.0
+    qkv = x.reshape(B * S, 3 * H * 64).bfloat16()
+    lens = torch.tensor(lens_list, device="cuda", dtype=torch.int32)
+    table = (torch.randn(H, 2 * S - 1, device="cuda") * 0.5).bfloat16().float().contiguous() if use_bias else None
+    out = ops.attention(qkv, B, S, H, seq_lens=lens, bias_table=table, scale=1.0)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = torch.matmul(q, k.transpose(-1, -2))
+    if use_bias:
+        idx = (torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None]) + S - 1
+        sc = sc + table[:, idx][None]
+    kmask = torch.arange(S, device="cuda")[None, :] < lens[:, None]
+    sc = sc.masked_fill(~kmask[:, None, None, :], float("-inf"))
+    assert float((sc.amax(-1)[:, :, :, None] - sc[..., :128].amax(-1)[:, :, :, None]).max()) > 16.0      # the fixture does exercise the rescale
+    ref = torch.matmul(torch.softmax(sc, -1), v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    qmask = kmask.reshape(B * S)
+    err = (out[qmask].float() - ref[qmask]).abs()
+    assert float(err.max()) < 0.03, float(err.max())
+    assert float(out[~qmask].float().abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("S,dist,ragged", [(672, 128, False), (672, 128, True), (400, 40, True), (300, 299, False)])
 def test_attention_saturating_t5_bias(ops, S, dist, ragged):
     """T5 buckets saturate at relative_attention_max_distance: the bias is one value per head and side for |key - query| >= dist

@@ -255,3 +255,17 @@ def test_plugins_refuse_inputs_the_kernels_cannot_take():
         CLIPT5Model._tokenize(fake, [q], ["<image>"])
     with pytest.raises(NotImplementedError, match="max_new_tokens=1"):
         qm.Qwen2VLModel.forward(types.SimpleNamespace(), ["a.png"], ["a dog"], max_new_tokens=2)
+
+
+def test_small_calls_are_bucketed_for_cuda_graph_replay():
+    """Calls with <= cuda_graph_max_pairs pairs pad the id matrix to a multiple of 16 columns (few call shapes -> few captured graphs); the true
+    lengths stay in `lens` (the engine masks the padding), and larger calls keep the tight width."""
+    fake = types.SimpleNamespace(tokenizer=FakeTok(), context_len=2048, cfg=types.SimpleNamespace(vocab=32128, pad_token_id=0), cuda_graph_max_pairs=4)
+    qs = [format_question('Does this figure show "{}"? Please answer yes or no.'.format(t)) for t in ("a dog", "two cats on a mat", "x")]
+    ids, lens, labels = CLIPT5Model._tokenize(fake, qs, ["Yes"] * 3)
+    assert ids.shape[1] % 16 == 0 and ids.shape[1] - int(lens.max()) < 16
+    for i in range(3):
+        assert bool((ids[i, int(lens[i]):] == 0).all()) and int((ids[i] == -200).sum()) == 1
+    fake.cuda_graph_max_pairs = 2
+    ids2, lens2, _ = CLIPT5Model._tokenize(fake, qs, ["Yes"] * 3)
+    assert ids2.shape[1] == int(lens2.max()) and torch.equal(lens, lens2) and torch.equal(ids[:, : ids2.shape[1]], ids2)
