@@ -25,7 +25,12 @@ def vision_rot_pos_ids(grid_thw: Sequence[Sequence[int]], merge: int) -> torch.T
 
 
 def vision_window_index(grid_thw: Sequence[Sequence[int]], merge: int, window_size: int, patch_size: int):
-    """Returns (window_index [n_groups], cu_window_seqlens (patches, duplicates removed), cu_frame_seqlens)."""
+    """Returns (window_index [n_groups], cu_window_seqlens (patches, duplicates removed), cu_frame_seqlens).
+
+    This is a TRANSCRIPTION of `Qwen2_5_VisionTransformerPretrainedModel.get_window_index` (transformers 5.5.0
+    models/qwen2_5_vl/modeling_qwen2_5_vl.py:411-451) -- same `F.pad(..., -100)`, same reshape / permute chain -- because the index arrays
+    must match the installed transformers bit for bit (tested as such in tests/test_qwen_host.py); `vision_rot_pos_ids` above likewise
+    follows `rot_pos_emb` (:382-409). Third-party index logic, not reference code."""
     unit = merge * merge
     vw = window_size // merge // patch_size
     window_index, cu_win, base = [], [0], 0
