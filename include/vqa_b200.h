@@ -319,6 +319,12 @@ int vqa_op_attention_d128_ex(const void* qkv, int32_t ld, int64_t rows, int32_t 
                              int32_t n_seq, int32_t max_len, int32_t q_heads, int32_t kv_group, const int32_t* cu_seqlens, const int32_t* kv_prefix,
                              float scale, int32_t causal, int32_t pair_sequences, int32_t o_head_stride, int32_t d_out, void* stream);
 
+/* Skinny GEMM (M <= 128): K cut into `splits` slices that run as one launch, fp32 partial tiles in `workspace` (splits * M * N floats), then one
+ * reduction kernel: C = [residual +] bf16(A W^T + bias). splits == 0: the library picks (returned in *splits_out, may be 1). */
+int vqa_op_gemm_bf16_splitk(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M, int32_t N,
+                            int32_t K, const void* bias, const void* residual, int32_t ldr, int32_t splits, void* workspace,
+                            size_t workspace_bytes, int32_t* splits_out, void* stream);
+
 /* vqa_op_gemm_bf16 with the plain store epilogue, output columns written in groups: logical column c -> (c / group_in) * group_out + c % group_in. */
 int vqa_op_gemm_bf16_grouped(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M, int32_t N,
                              int32_t K, const void* bias, int32_t group_in, int32_t group_out, int32_t variant, void* stream);

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "vqa_clip_preprocess_workspace_bytes", "vqa_clip_preprocess", "vqa_resample_table", "vqa_qwen_preprocess_plan",
     "vqa_qwen_preprocess", "vqa_clipt5_debug_layout", "vqa_qwen25vl_debug_layout", "vqa_set_gemm_schedule",
     "vqa_qwen25vl_topk", "vqa_op_gemm_bf16_normfuse",
-    "vqa_qwen25vl_packed_workspace_bytes", "vqa_qwen25vl_score_packed", "vqa_debug_max_active_clusters", "vqa_op_attention_d128_ex", "vqa_op_gemm_bf16_grouped",
+    "vqa_qwen25vl_packed_workspace_bytes", "vqa_qwen25vl_score_packed", "vqa_debug_max_active_clusters", "vqa_op_attention_d128_ex", "vqa_op_gemm_bf16_grouped", "vqa_op_gemm_bf16_splitk",
 ]
 
 VQA_DTYPE_BF16, VQA_DTYPE_F32, VQA_DTYPE_I32 = 0, 1, 2
@@ -141,6 +141,8 @@ def load() -> C.CDLL:
     lib.vqa_op_attention_d128_ex.restype = C.c_int
     lib.vqa_op_gemm_bf16_grouped.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.vqa_op_gemm_bf16_grouped.restype = C.c_int
+    lib.vqa_op_gemm_bf16_splitk.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, C.c_size_t, C.POINTER(i32), vp]
+    lib.vqa_op_gemm_bf16_splitk.restype = C.c_int
     lib.vqa_debug_max_active_clusters.argtypes = [i32]
     lib.vqa_debug_max_active_clusters.restype = C.c_int
     lib.vqa_resample_table.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]

@@ -106,6 +106,7 @@ struct AttnTc2Params {
     const int* seq_lens; const float* bias_table;   // [H, 2S-1] fp32 (natural-log domain) or nullptr
     int S, H, q_col0, k_col0, v_col0;
     float scale_log2e;
+    int q_per_cta;      // split-row kernel: query tiles per CTA (grid.x CTAs per (sample, head)); the streaming kernel always takes all of them
     int near_tiles;     // key tiles with |kt - qt| <= near_tiles read the bias table; beyond, the table's end values (constant there)
     float scale;        // ROUND kernels: softmax scale applied after the bf16 rounding of the scores (1 for T5, 1/8 for CLIP)
 };
@@ -585,13 +586,18 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const size_t row_base = (size_t)b * p.S;
-    const int nq = (len + AT_BQ - 1) / AT_BQ;     // query tiles that contain at least one valid row
+    const int nq_all = (len + AT_BQ - 1) / AT_BQ; // query tiles that contain at least one valid row
     const int nkt = (len + AT_BK - 1) / AT_BK;    // key tiles that contain at least one valid key
+    // blockIdx.x > 0 only for small batches (launch_attn_tc: B * H CTAs would leave most SMs idle): this CTA owns q_per_cta consecutive query tiles
+    const int q_first = blockIdx.x * p.q_per_cta;
+    const int nq = max(0, min(p.q_per_cta, nq_all - q_first));
 
     // rows past the last valid query tile: deterministic zeros
-    for (int i = threadIdx.x; i < (p.S - nq * AT_BQ) * 8; i += blockDim.x) {
-        const int r = nq * AT_BQ + (i >> 3), c = i & 7;
-        *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < (p.S - nq_all * AT_BQ) * 8; i += blockDim.x) {
+            const int r = nq_all * AT_BQ + (i >> 3), c = i & 7;
+            *reinterpret_cast<uint4*>(p.o + (row_base + r) * p.ldo + h * AT_D + c * 8) = make_uint4(0, 0, 0, 0);
+        }
     }
     if (nq == 0) return;
 
@@ -637,7 +643,7 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         fence_barrier_init();
         // the first loads only need the barriers: get them in flight before the rest of the CTA finishes its set-up
         mbar_arrive_expect_tx(&q_full[0], AT_TILE_BYTES);
-        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)row_base);
+        tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col0 + h * AT_D, (int)(row_base + q_first * AT_BQ));
         mbar_arrive_expect_tx(&kv_full[0], 2 * AT_TILE_BYTES);
         tma_load_2d(sK, &tmap_qkv, &kv_full[0], p.k_col0 + h * AT_D, (int)row_base);
         tma_load_2d(sV, &tmap_qkv, &kv_full[0], p.v_col0 + h * AT_D, (int)row_base);
@@ -685,7 +691,7 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 if (qi > 0) {   // (tile 0 was issued during set-up)
                     mbar_wait(&q_empty[qb], (((uint32_t)qi >> 1) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&q_full[qb], AT_TILE_BYTES);
-                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + qi * AT_BQ));
+                    tma_load_2d(sQ + qb * AT_TILE_BYTES, &tmap_qkv, &q_full[qb], p.q_col0 + h * AT_D, (int)(row_base + (q_first + qi) * AT_BQ));
                 }
                 for (int j = 0; j < nkt; ++j) {
                     const int g = qi * nkt + j;
@@ -777,7 +783,7 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
         };
         int g = 0;
         for (int qi = 0; qi < nq; ++qi) {
-            const int q0 = qi * AT_BQ;
+            const int q0 = (q_first + qi) * AT_BQ;
             const int qrow = q0 + row;
             __nv_bfloat16* orow = p.o + (row_base + qrow) * p.ldo + h * AT_D + half * 32;
             if (q0 + (int)quad * 32 >= len) {
@@ -806,7 +812,7 @@ attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Att
                 const int nch = min(4, (len - k0 + 31) >> 5);   // 32-key chunks of the tile that contain at least one valid key
                 const int c_lo = 2 * (int)half;
                 const int n_mine = max(0, min(nch - c_lo, 2));  // this half's chunks: c_lo .. c_lo + n_mine - 1
-                const int dt = j - qi;
+                const int dt = j - (q_first + qi);
                 const bool near = HAS_BIAS && (dt <= p.near_tiles) && (dt >= -p.near_tiles);
                 const float bias_ub = near ? bmax_near : (dt < 0 ? b_left : b_right);   // 0 without bias
                 const uint32_t s_addr = tmem_S + lane_off + c_lo * 32;
@@ -966,7 +972,7 @@ inline cudaError_t launch_attn_stream_t(const CUtensorMap& tm, const AttnTc2Para
 }
 
 template <bool HAS_BIAS, bool ROUND>
-inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream) {
+inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Params& p, int B, size_t smem, cudaStream_t stream, int q_ctas) {
     auto kernel = attn_tc_d64_split_kernel<HAS_BIAS, ROUND>;
     static std::atomic<size_t> max_set[64];
     int dev = 0;
@@ -977,7 +983,7 @@ inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Param
         if (e != cudaSuccess) return e;
         max_set[dev & 63].store(smem, std::memory_order_release);
     }
-    kernel<<<dim3(1, p.H, B), 320, smem, stream>>>(tm, p);
+    kernel<<<dim3((unsigned)q_ctas, p.H, B), 320, smem, stream>>>(tm, p);
     return cudaGetLastError();
 }
 
@@ -1002,10 +1008,19 @@ inline cudaError_t launch_attn_tc(const __nv_bfloat16* qkv, int ld, int q_col0, 
     if (bias_table && bias_const_from > 0 && bias_const_from < S) near = min(n_tiles, (bias_const_from - 1 + 127) / 128);
     p.near_tiles = bias_table ? near : 0;
     const size_t smem = attn_tc2_smem_bytes(p.near_tiles, bias_table != nullptr, round_scores);
+    p.q_per_cta = n_tiles;
     if (stage == 2) {
         const size_t smem4 = smem + 2048 + 64 + 128;  // + the row-pair exchange buffers / barriers and the wider per-warp reduction scratch
-        if (bias_table) return round_scores ? launch_attn_split_t<true, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<true, false>(tm, p, B, smem4, stream_);
-        return round_scores ? launch_attn_split_t<false, true>(tm, p, B, smem4, stream_) : launch_attn_split_t<false, false>(tm, p, B, smem4, stream_);
+        // small batches: B * H CTAs do not fill 148 SMs x 2 CTAs -> give each (sample, head) several CTAs, each with a share of the query tiles
+        // (the K/V tiles are then read once per CTA instead of once per (sample, head): irrelevant at this size)
+        int q_ctas = 1;
+        if (B * H < 296 && n_tiles > 1) {
+            q_ctas = min(n_tiles, (296 + B * H - 1) / (B * H));
+            p.q_per_cta = (n_tiles + q_ctas - 1) / q_ctas;
+            q_ctas = (n_tiles + p.q_per_cta - 1) / p.q_per_cta;
+        }
+        if (bias_table) return round_scores ? launch_attn_split_t<true, true>(tm, p, B, smem4, stream_, q_ctas) : launch_attn_split_t<true, false>(tm, p, B, smem4, stream_, q_ctas);
+        return round_scores ? launch_attn_split_t<false, true>(tm, p, B, smem4, stream_, q_ctas) : launch_attn_split_t<false, false>(tm, p, B, smem4, stream_, q_ctas);
     }
     if (bias_table) return round_scores ? launch_attn_stream_t<true, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<true, false>(tm, p, B, smem, stream_);
     return round_scores ? launch_attn_stream_t<false, true>(tm, p, B, smem, stream_) : launch_attn_stream_t<false, false>(tm, p, B, smem, stream_);

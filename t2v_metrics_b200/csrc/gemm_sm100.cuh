@@ -51,7 +51,9 @@ struct GemmParams {
     const __nv_bfloat16* bias;      // [N] or nullptr
     const __nv_bfloat16* residual;  // [M, ldr] or nullptr
     int ldr;
-    int c_f32;                // EPI_STORE only: C and residual are fp32 buffers (ldc / ldr in floats): C = residual + bf16(acc + bias), unrounded
+    int c_f32;                // EPI_STORE only. 1: C and residual are fp32 buffers (ldc / ldr in floats): C = residual + bf16(acc + bias), unrounded
+                              // 2: C is an fp32 buffer that receives the RAW accumulator (split-K partial sums: batches = K slices, reduced by
+                              //    splitk_reduce_kernel, which also applies bias / rounding / residual)
                               // (the CLIP tower's residual stream stays fp32 under the reference's autocast: LayerNorm is on autocast's fp32 list)
     int gate_up_offset;       // GATED: row offset of the "up" weight block inside W (= d_ff)
     int c_group_in, c_group_out;   // EPI_STORE without residual, c_group_in > 0: logical output column c is stored at column
@@ -419,6 +421,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (nc + j * 4 < p.N) {
+                                if (p.c_f32 == 2) {
+                                    *reinterpret_cast<float4*>(crow + j * 4) = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                                                                          __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+                                    continue;
+                                }
                                 float4 r = rrow ? *reinterpret_cast<const float4*>(rrow + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                                 float b[4] = {0.f, 0.f, 0.f, 0.f};
                                 if (p.bias) {

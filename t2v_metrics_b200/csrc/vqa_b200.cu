@@ -245,6 +245,69 @@ static cudaError_t run_gemm_batched(const bf16* A, int lda, const bf16* W, int l
     return gemm_dispatch_variant<EPI_STORE>(g, variant, num_sms, st);
 }
 
+// Split-K for skinny GEMMs (M <= 128 decoder rows x a 4096-row weight): 32 N tiles alone leave 116 SMs idle and stream the weight at ~1 TB/s
+// (profiles/r02_small_batch.md), so the K range is cut into `splits` slices that run as the batches of ONE launch (fp32 partial tiles in `ws`),
+// and this kernel adds the slices: C = [residual +] bf16(sum_s partial_s + bias) -- the Linear's bf16 output, then the residual add, like EPI_STORE.
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, const bf16* __restrict__ bias,
+                                     const bf16* __restrict__ residual, int ldr, bf16* __restrict__ C, int ldc) {
+    const int nv = N / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)M * nv) return;
+    const int m = (int)(i / nv), n = (int)(i % nv) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < splits; ++s) {
+        const float4* src = reinterpret_cast<const float4*>(part + ((size_t)s * M + m) * N + n);
+        const float4 a = src[0], b = src[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    if (bias) {
+        const uint4 bb = __ldg(reinterpret_cast<const uint4*>(bias + n));
+        const float2 b0 = unpack_bf16x2(bb.x), b1 = unpack_bf16x2(bb.y), b2 = unpack_bf16x2(bb.z), b3 = unpack_bf16x2(bb.w);
+        acc[0] += b0.x; acc[1] += b0.y; acc[2] += b1.x; acc[3] += b1.y; acc[4] += b2.x; acc[5] += b2.y; acc[6] += b3.x; acc[7] += b3.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bf16_round(acc[e]);
+    if (residual) {
+        const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)m * ldr + n);
+        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+        acc[0] += r0.x; acc[1] += r0.y; acc[2] += r1.x; acc[3] += r1.y; acc[4] += r2.x; acc[5] += r2.y; acc[6] += r3.x; acc[7] += r3.y;
+    }
+    *reinterpret_cast<uint4*>(C + (size_t)m * ldc + n) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                     pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// number of K slices a skinny store-GEMM is cut into (1 = not worth it / not possible)
+static int splitk_slices(int M, int N, int K, int num_sms) {
+    static const int off = env_int("VQA_GEMM_SPLITK", 1) == 0;
+    if (off || M > 128 || N % 8 || K < 2048) return 1;
+    const int n_tiles = (N + 127) / 128;
+    int s = num_sms / n_tiles;
+    if (s > 8) s = 8;
+    while (s >= 2 && K % (s * 64) != 0) --s;
+    return s >= 2 ? s : 1;
+}
+static size_t splitk_workspace_bytes(int M, int N, int K, int num_sms) {
+    const int s = splitk_slices(M, N, K, num_sms);
+    return s > 1 ? (size_t)s * M * N * 4 : 0;
+}
+static cudaError_t run_gemm_splitk(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M, int N, int K,
+                                   const bf16* bias, const bf16* residual, int ldr, int splits, float* ws, int num_sms, cudaStream_t st,
+                                   int64_t* launch_counter) {
+    GemmLaunch g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.w_rows = w_rows;
+    g.a_rows = M; g.a_cols = K; g.w_cols = K;
+    memset(&g.p, 0, sizeof(g.p));
+    const int Ks = K / splits;
+    g.p.M = M; g.p.N = N; g.p.K = Ks; g.p.C = reinterpret_cast<bf16*>(ws); g.p.ldc = N; g.p.c_f32 = 2;
+    g.p.num_batches = splits; g.p.a_k_off = Ks; g.p.w_k_off = Ks; g.p.c_batch_stride = (long long)M * N;
+    if (launch_counter) *launch_counter += 2;
+    cudaError_t e = gemm_dispatch_variant<EPI_STORE>(g, 1281, num_sms, st);
+    if (e != cudaSuccess) return e;
+    const long long n = (long long)M * (N / 8);
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, splits, M, N, bias, residual, ldr, C, ldc);
+    return cudaGetLastError();
+}
+
 constexpr int LMHEAD_BN = 128;
 constexpr int LMHEAD_PARTS = GemmConfig<LMHEAD_BN, 1>::LSE_PARTS;   // (max, sum) partials per (row, n tile)
 static cudaError_t run_lmhead(const bf16* H, int ldh, const bf16* W, int ldw, int M, int N, int K, const int* labels,
@@ -504,7 +567,7 @@ struct ClipT5Workspace {
     size_t patches, patch_out, hv, vn, vqkv, vattn, vmlp, proj1, proj2;
     // t5
     size_t x, xn, qkv, attn, ff, bias_table, seq_lens, ckv, ssq_a, ssq_b;
-    size_t y, yn, dqkv, dattn, dq, dff;
+    size_t y, yn, dqkv, dattn, dq, dff, splitk, splitk_bytes;
     size_t xt, qt, csc, cctx;   // absorbed cross-attention: Xenc^T, q~ = Wk^T q, scores/probs, context sum p.h
     size_t lse_max, lse_sum, label_logit;
     size_t total;
@@ -557,6 +620,13 @@ static ClipT5Workspace plan_workspace(const vqa_handle* h, int B, int NI, int L,
     w.dattn = pl.take(Md * inner * 2);
     w.dq = pl.take(Md * inner * 2);
     w.dff = pl.take(Md * c.d_ff * 2);
+    {   // fp32 partial tiles of the decoder's split-K GEMMs (largest of the eligible shapes; 0 when none is)
+        size_t sk = 0;
+        const int shapes[4][2] = {{(int)(3 * inner), c.d_model}, {c.d_model, (int)inner}, {(int)inner, c.d_model}, {c.d_model, c.d_ff}};
+        for (const auto& nk : shapes) sk = std::max(sk, splitk_workspace_bytes((int)Md, nk[0], nk[1], h->num_sms));
+        w.splitk = pl.take(sk);
+        w.splitk_bytes = sk;
+    }
     const size_t ntiles = (size_t)LMHEAD_PARTS * ((c.vocab + LMHEAD_BN - 1) / LMHEAD_BN);
     w.lse_max = pl.take(Md * ntiles * 4);
     w.lse_sum = pl.take(Md * ntiles * 4);
@@ -796,11 +866,21 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
         decoder_embed_kernel<<<Md, 128, 0, st>>>(labels, h->shared, P_(w.y), T, Dm, c.decoder_start_id, c.pad_token_id);
         TRY(cuda_ok(cudaSuccess, "decoder embed"));
     }
+    // decoder store-GEMMs: M = B*T rows against 4096-row weights -> split-K when that fills the SMs (run_gemm_splitk), else the plain path
+    auto dgemm = [&](const bf16* A, int lda, const bf16* W, int ldw, int w_rows, bf16* C, int ldc, int M_, int N_, int K_,
+                     const bf16* bias, const bf16* res, int ldr, int epi, int gate_off) -> int {
+        const int sl = epi == EPI_STORE ? splitk_slices(M_, N_, K_, nsm) : 1;
+        if (sl <= 1 || (size_t)sl * M_ * N_ * 4 > w.splitk_bytes) return gemm(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, bias, res, ldr, epi, gate_off);
+        const double bytes = 2.0 * ((double)M_ * K_ + (double)N_ * K_ + (double)M_ * N_ * (res ? 2 : 1));
+        ProfScope ps(h, CAT_GEMM, 2.0 * M_ * (double)N_ * K_, st, bytes);
+        return cuda_ok(run_gemm_splitk(A, lda, W, ldw, w_rows, C, ldc, M_, N_, K_, bias, res, ldr, sl, reinterpret_cast<float*>(ws + w.splitk), nsm, st, lc),
+                       "split-K gemm");
+    };
     for (int l = 0; l < c.dec_layers; ++l) {
         const T5DecLayerW& Lw = h->dec[l];
         // self-attention
         TRY(rms(P_(w.y), Lw.ln0, P_(w.yn), Md));
-        TRY(gemm(P_(w.yn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.dqkv), 3 * inner, Md, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        TRY(dgemm(P_(w.yn), Dm, Lw.qkv, Dm, 3 * inner, P_(w.dqkv), 3 * inner, Md, 3 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
         {
             ProfScope ps(h, CAT_ATTENTION, 4.0 * B * (double)H * T * T * 64, st);
             ++*lc;
@@ -808,9 +888,9 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
                                                                              c.rel_max_distance, B, T, H, rnd);
             TRY(cuda_ok(cudaSuccess, "decoder self attention"));
         }
-        TRY(gemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
+        TRY(dgemm(P_(w.dattn), inner, Lw.o, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
         TRY(rms(P_(w.y), Lw.ln1, P_(w.yn), Md));
-        TRY(gemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
+        TRY(dgemm(P_(w.yn), Dm, Lw.cq, Dm, inner, P_(w.dq), inner, Md, inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
         if (c.cross_attention_mode != 0) {
             // reference association: K/V projection of all S encoder rows in every layer (modeling_t5.py:297-299)
             TRY(gemm(P_(w.xn), Dm, Lw.ckv, Dm, 2 * inner, P_(w.ckv), 2 * inner, M, 2 * inner, Dm, nullptr, nullptr, 0, EPI_STORE, 0));
@@ -848,12 +928,12 @@ extern "C" int vqa_clipt5_score(vqa_handle* h, const void* pixels, int32_t pixel
             TRY(bgemm(P_(w.cctx), H * Dm, Lw.ckv + (size_t)inner * Dm, Dm, P_(w.dattn), inner, Md, 64, Dm,
                       BatchSpec{H, 0, Dm, 64, 0, 64, Md, (long long)H * Dm, inner, Dm}, 641));
         }
-        TRY(gemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
+        TRY(dgemm(P_(w.dattn), inner, Lw.co, inner, Dm, P_(w.y), Dm, Md, Dm, inner, nullptr, P_(w.y), Dm, EPI_STORE, 0));
         // gated FFN
         TRY(rms(P_(w.y), Lw.ln2, P_(w.yn), Md));
         TRY(gemm(P_(w.yn), Dm, Lw.wi, Dm, 2 * c.d_ff, P_(w.dff), c.d_ff, Md, 2 * c.d_ff, Dm, nullptr, nullptr, 0, EPI_GATED_GELU,
                  c.d_ff));
-        TRY(gemm(P_(w.dff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.y), Dm, Md, Dm, c.d_ff, nullptr, P_(w.y), Dm, EPI_STORE, 0));
+        TRY(dgemm(P_(w.dff), c.d_ff, Lw.wo, c.d_ff, Dm, P_(w.y), Dm, Md, Dm, c.d_ff, nullptr, P_(w.y), Dm, EPI_STORE, 0));
     }
     TRY(rms(P_(w.y), h->dec_final_ln, P_(w.yn), Md));
 
@@ -1128,6 +1208,23 @@ extern "C" int vqa_op_gemm_bf16_grouped(const void* A, int32_t lda, const void* 
     if (lda % 8 || ldw % 8 || ldc % 8 || N % 8 || K % 8) return fail(nullptr, VQA_ERR_INVALID_ARG, "gemm: ld/N/K must be multiples of 8");
     cudaError_t e = run_gemm((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, (const bf16*)bias, nullptr, 0, EPI_STORE, 0, variant,
                              device_sms(), (cudaStream_t)stream, nullptr, false, nullptr, group_in, group_out);
+    if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// Skinny GEMM (M <= 128) with the K range cut into slices that run as one launch, partial tiles in `workspace` (fp32, splits * M * N floats; the
+// slice count the library would pick is returned in *splits_out when splits == 0): C = [residual +] bf16(A W^T + bias).
+extern "C" int vqa_op_gemm_bf16_splitk(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t w_rows, void* C, int32_t ldc, int32_t M, int32_t N,
+                                       int32_t K, const void* bias, const void* residual, int32_t ldr, int32_t splits, void* workspace,
+                                       size_t workspace_bytes, int32_t* splits_out, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return fail(nullptr, VQA_ERR_INVALID_ARG, "bad gemm argument");
+    if (lda % 8 || ldw % 8 || ldc % 8 || N % 8 || K % 8) return fail(nullptr, VQA_ERR_INVALID_ARG, "gemm: ld/N/K must be multiples of 8");
+    if (splits == 0) splits = splitk_slices(M, N, K, device_sms());
+    if (splits_out) *splits_out = splits;
+    if (splits < 1 || K % (splits * 64)) return fail(nullptr, VQA_ERR_INVALID_ARG, "split-K: K must be a multiple of splits * 64");
+    if (!workspace || workspace_bytes < (size_t)splits * M * N * 4) return fail(nullptr, VQA_ERR_WORKSPACE, "split-K workspace too small");
+    cudaError_t e = run_gemm_splitk((const bf16*)A, lda, (const bf16*)W, ldw, w_rows, (bf16*)C, ldc, M, N, K, (const bf16*)bias, (const bf16*)residual, ldr,
+                                    splits, (float*)workspace, device_sms(), (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return fail(nullptr, VQA_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -17,9 +17,11 @@ and the bf16 run sits 3.7e-3 / 3.5e-3 away from the same model in fp32 (round-2 
 The engine is 3.2e-3 / 6.6e-3 from the eager bf16 run and 1.7e-3 / 4.2e-3 from fp32. So the assertions for CLIP-FlanT5 are
     |engine - HF bf16|  <=  1e-3 + 2 x N        N = the reference's own spread, measured in the same test run:
                                                  max(|HF bf16 eager - HF bf16 sdpa|, |HF bf16 - HF fp32|, |HF batch-1 - HF batched|)
-    |engine - HF fp32|  <=  1e-3 + 2 x |HF bf16 - HF fp32|
+    |engine - HF fp32|  <=  1e-3 + 2 x N
 (the factor 2: N is itself a maximum over four samples of a noise), and the literal 1e-3 comparison is kept as an `xfail` test so the
-gap stays visible in every test report instead of being tuned away.
+gap stays visible in every test report instead of being tuned away. The fixture is steep by construction (|lm_head answer row| x |h| = 22:
+a 1e-4 relative change of the final hidden state moves a score by 5e-4), so ANY change of fp32 summation order lands somewhere else inside
+the spread: the same engine measured 1.2e-3 (streaming softmax stage), 3.2e-3 (two-pass stage) and 4.9e-3 (split-K decoder GEMMs) on xxl.
 """
 import dataclasses
 import gc
@@ -172,7 +174,7 @@ def _assert_within_reference_spread(r):
     assert "ref_impl_noise" in r, "the sdpa run of the reference did not complete: no measured spread to compare with"
     assert r["err"] <= TOL + 2 * noise, r
     if "err_fp32" in r:
-        assert r["err_fp32"] <= TOL + 2 * r["ref_prec_noise"], r
+        assert r["err_fp32"] <= TOL + 2 * noise, r
 
 
 def test_clipt5_xxl_within_the_references_own_bf16_spread(dev):

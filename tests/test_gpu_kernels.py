@@ -69,6 +69,31 @@ def test_gemm_fused_epilogues(ops, variant, epi):
     close(c, ref_gemm(a, w, bias, None, epi, N // 2), epi)
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(128, 4096, 4096, 0), (2, 4096, 10240, 0), (100, 1024, 2048, 4), (7, 512, 4096, 8)])
+def test_gemm_split_k_for_decoder_rows(ops, M, N, K, splits):
+    """Skinny store-GEMM with K cut into slices (one launch, fp32 partials, one reduction): C = residual + bf16(A W^T + bias), the same rounding
+    points as the plain epilogue, so it must agree with it to the last bit of the bf16 sum order."""
+    import ctypes as C
+    from t2v_metrics_b200 import _lib
+    from t2v_metrics_b200.engine import _ptr, _stream_ptr, _check
+    lib = _lib.load()
+    torch.manual_seed(12)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    bias = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(8 * M * N, dtype=torch.float32, device="cuda")
+    used = C.c_int32(0)
+    _check(lib.vqa_op_gemm_bf16_splitk(_ptr(a), K, _ptr(w), K, N, _ptr(out), N, M, N, K, _ptr(bias), _ptr(res), N, splits, _ptr(ws), ws.numel() * 4,
+                                       C.byref(used), _stream_ptr(a.device)), None, "vqa_op_gemm_bf16_splitk")
+    torch.cuda.synchronize()
+    assert used.value >= 2, used.value          # every case here is meant to split
+    plain = ops.gemm(a, w, bias=bias, residual=res)
+    close(out, ref_gemm(a, w, bias, res, "store", 0), (M, N, K, used.value))
+    assert float((out.float() - plain.float()).abs().max()) <= 0.0625          # one bf16 ulp of the rounded Linear output at |y| <= 8
+
+
 def test_gemm_empty_and_ragged_edges(ops):
     torch.manual_seed(3)
     for (M, N, K) in [(1, 8, 8), (129, 264, 72), (257, 40, 200)]:
@@ -94,7 +119,8 @@ def test_gemm_linearity_full_size(ops):
 
 @pytest.mark.parametrize("B,S,H,use_bias,ragged,scale", [(2, 100, 4, True, True, 1.0), (3, 577, 16, False, False, 0.125),
                                                          (2, 672, 8, True, True, 1.0), (1, 64, 1, True, False, 1.0),
-                                                         (2, 65, 2, False, True, 0.125)])
+                                                         (2, 65, 2, False, True, 0.125),
+                                                         (5, 300, 64, True, True, 1.0)])   # B*H >= 296: one CTA per (sample, head), all query tiles
 def test_attention_matches_torch(ops, B, S, H, use_bias, ragged, scale):
     torch.manual_seed(5)
     qkv = (torch.randn(B * S, 3 * H * 64, device="cuda") * 0.5).bfloat16()
