@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--text-len", type=int, default=97)
     ap.add_argument("--ragged", action="store_true", help="clip-flant5: text lens ~U[64, text_len] instead of all = text_len (SURVEY 8d)")
     ap.add_argument("--video", action="store_true", help="qwen: SURVEY 8(d) config 5 shape (grid 8x16x16, S=576, batch 8)")
+    ap.add_argument("--video-size", type=int, default=224, help="qwen --video: frame side in pixels (224 -> grid 8x16x16; 336 -> 8x24x24, the shape "
+                    "qwen_vl_utils' frame upscaling would probably produce, SURVEY 8(d) config 5 secondary shape)")
     ap.add_argument("--pairs", type=int, default=0, help="clip-flant5: SURVEY 8(d) config 4 -- a JOB of this many pairs sharded "
                     "contiguously over the ranks in batches of --batch (+ tail), one all-gather; a step = the whole job; strong scaling")
     ap.add_argument("--fuse-norms", type=int, default=-1, help="1/0: fold the encoder's T5LayerNorms into the GEMMs (default: the engine's default)")
@@ -224,7 +226,7 @@ def cpu_reference_qwen(model: str, timed_pairs: int, budget_s: float, video: boo
     m = hf.build_hf_qwen(cfg, sd, dtype=torch.float32, device="cpu", attn="sdpa", fast_construct=True, assign=True)
     del sd
     t_build = time.perf_counter() - t_build
-    hw, frames = ((224, 224), 8) if video else ((448, 448), 1)
+    hw, frames = ((args.video_size, args.video_size), 8) if video else ((448, 448), 1)
 
     def one_pair(seed):
         inp = qo.make_synthetic_inputs(cfg, 1, hw, 64, seed=100 + seed, frames=frames)
@@ -604,10 +606,10 @@ def run_engine_qwen(args, rank, local_rank, world):
     # --video = SURVEY 8(d) config 5: 16 frames of 224x224 -> grid (8, 16, 16) = 2048 patches / 512 video tokens, S = 576, B = 8
     video = bool(args.video)
     B = args.batch if args.batch != 64 else (8 if video else 32)
-    hw, frames = ((224, 224), 8) if video else ((448, 448), 1)
+    hw, frames = ((args.video_size, args.video_size), 8) if video else ((448, 448), 1)
     host = synthetic_qwen_batch(cfg, B, hw, 64, seed=1 + rank, frames=frames)
     seq_len = 64 + frames * (hw[0] // 28) * (hw[1] // 28)
-    flops_pair = 10.25e12 if video else FLOPS_PER_PAIR[args.model]
+    flops_pair = (22.19e12 if args.video_size == 336 else 10.25e12) if video else FLOPS_PER_PAIR[args.model]
     idx = qwen_host.build_batch_indices(host["prompts"], host["grid_thw"], list(range(B)), cfg.image_token_id, cfg.spatial_merge_size,
                                         cfg.tokens_per_second, video_token_id=cfg.video_token_id,
                                         second_per_grid_ts=[1.0] * B if video else None)
@@ -696,9 +698,10 @@ def run_engine_qwen(args, rank, local_rank, world):
         gemm_ms, gemm_flops, gemm_n, gemm_bytes = prof["gemm"]
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         value = total / (ms_step * 1e-3)
-        shape = ("synthetic 16-frame 224x224 videos (grid 8x16x16: 2048 patches, 512 video tokens) + 64 text ids (S=576)" if video else
+        g_ = hw[0] // 14
+        shape = (f"synthetic 16-frame {hw[0]}x{hw[1]} videos (grid 8x{g_}x{g_}: {8 * g_ * g_} patches, {2 * g_ * g_} video tokens) + 64 text ids (S={seq_len})" if video else
                  "synthetic 448x448 images (1024 patches, 256 vision tokens) + 64 text ids (S=320)")
-        line = dict(metric="VQAScore (video,text) pairs/sec @ qwen2.5-vl-7b, 16x224px" if video else
+        line = dict(metric=f"VQAScore (video,text) pairs/sec @ qwen2.5-vl-7b, 16x{hw[0]}px" if video else
                     "VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px", value=value, unit="pairs/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",

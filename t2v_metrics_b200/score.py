@@ -31,6 +31,9 @@ class Score(nn.Module):
         self.model = self.prepare_scoremodel(model, device, cache_dir, **kwargs)
         self.model_name = model
         self.max_pairs = 64
+        # one process per GPU (torchrun): forward() splits the IMAGES over the ranks so that every image's vision features are computed on
+        # one rank only, and all-gathers the [m, n] score rows. Off: every rank scores everything, like the reference.
+        self.shard_over_images = True
 
     def prepare_scoremodel(self, model: str, device: str, cache_dir: str, **kwargs):
         raise NotImplementedError("Subclasses must implement prepare_scoremodel")
@@ -49,12 +52,28 @@ class Score(nn.Module):
             raise NotImplementedError("video inputs (frame extraction + concat, reference score.py:72-98) are outside the "
                                       "B200 engine's hot-path scope; pass image files")
         m, n = len(images), len(texts)
-        pair_images = [img for img in images for _ in range(n)]
-        pair_texts = [t for _ in range(m) for t in texts]
-        out = []
-        for s in range(0, m * n, self.max_pairs):
-            out.append(self.model.forward(pair_images[s:s + self.max_pairs], pair_texts[s:s + self.max_pairs], **kwargs))
-        return torch.cat(out).view(m, n).to(self.device)
+        import torch.distributed as dist
+        world = dist.get_world_size() if (self.shard_over_images and dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            from .parallel import shard_bounds
+            start, end, per = shard_bounds(m, world, dist.get_rank())
+        else:
+            start, end, per = 0, m, m
+        pair_images = [img for img in images[start:end] for _ in range(n)]
+        pair_texts = [t for _ in range(end - start) for t in texts]
+        out = [torch.zeros(0)]
+        for s in range(0, len(pair_images), self.max_pairs):
+            out.append(self.model.forward(pair_images[s:s + self.max_pairs], pair_texts[s:s + self.max_pairs], **kwargs).float().cpu())
+        local = torch.cat(out)
+        if world > 1:
+            # equal-sized shards of `per` images (the last ranks may hold fewer or none: zero rows, trimmed after the gather)
+            dev = torch.device(self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            padded = torch.zeros(per * n, dtype=torch.float32, device=dev)
+            padded[: local.numel()] = local.to(dev)
+            gathered = torch.empty(world * per * n, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gathered, padded)
+            local = gathered[: m * n]
+        return local.view(m, n).to(self.device)
 
     def batch_forward(self, dataset: List[ImageTextDict], batch_size: int = 16, num_frames: int = 4, **kwargs) -> torch.Tensor:
         """[num_samples, num_visuals, num_texts] scores for a dataset of {'images': [...], 'texts': [...]} items."""
