@@ -17,6 +17,7 @@ __global__ void t5_decoder_self_attn_kernel(const __nv_bfloat16* __restrict__ qk
                                             const __nv_bfloat16* __restrict__ rel_emb,  // [num_buckets, H]
                                             const int* __restrict__ bucket_lut,         // [2*max_dist+1] unidirectional
                                             int max_dist, int B, int T, int H, int round_scores) {
+    pdl_launch_dependents();
     extern __shared__ float dec_sc[];
     const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (widx >= B * H * T) return;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(128) t5_cross_attn_kernel(const __nv_bfloat16*
                                                            __nv_bfloat16* __restrict__ out,       // [B*T, H*64]
                                                            const int* __restrict__ seq_lens, int ldkv, int B, int T,
                                                            int S, int H, int round_scores) {
+    pdl_launch_dependents();
     const int h = blockIdx.x % H, b = blockIdx.x / H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int len = seq_lens ? seq_lens[b] : S;
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(128) t5_cross_attn_kernel(const __nv_bfloat16*
 // [B, S, D] -> [B, D, Sp] (Sp >= S, multiple of 8; columns >= S are zero). 32x32 tiles through shared memory.
 __global__ void transpose_bsd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xt, int S, int D,
                                      int Sp) {
+    pdl_launch_dependents();
     __shared__ __nv_bfloat16 tile[32][33];
     const int b = blockIdx.z;
     const int s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -149,6 +152,7 @@ __global__ void transpose_bsd_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // fp32 softmax, probabilities cast back to bf16 (modeling_t5.py:331). One warp per row.
 __global__ void cross_softmax_kernel(__nv_bfloat16* __restrict__ sc, const int* __restrict__ seq_lens, int rows_per_b,
                                      int total_rows, int S, int Sp) {
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= total_rows) return;
     const int lane = threadIdx.x & 31;

@@ -20,6 +20,22 @@
 
 namespace vqa {
 
+// launch with the programmatic-stream-serialisation attribute (the kernel calls pdl_wait() before its first global access)
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 
 constexpr int AT_BQ = 128, AT_BK = 128, AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, K or V tile
@@ -228,6 +244,8 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t
 template <bool HAS_BIAS, bool ROUND>
 __global__ void __launch_bounds__(192, 2)
 attn_tc_d64_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
+    pdl_launch_dependents();
+    pdl_wait();      // seq_lens / the bias table / qkv are outputs of earlier kernels
     constexpr int POLY = 0;
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
@@ -581,6 +599,8 @@ attn_tc_d64_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const At
 template <bool HAS_BIAS, bool ROUND>
 __global__ void __launch_bounds__(320, 2)
 attn_tc_d64_split_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc2Params p) {
+    pdl_launch_dependents();
+    pdl_wait();      // seq_lens / the bias table / qkv are outputs of earlier kernels
     constexpr int POLY = 0;
     const int h = blockIdx.y, b = blockIdx.z;
     const int len = p.seq_lens ? min(p.seq_lens[b], p.S) : p.S;
@@ -967,8 +987,7 @@ inline cudaError_t launch_attn_stream_t(const CUtensorMap& tm, const AttnTc2Para
         if (e != cudaSuccess) return e;
         max_set[dev & 63].store(smem, std::memory_order_release);
     }
-    kernel<<<dim3(1, p.H, B), 192, smem, stream>>>(tm, p);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3(1, p.H, B), dim3(192), smem, stream, tm, p);
 }
 
 template <bool HAS_BIAS, bool ROUND>
@@ -983,8 +1002,7 @@ inline cudaError_t launch_attn_split_t(const CUtensorMap& tm, const AttnTc2Param
         if (e != cudaSuccess) return e;
         max_set[dev & 63].store(smem, std::memory_order_release);
     }
-    kernel<<<dim3((unsigned)q_ctas, p.H, B), 320, smem, stream>>>(tm, p);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3((unsigned)q_ctas, p.H, B), dim3(320), smem, stream, tm, p);
 }
 
 // round_scores: reproduce the bf16 tensors of the reference's eager attention (scores, scores + bias) before the fp32 softmax.
@@ -1058,6 +1076,8 @@ inline size_t attn_tc128_smem_bytes() { return 1024 + 5 * A8_TILE + 128; }
 template <bool CAUSAL, int POLY>
 __global__ void __launch_bounds__(192, 1)
 attn_tc_d128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTc128Params p) {
+    pdl_launch_dependents();
+    pdl_wait();      // cu_seqlens / qkv are outputs of earlier kernels
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / p.kv_group;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -1326,8 +1346,7 @@ inline cudaError_t launch_attn_tc128(const __nv_bfloat16* qkv, int ld, long long
     auto go = [&](auto kernel, PerDeviceOnce& once) -> cudaError_t {
         cudaError_t e = once.ensure([&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         if (e != cudaSuccess) return e;
-        kernel<<<grid, 192, smem, stream>>>(tm, p);
-        return cudaGetLastError();
+        return launch_pdl(kernel, grid, dim3(192), smem, stream, tm, p);
     };
     static PerDeviceOnce once[4];
     if (causal) return poly == 0 ? go(attn_tc_d128_kernel<true, 0>, once[0]) : go(attn_tc_d128_kernel<true, 2>, once[1]);

@@ -38,6 +38,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) t5_rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x,
                                                              const __nv_bfloat16* __restrict__ w,
                                                              __nv_bfloat16* __restrict__ y, int rows, float eps) {
+    pdl_launch_dependents();
     constexpr int D = 256 * NV;
     const int lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -83,6 +84,7 @@ template <int VPT>
 __global__ void __launch_bounds__(256) t5_rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                         const __nv_bfloat16* __restrict__ w,
                                                         __nv_bfloat16* __restrict__ y, int D, float eps) {
+    pdl_launch_dependents();
     __shared__ float red[32];
     const size_t row = blockIdx.x;
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
                                                        const __nv_bfloat16* __restrict__ gamma,
                                                        const __nv_bfloat16* __restrict__ beta,
                                                        __nv_bfloat16* __restrict__ y, int rows, float eps) {
+    pdl_launch_dependents();
     constexpr int VPL = D / 256;  // groups of 8 elements per lane
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
 template <typename PixelT>
 __global__ void patchify_kernel(const PixelT* __restrict__ pix, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                 int ps, int kpad) {
+    pdl_launch_dependents();
     const int gw = W / ps, gh = H / ps;
     const int P = gw * gh;
     const size_t row = blockIdx.x;  // b * P + p
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(256) clip_embed_ln_kernel(const __nv_bfloat16*
                                                            const __nv_bfloat16* __restrict__ beta,
                                                            float* __restrict__ y,  // [B*(P+1), D] fp32: pre_layrnorm's output under autocast
                                                            int B, int P, float eps) {
+    pdl_launch_dependents();
     constexpr int VPL = D / 256;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B * (P + 1)) return;
@@ -296,6 +301,7 @@ __global__ void splice_embed_kernel(const int* __restrict__ ids,          // [B,
                                     __nv_bfloat16* __restrict__ out,  // [B, S, D]
                                     int* __restrict__ seq_lens,       // [B]
                                     int B, int L, int S, int P, int D, int image_token) {
+    pdl_launch_dependents();
     const int b = blockIdx.x / S, s = blockIdx.x % S;
     const int tl = text_lens[b];
     __shared__ int slot_sh;
@@ -329,6 +335,7 @@ __global__ void splice_embed_kernel(const int* __restrict__ ids,          // [B,
 __global__ void decoder_embed_kernel(const int* __restrict__ labels,  // [B, T]
                                      const __nv_bfloat16* __restrict__ shared_emb, __nv_bfloat16* __restrict__ out,
                                      int T, int D, int start_id, int pad_id) {
+    pdl_launch_dependents();
     const int b = blockIdx.x / T, t = blockIdx.x % T;
     int id = (t == 0) ? start_id : labels[b * T + t - 1];
     if (id == -100) id = pad_id;
@@ -341,6 +348,7 @@ __global__ void decoder_embed_kernel(const int* __restrict__ labels,  // [B, T]
 // The bucket LUT is computed on the host (vqa_b200.cu host_rel_bucket, mirror of modeling_t5.py:189-234).
 __global__ void bias_table_from_lut_kernel(const __nv_bfloat16* __restrict__ rel_emb, const int* __restrict__ lut,
                                            int max_dist, float* __restrict__ table, int H, int S) {
+    pdl_launch_dependents();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int width = 2 * S - 1;
     if (idx >= H * width) return;
@@ -357,6 +365,7 @@ __global__ void lse_finalize_kernel(const float* __restrict__ lse_max, const flo
                                     const float* __restrict__ label_logit, const int* __restrict__ labels,
                                     float* __restrict__ scores, float* __restrict__ logprobs, int B, int T,
                                     int num_tiles) {
+    pdl_launch_dependents();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;

@@ -146,6 +146,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                        const GemmParams p) {
     using Cfg = GemmConfig<BLOCK_N, CG>;
     static_assert(!epi_is_gated(EPI) || BLOCK_N >= 64, "gated epilogue pairs two >=32-column half tiles");
+    pdl_launch_dependents();
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BLOCK_M = Cfg::BLOCK_M;
     constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -189,6 +190,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above touched only this CTA's shared memory / TMEM; from here on operands of earlier kernels are read
 
     const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int tiles_per_batch = p.num_m_tiles * p.num_n_tiles;
@@ -710,13 +712,15 @@ inline cudaError_t launch_gemm_t(const GemmLaunch& g, int num_sms, cudaStream_t 
     cfg.blockDim = dim3(Cfg::NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = CG;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
 }
 

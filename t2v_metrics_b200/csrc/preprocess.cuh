@@ -159,6 +159,7 @@ template <typename OUT, int LAYOUT>
 __global__ void __launch_bounds__(PRE_THREADS)
 image_preprocess_kernel(const uint8_t* __restrict__ src, const PreImage* __restrict__ images, const int* __restrict__ tables,
                         uchar3 background, float3 mean, float3 stdv, PrePatchGeom geom, OUT* __restrict__ out) {
+    pdl_launch_dependents();
     extern __shared__ uint32_t pre_smem[];
     const PreImage im = images[blockIdx.y];
     const int y0 = blockIdx.x * im.tile_rows;

@@ -1,6 +1,7 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
 // No CUTLASS/CuTe dependency: everything the kernels need is spelled out here.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -60,6 +61,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// Programmatic dependent launch (PDL). Every kernel of the library signals at its very top that its successor may be launched; the GEMM and
+// attention kernels, which are launched with cudaLaunchAttributeProgrammaticStreamSerialization, then run their set-up (barrier init, TMEM
+// allocation, tensor-map prefetch) while the predecessor is still draining and call pdl_wait() -- which returns once the predecessor grid has
+// COMPLETED and its memory is visible -- before they touch global memory. The dependent grid starts only after every CTA of the predecessor has
+// executed the trigger or exited, so it can never starve the predecessor's own CTAs of SM resources.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Off unless VQA_PDL=1: measured on B200 (profiles/r02_small_batch.md) it is worth 1.3 % at one pair per call, 0.8 % at four and nothing at
+// B = 64 (the 200 KB GEMM CTAs cannot become resident before the predecessor's CTAs exit, so only the launch latency overlaps).
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("VQA_PDL"); return v && v[0] == '1'; }();
+    return on;
+}
+
 // the same wait without the hint (plain try_wait loop): A/B switch for the GEMM (-DVQA_GEMM_WAIT_HINT=0), see profiles/r02_gemm_traffic.md
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     asm volatile(

@@ -14,6 +14,7 @@ namespace vqa {
 __global__ void rope_table_kernel(const int* __restrict__ pos, int rows, const int* __restrict__ axis_of_dim,
                                   const float* __restrict__ inv_freq, int half, float* __restrict__ cos_t,
                                   float* __restrict__ sin_t, int round_bf16) {
+    pdl_launch_dependents();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * half) return;
     const int row = idx / half, i = idx % half;
@@ -32,6 +33,7 @@ __global__ void rope_table_kernel(const int* __restrict__ pos, int rows, const i
 __global__ void rope_inplace_kernel(__nv_bfloat16* __restrict__ x, int ld, int col0, int n_heads, int head_stride,
                                     int head_dim, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                     long long rows, int bf16_products) {
+    pdl_launch_dependents();
     const int half = head_dim >> 1;
     const int chunks = half >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,6 +83,7 @@ __global__ void rope_inplace_kernel(__nv_bfloat16* __restrict__ x, int ld, int c
 // merged tokens with group = 1). D % 8 == 0. One block per destination row.
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                    const int* __restrict__ index, int group, int D) {
+    pdl_launch_dependents();
     const size_t r = blockIdx.x;
     const size_t s = (size_t)index[r / group] * group + r % group;
     const uint4* sp = reinterpret_cast<const uint4*>(src + s * D);
@@ -90,6 +93,7 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_b
 
 // fp32 (or bf16) pixel patches -> bf16 (the Conv3d input cast, modeling_qwen2_5_vl.py:112-113)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    pdl_launch_dependents();
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         const float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -104,6 +108,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 __global__ void qwen_embed_kernel(const int* __restrict__ ids, const int* __restrict__ feat_index, const int* __restrict__ seq_lens,
                                   const __nv_bfloat16* __restrict__ embed, const __nv_bfloat16* __restrict__ feats,
                                   __nv_bfloat16* __restrict__ out, int S, int D) {
+    pdl_launch_dependents();
     const int b = blockIdx.x / S, s = blockIdx.x % S;
     const uint4* src = nullptr;
     if (s < seq_lens[b]) {
@@ -118,6 +123,7 @@ __global__ void qwen_embed_kernel(const int* __restrict__ ids, const int* __rest
 // out[b] = x[b*S + seq_len[b] - 1]: the last prompt position, the only one lm_head is applied to (logits_to_keep = 1).
 __global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ seq_lens,
                                         __nv_bfloat16* __restrict__ out, int S, int D) {
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int last = max(seq_lens[b], 1) - 1;
     const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * S + last) * D);
@@ -128,6 +134,7 @@ __global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, con
 // bitmap[b, id / 32] |= 1 << (id % 32) for every prompt id of sample b (the set RepetitionPenaltyLogitsProcessor gathers over).
 __global__ void token_bitmap_kernel(const int* __restrict__ ids, const int* __restrict__ seq_lens, int B, int S, int vocab,
                                     uint32_t* __restrict__ bitmap, int words) {
+    pdl_launch_dependents();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * S) return;
     const int b = idx / S, s = idx % S;
@@ -139,6 +146,7 @@ __global__ void token_bitmap_kernel(const int* __restrict__ ids, const int* __re
 
 // Packed-rows mode (shared vision prefixes): out[b] = x[row[b]], the last prompt position of pair b.
 __global__ void gather_rows_by_index_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ row, __nv_bfloat16* __restrict__ out, int D) {
+    pdl_launch_dependents();
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row[blockIdx.x] * D);
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * D);
     for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = src[i];
@@ -148,6 +156,7 @@ __global__ void gather_rows_by_index_kernel(const __nv_bfloat16* __restrict__ x,
 // grid (ceil(max_prompt_len / 256), B).
 __global__ void token_bitmap_packed_kernel(const int* __restrict__ ids, const int* __restrict__ cu, const int* __restrict__ kv_prefix,
                                            const int* __restrict__ pair_seq, int vocab, uint32_t* __restrict__ bitmap, int words) {
+    pdl_launch_dependents();
     const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sq = pair_seq[b], pre = kv_prefix ? kv_prefix[sq] : -1;
     const int pre_len = pre >= 0 ? cu[pre + 1] - cu[pre] : 0;
@@ -160,6 +169,7 @@ __global__ void token_bitmap_packed_kernel(const int* __restrict__ ids, const in
 
 // prob[b] = exp(logprob[b])
 __global__ void exp_kernel(const float* __restrict__ lp, float* __restrict__ out, int n) {
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = expf(lp[i]);
 }
@@ -171,6 +181,7 @@ constexpr int TOPK_MAX = 8;
 __global__ void __launch_bounds__(256) topk_softmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl, int V, float inv_temp,
                                                            const uint32_t* __restrict__ pen_bitmap, int pen_words, float penalty, int K,
                                                            int* __restrict__ out_ids, float* __restrict__ out_probs) {
+    pdl_launch_dependents();
     __shared__ float s_val[256 * TOPK_MAX];
     __shared__ int s_idx[256 * TOPK_MAX];
     __shared__ float s_red[2][8];

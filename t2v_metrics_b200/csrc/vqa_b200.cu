@@ -167,6 +167,7 @@ static int ssq_parts_for(int variant, int N) {
 // Sum of squares of every row of x (bf16 [rows, D]) into slot 0 of its partial-sum row (the other slots are zero): seeds the fused
 // RMSNorm chain for the encoder's input embeddings. One warp per row.
 __global__ void __launch_bounds__(256) row_ssq_kernel(const bf16* __restrict__ x, float* __restrict__ ssq, int rows, int D, int stride) {
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -250,6 +251,7 @@ static cudaError_t run_gemm_batched(const bf16* A, int lda, const bf16* W, int l
 // and this kernel adds the slices: C = [residual +] bf16(sum_s partial_s + bias) -- the Linear's bf16 output, then the residual add, like EPI_STORE.
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, const bf16* __restrict__ bias,
                                      const bf16* __restrict__ residual, int ldr, bf16* __restrict__ C, int ldc) {
+    pdl_launch_dependents();
     const int nv = N / 8;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)M * nv) return;
@@ -644,6 +646,7 @@ extern "C" size_t vqa_clipt5_workspace_bytes(vqa_handle* h, int32_t batch, int32
 }
 
 __global__ void identity_index_kernel(int* idx, int n) {
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) idx[i] = i;
 }
