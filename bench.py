@@ -208,7 +208,7 @@ def cpu_reference_clipt5(model: str, text_len: int, timed_pairs: int, budget_s: 
                 score_range=[round(min(scores), 6), round(max(scores), 6)], **_stats(times))
 
 
-def cpu_reference_qwen(model: str, timed_pairs: int, budget_s: float, video: bool = False):
+def cpu_reference_qwen(model: str, timed_pairs: int, budget_s: float, video: bool = False, video_size: int = 224):
     """BASELINE config 3 / 5 on the host cores: the real Qwen2_5_VLForConditionalGeneration (fp32, eager) driven exactly like the reference
     drives it -- one sample at a time, generate(max_new_tokens=1, output_scores=True), softmax(scores)[answer]
     (t2v_metrics/models/vqascore_models/qwen2vl_model.py:190-289)."""
@@ -226,7 +226,7 @@ def cpu_reference_qwen(model: str, timed_pairs: int, budget_s: float, video: boo
     m = hf.build_hf_qwen(cfg, sd, dtype=torch.float32, device="cpu", attn="sdpa", fast_construct=True, assign=True)
     del sd
     t_build = time.perf_counter() - t_build
-    hw, frames = ((args.video_size, args.video_size), 8) if video else ((448, 448), 1)
+    hw, frames = ((video_size, video_size), 8) if video else ((448, 448), 1)
 
     def one_pair(seed):
         inp = qo.make_synthetic_inputs(cfg, 1, hw, 64, seed=100 + seed, frames=frames)
@@ -266,7 +266,7 @@ def run_reference(args, rank, world):
         return
     t0 = time.perf_counter()
     if args.model.startswith("qwen"):
-        best = cpu_reference_qwen(args.model, timed_pairs=max(3, min(args.steps, 6)), budget_s=150.0, video=args.video)
+        best = cpu_reference_qwen(args.model, timed_pairs=max(3, min(args.steps, 6)), budget_s=150.0, video=args.video, video_size=args.video_size)
         metric = "VQAScore (video,text) pairs/sec @ qwen2.5-vl-7b, 16x224px" if args.video else "VQAScore (image,text) pairs/sec @ qwen2.5-vl-7b, 448px"
         workload = f"{args.model} VQAScore on the host CPU, one sample per generate() call"
         cfg1 = None
@@ -727,7 +727,7 @@ def run_engine_qwen(args, rank, local_rank, world):
                 line["hf_gpu_baseline"] = dict(value=None, unit="pairs/s", what=f"failed: {e!r}")
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = {k: v for k, v in cpu_reference_qwen(args.model, timed_pairs=3, budget_s=30.0, video=video).items()
+                line["cpu_baseline"] = {k: v for k, v in cpu_reference_qwen(args.model, timed_pairs=3, budget_s=30.0, video=video, video_size=args.video_size).items()
                                         if k != "seconds_per_pair"}
             except Exception as e:  # noqa
                 line["cpu_baseline"] = dict(value=None, unit="pairs/s", cores=host_threads()[0], kind="port", sample=f"failed: {e!r}")

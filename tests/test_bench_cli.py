@@ -43,6 +43,13 @@ def test_reference_arm_qwen_follows_the_reference_loop():
     assert line["impl"] == "reference" and line["value"] > 0 and "generate(max_new_tokens=1" in line["cpu_baseline"]["sample"]
 
 
+def test_reference_arm_qwen_video_shapes():
+    line = _run_reference(["--model", "qwen2.5-vl-7b", "--video"])
+    assert line["impl"] == "reference" and line["value"] > 0 and "video" in line["metric"]
+    line = _run_reference(["--model", "qwen2.5-vl-7b", "--video", "--video-size", "336"])
+    assert line["value"] > 0
+
+
 def test_host_threads_respects_affinity():
     import bench
     phys, logical = bench.host_threads()
