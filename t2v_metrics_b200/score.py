@@ -31,9 +31,10 @@ class Score(nn.Module):
         self.model = self.prepare_scoremodel(model, device, cache_dir, **kwargs)
         self.model_name = model
         self.max_pairs = 64
-        # one process per GPU (torchrun): forward() splits the IMAGES over the ranks so that every image's vision features are computed on
-        # one rank only, and all-gathers the [m, n] score rows. Off: every rank scores everything, like the reference.
-        self.shard_over_images = True
+        # Opt-in for one process per GPU (torchrun) when EVERY rank calls forward() with the SAME images and texts: the IMAGES are split over
+        # the ranks, so that every image's vision features are computed on one rank only, and the [m, n] score rows are all-gathered
+        # (SURVEY 8e). Off (default): every rank scores what it is given, like the reference -- ranks may then hold different data.
+        self.shard_over_images = False
 
     def prepare_scoremodel(self, model: str, device: str, cache_dir: str, **kwargs):
         raise NotImplementedError("Subclasses must implement prepare_scoremodel")

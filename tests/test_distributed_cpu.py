@@ -62,6 +62,7 @@ def _score_worker(rank, world, port, m, n, q):
             return ["fake"]
 
     sc = S("fake", device="cpu")
+    sc.shard_over_images = True
     sc.max_pairs = 4
     images, texts = [f"img{i}" for i in range(m)], [f"t{j}" for j in range(n)]
     got = sc(images=images, texts=texts)
