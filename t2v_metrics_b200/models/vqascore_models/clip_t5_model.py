@@ -149,7 +149,14 @@ class CLIPT5Model(VQAScoreModel):
         pixels = self.load_images(list(uniq.keys()))
         dev = self.engine.device
         image_index = torch.tensor(index, dtype=torch.int32).to(dev, non_blocking=True)
-        run = self.engine.score_tensors_graphed if 0 < len(images) <= self.cuda_graph_max_pairs else self.engine.score_tensors
-        scores = run(pixels, input_ids.to(dev, non_blocking=True), lens.to(dev, non_blocking=True), labels.to(dev, non_blocking=True),
-                     image_index=image_index if len(uniq) != len(images) else None)
-        return scores.float().cpu()
+        args = (pixels, input_ids.to(dev, non_blocking=True), lens.to(dev, non_blocking=True), labels.to(dev, non_blocking=True))
+        kw = dict(image_index=image_index if len(uniq) != len(images) else None)
+        if 0 < len(images) <= self.cuda_graph_max_pairs:
+            try:
+                return self.engine.score_tensors_graphed(*args, **kw).float().cpu()
+            except RuntimeError as e:        # stream capture refused (e.g. another thread is issuing CUDA calls): same kernels, launched directly
+                import warnings
+                warnings.warn(f"CUDA-graph capture failed ({e}); small calls will be launched directly from now on")
+                self.cuda_graph_max_pairs = 0
+                torch.cuda.synchronize(dev)
+        return self.engine.score_tensors(*args, **kw).float().cpu()
